@@ -1,0 +1,179 @@
+/*
+ * lc2is_b200.h - C ABI of the B200-native LC2IS segmentation-head hot path.
+ *
+ * The reference (AntoineBlanot/LC2IS) is pure Python: it has no FFI / plugin registry.
+ * Each entry point below replaces a group of reference *lines* (cited per function, paths
+ * relative to the reference root) and is what a ctypes binding on the reference side calls
+ * (see INTEGRATION.md).  Conventions, all entry points:
+ *
+ *   - return 0 on success, non-zero on error (negative = argument error, positive =
+ *     cudaError_t); no exception crosses the boundary; lc2is_last_error() returns text
+ *     (thread-local).
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; the library never
+ *     allocates or frees device memory and never synchronises the host (except the
+ *     *_host entry points, documented there).  Work is enqueued on `stream` only, so every
+ *     call is CUDA-graph capturable.
+ *   - accumulated outputs (confmat, per_image, loss_sum, n_valid, grad_t) are ADDED to:
+ *     the caller zeroes them (lets several batches / ranks accumulate into one buffer).
+ *   - tensors are dense row-major with the shapes given; int64 = long long.
+ *   - there is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef LC2IS_B200_H
+#define LC2IS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* lc2is_stream_t;                 /* cudaStream_t */
+
+enum { LC2IS_F32 = 0, LC2IS_BF16 = 1 };        /* dtype codes            */
+enum { LC2IS_BILINEAR = 0, LC2IS_BICUBIC = 1 }; /* upsample modes         */
+
+#define LC2IS_ERR_ARG      (-1)
+#define LC2IS_ERR_SHAPE    (-2)
+#define LC2IS_ERR_NODEVICE (-3)
+#define LC2IS_ERR_UNSUPPORTED (-4)
+
+const char* lc2is_last_error(void);
+int         lc2is_abi_version(void);
+/* number of kernels this library has launched in this process (bench `gpu_launches`) */
+int64_t     lc2is_launch_count(void);
+
+/* Round C up to the class padding the tensor-core kernels use (multiple of 16). */
+int lc2is_class_pad(int C);
+
+/* ---------------------------------------------------------------------------------------
+ * K0  proto_normalize.   Replaces  t = F.normalize(t, dim=2, p=2)   model/final.py:42
+ *     (and :80,:142,:204,:267,:279,:342,:354; model/new.py:67; model/ftn.py:58).
+ * d_t      [n_sets, C, D] fp32 text embeddings (n_sets = 1 shared, or B per-image prompts,
+ *          final.py:129-130).
+ * d_t_hat  [n_sets, C_pad, D] bf16 out: t / max(||t||, 1e-12) (or t itself if !normalize),
+ *          rows C..C_pad-1 zero.  C_pad = lc2is_class_pad(C).
+ * d_inv_norm [n_sets, C] fp32 out: 1 / max(||t||, 1e-12) (1.0 if !normalize).
+ */
+int lc2is_proto_normalize(const float* d_t, int n_sets, int C, int D, int normalize,
+                          void* d_t_hat, float* d_inv_norm, lc2is_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  cosine_logits_fwd.  Replaces
+ *       v = F.normalize(v, dim=1, p=2); score = einsum('bchw,bkc->bkhw', v, t)
+ *       model/final.py:41,43  (normalize=1)      and
+ *       matmul(feature_v, feature_t.T) + rearrange       model/model.py:50,53 (normalize=0)
+ * d_v        [B, hw, D] patch embeddings, v_dtype LC2IS_F32 or LC2IS_BF16.  D % 64 == 0.
+ * d_t_hat    [n_sets, C_pad, D] bf16 from K0.
+ * d_v_hat    [B*hw, D] bf16 out/workspace: normalised (or plain) patch rows as fed to the
+ *            tensor cores; kept for the backward.
+ * d_inv_norm_v [B*hw] fp32 out: 1/max(||v||,1e-12) (1.0 if !normalize).
+ * d_logits   [B, C, hw] fp32 out (class-plane major = the reference's 'b k h w'):
+ *            logit_scale * <v_hat, t_hat>.  bf16 operands, fp32 accumulate (tcgen05/TMEM).
+ */
+int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int hw, int D,
+                            const void* d_t_hat, int n_sets, int C,
+                            int normalize, float logit_scale,
+                            void* d_v_hat, float* d_inv_norm_v, float* d_logits,
+                            lc2is_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K1b cosine_logits_bwd.  Replaces autograd of the K1 lines (loss.backward(), engine.py:100).
+ * d_grad_logits_bf16 [B, C_pad, hw] bf16: dL/dlogits (rows C..C_pad-1 zero) - produced by K2
+ *            (or lc2is_grad_to_bf16).
+ * d_logits   [B, C, hw] fp32 from K1 (used for the normalise-backward projection
+ *            v_hat . dV_hat = sum_c G_c * logits_c).
+ * d_grad_scale: optional DEVICE fp32 scalar multiplied into every gradient (the upstream
+ *            grad_output, e.g. 0.4 for the aux loss, engine.py:98); NULL = 1.
+ * d_grad_v   [B*hw, D] out, gv_dtype LC2IS_F32 or LC2IS_BF16 (overwritten).
+ * d_grad_t   [n_sets, C, D] fp32, ACCUMULATED (zero it first): gradient w.r.t. the raw
+ *            (un-normalised) text embeddings.
+ * d_ws       workspace, lc2is_cosine_logits_bwd_workspace(...) bytes.
+ */
+int64_t lc2is_cosine_logits_bwd_workspace(int B, int hw, int D, int n_sets, int C);
+int lc2is_cosine_logits_bwd(const void* d_grad_logits_bf16, const float* d_logits,
+                            const void* d_v_hat, const float* d_inv_norm_v,
+                            const void* d_t_hat, const float* d_inv_norm_t,
+                            int B, int hw, int D, int n_sets, int C,
+                            int normalize, float logit_scale, const float* d_grad_scale,
+                            void* d_grad_v, int gv_dtype, float* d_grad_t,
+                            void* d_ws, lc2is_stream_t stream);
+
+/* fp32 [B,C,hw] -> bf16 [B,C_pad,hw] (zero pad rows); for callers whose dL/dlogits did not
+ * come from K2. */
+int lc2is_grad_to_bf16(const float* d_grad, int B, int C, int hw, void* d_grad_bf16,
+                       lc2is_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K2  upsample + softmax cross-entropy, forward and backward in one pass.  Replaces
+ *       input = F.interpolate(input, mode="bilinear", size=H); CrossEntropyLoss(input,target)
+ *       model/loss.py:19-20 (AuxiliaryLoss)  and  final.py:44 + engine.py:94 (criterion),
+ *       plus their autograd backward (engine.py:100).
+ * lc2is_count_valid: n_valid += #{labels != ignore_index} (the 'mean' denominator).
+ * d_low      [B, C, h, w] fp32 low-resolution logits.
+ * d_labels   [B, H, W] int64, values in [0,C) or ignore_index.
+ * d_grad_scale DEVICE fp32 scalar g: gradients are g * (softmax - onehot) scattered through
+ *            the bilinear taps (pass 1/n_valid for reduction='mean'); NULL = 1.
+ * d_loss_sum DEVICE double, ACCUMULATED: sum over valid pixels of -log softmax[target].
+ * d_grad_low [B, C, h, w] fp32 out (overwritten) or NULL.
+ * d_grad_low_bf16 [B, C_pad, h*w] bf16 out (overwritten, pad rows zeroed) or NULL.
+ * The upsampled [B,C,H,W] tensor never exists in memory.
+ */
+int lc2is_count_valid(const int64_t* d_labels, int64_t n, int64_t ignore_index,
+                      int64_t* d_n_valid, lc2is_stream_t stream);
+/* *d_scale = mult / *d_n_valid (0 if no valid pixel): the 'mean' gradient scale, no host sync. */
+int lc2is_mean_scale(const int64_t* d_n_valid, float mult, float* d_scale, lc2is_stream_t stream);
+/* *d_loss = *d_loss_sum / *d_n_valid  (NaN when nothing is valid, like torch). */
+int lc2is_finalize_loss(const double* d_loss_sum, const int64_t* d_n_valid, float* d_loss,
+                        lc2is_stream_t stream);
+int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_labels,
+                              int B, int C, int h, int w, int H, int W,
+                              int64_t ignore_index, const float* d_grad_scale,
+                              double* d_loss_sum, float* d_grad_low, void* d_grad_low_bf16,
+                              lc2is_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  argmax + confusion matrix.  Replaces, per image,
+ *       F.interpolate(bicubic) + nn.Softmax2d + JaccardIndex (argmax + bincount)
+ *       metrics.py:84-92 (compute_mIOU), :63-69 (compute_gt_mIOU), :127-134
+ *       (compute_mIOU_tensor), utils.py:15-22 (generate_masks).
+ * lc2is_argmax_confmat        : logits already at mask resolution [N,C,H,W] (fp32/bf16).
+ * lc2is_argmax_confmat_lowres : logits at [N,C,h,w]; bilinear / bicubic (A=-0.75,
+ *                               align_corners=False) resize to H x W done in registers.
+ * d_labels   [N, lh, lw] int64; H % lh == 0 and W % lw == 0: nearest-upsampled in-kernel
+ *            (metrics.py:90).  Targets outside [0,C) are skipped.
+ * d_confmat  [C, C] int64 ACCUMULATED, rows = target, cols = prediction (all rows kept: the
+ *            host zeroes the ignore row where the reference does).
+ * d_per_image [N, 3, C] int64 ACCUMULATED or NULL: per image (true-positive, target count,
+ *            prediction count) per class - enough for metrics.py:91-97's per-image IoU.
+ * d_pred     [N, H, W] int64 out or NULL: the argmax masks (first index wins ties).
+ */
+int lc2is_argmax_confmat(const void* d_logits, int dtype, int N, int C, int H, int W,
+                         const int64_t* d_labels, int lh, int lw,
+                         int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                         lc2is_stream_t stream);
+int lc2is_argmax_confmat_lowres(const float* d_low, int N, int C, int h, int w, int H, int W,
+                                int mode, const int64_t* d_labels, int lh, int lw,
+                                int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                                lc2is_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Whole step from HOST buffers (the end-to-end path bench.py times as `e2e`).  Replaces one
+ * iteration of Engine.train_loop / eval_loop over the head (engine.py:75-101,145-163):
+ * H2D of the batch, K0..K3, D2H of loss / n_valid / confusion matrix.  Synchronises
+ * `stream` before returning.  Host pointers should be pinned.
+ * h_v [B,hw,D] bf16, h_t [C,D] fp32, h_labels [B,H,W] int64.
+ * h_out_loss (mean CE), h_out_n_valid, h_out_confmat [C,C] (overwritten).
+ * d_ws: device workspace of lc2is_head_step_workspace(...) bytes (caller-allocated).
+ * do_backward: also run K1b (gradients stay on the device, in the workspace).
+ */
+int64_t lc2is_head_step_workspace(int B, int hw, int D, int C, int H, int W);
+int lc2is_head_step_host(const void* h_v, const float* h_t, const int64_t* h_labels,
+                         int B, int h, int w, int D, int C, int H, int W,
+                         int64_t ignore_index, float logit_scale, int do_backward,
+                         float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
+                         void* d_ws, lc2is_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LC2IS_B200_H */

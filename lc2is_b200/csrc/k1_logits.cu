@@ -1,0 +1,342 @@
+// K0 proto_normalize, K1a patch-row normalise, K1 cosine-logits GEMM (tcgen05 + TMEM + TMA).
+//
+// Replaces reference model/final.py:41-43:
+//     v = F.normalize(v, dim=1, p=2); t = F.normalize(t, dim=2, p=2)
+//     score_map = torch.einsum('bchw,bkc->bkhw', v, t)
+// (and the un-normalised matmul of model/model.py:50,53).
+//
+// GEMM view: logits[b, c, p] = scale * sum_d Vhat[b*hw + p, d] * That[c, d]
+//   A = Vhat  [B*hw, D]   bf16, K-major, 128-row tiles          (TMA, 128B swizzle)
+//   B = That  [C_pad, D]  bf16, K-major, NB <= 256 row tiles    (TMA, 128B swizzle)
+//   D = 128 x NB fp32 accumulator in TMEM, two buffers (2 x 256 columns) so the epilogue of
+//       tile i overlaps the loads + MMAs of tile i+1.
+// Persistent CTAs (one per SM), 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (one
+// elected thread) + TMEM owner, warps 2..5 = epilogue.  The epilogue writes class-plane major
+// [B, C, hw]: TMEM lane = pixel, so for a fixed class the 32 lanes of a warp store 128
+// contiguous bytes.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace lc2is {
+
+// ---------------------------------------------------------------------------------------------
+// One warp per row: out = bf16(x / max(||x||, 1e-12)) (or bf16(x)), inv_norm = 1/max(||x||,eps).
+// rows_out >= rows_in: extra rows (class padding) are zero-filled.  pad_group: rows_in rows are
+// grouped as [n_sets][rows_per_set] and written to [n_sets][rows_per_set_pad].
+template <typename T>
+__global__ void __launch_bounds__(256)
+rownorm_kernel(const T* __restrict__ x, long long n_sets, int rows_per_set, int rows_per_set_pad, int D,
+               int normalize, __nv_bfloat16* __restrict__ out, float* __restrict__ inv_norm) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = n_sets * rows_per_set_pad;
+    for (long long r = warp; r < total; r += nwarps) {
+        const long long set = r / rows_per_set_pad;
+        const int row = (int)(r - set * rows_per_set_pad);
+        __nv_bfloat16* o = out + (size_t)r * D;
+        if (row >= rows_per_set) {
+            for (int d = lane * 8; d < D; d += 256) *reinterpret_cast<uint4*>(o + d) = make_uint4(0, 0, 0, 0);
+            continue;
+        }
+        const T* xi = x + ((size_t)set * rows_per_set + row) * D;
+        float ss = 0.f;
+        // 8 elements per lane per step (D % 8 == 0)
+        for (int d = lane * 8; d < D; d += 256) {
+            float v[8];
+            if constexpr (sizeof(T) == 4) {
+                float4 a = __ldg(reinterpret_cast<const float4*>(xi + d));
+                float4 b = __ldg(reinterpret_cast<const float4*>(xi + d) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+                uint4 a = __ldg(reinterpret_cast<const uint4*>(xi + d));
+                unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[2 * i] = __uint_as_float(w[i] << 16);
+                    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
+        }
+        ss = warp_sum(ss);
+        const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+        if (lane == 0 && inv_norm) inv_norm[(size_t)set * rows_per_set + row] = 1.f / denom;
+        for (int d = lane * 8; d < D; d += 256) {
+            float v[8];
+            if constexpr (sizeof(T) == 4) {
+                float4 a = __ldg(reinterpret_cast<const float4*>(xi + d));
+                float4 b = __ldg(reinterpret_cast<const float4*>(xi + d) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+                uint4 a = __ldg(reinterpret_cast<const uint4*>(xi + d));
+                unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[2 * i] = __uint_as_float(w[i] << 16);
+                    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+                }
+            }
+            __nv_bfloat162 p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                p[i] = __floats2bfloat162_rn(normalize ? v[2 * i] / denom : v[2 * i],
+                                             normalize ? v[2 * i + 1] / denom : v[2 * i + 1]);
+            *reinterpret_cast<uint4*>(o + d) = *reinterpret_cast<uint4*>(p);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+constexpr int K1_THREADS = 192;
+constexpr int K1_BM = 128;
+constexpr int K1_BK = 64;                 // 64 bf16 = 128 B = one swizzle row
+constexpr int K1_A_BYTES = K1_BM * K1_BK * 2;
+constexpr int K1_MAX_STAGES = 8;
+
+struct K1Params {
+    float* out;            // [B, C, hw]
+    int B, hw, C, C_pad, n_sets;
+    int NB, n_ntiles, tiles_per_img, num_kb, stages;
+    float scale;
+};
+
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const K1Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base_u32 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base_u32 - tc::smem_u32(smem_raw));
+    const int stage_bytes = K1_A_BYTES + P.NB * 128;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+    uint64_t* empty = full + K1_MAX_STAGES;
+    uint64_t* tfull = empty + K1_MAX_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = P.B * P.tiles_per_img * P.n_ntiles;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmA);
+        tc::prefetch_tmap(&tmB);
+        for (int i = 0; i < P.stages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % P.n_ntiles, mt = tile / P.n_ntiles;
+                const int b = mt / P.tiles_per_img, ti = mt - b * P.tiles_per_img;
+                const int arow = b * P.hw + ti * K1_BM;
+                const int brow = (P.n_sets > 1 ? b : 0) * P.C_pad + nt * P.NB;
+                for (int kb = 0; kb < P.num_kb; ++kb) {
+                    tc::mbar_wait(empty + stage, phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    tc::mbar_arrive_expect_tx(full + stage, (uint32_t)stage_bytes);
+                    tc::tma_load_2d(sa, &tmA, full + stage, kb * K1_BK, arow);
+                    tc::tma_load_2d(sa + K1_A_BYTES, &tmB, full + stage, kb * K1_BK, brow);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(K1_BM, P.NB, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t bphase = (it >> 1) & 1;
+                tc::mbar_wait(tempty + buf, bphase ^ 1);       // epilogue drained this buffer
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kb = 0; kb < P.num_kb; ++kb) {
+                    tc::mbar_wait(full + stage, phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = base_u32 + stage * stage_bytes;
+                    const uint64_t adesc = tc::make_smem_desc(sa, 16, 1024);
+                    const uint64_t bdesc = tc::make_smem_desc(sa + K1_A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < K1_BK / 16; ++k)
+                        tc::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    tc::umma_commit(empty + stage);             // frees the smem slot when the MMAs retire
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(tfull + buf);                   // accumulator ready
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> global (class-plane major) =====
+        const int q = warp & 3;                                 // TMEM lane quarter this warp may read
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t bphase = (it >> 1) & 1;
+            const int nt = tile % P.n_ntiles, mt = tile / P.n_ntiles;
+            const int b = mt / P.tiles_per_img, ti = mt - b * P.tiles_per_img;
+            const int p = ti * K1_BM + q * 32 + lane;
+            const bool rvalid = p < P.hw;
+            float* orow = P.out + (size_t)b * P.C * P.hw + p;
+            tc::mbar_wait(tfull + buf, bphase);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+            const int n0 = nt * P.NB;
+            for (int col = 0; col < P.NB; col += 16) {
+                if (n0 + col >= P.C) break;                     // warp-uniform
+                uint32_t r[16];
+                tc::tmem_ld16(taddr + col, r);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = n0 + col + j;
+                    if (rvalid && c < P.C) __stcs(orow + (size_t)c * P.hw, __uint_as_float(r[j]) * P.scale);
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tempty + buf);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                      uint32_t box_cols) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(LC2IS_ERR_NODEVICE, "cuTensorMapEncodeTiled entry point unavailable%s");
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LC2IS_ERR_ARG, "cuTensorMapEncodeTiled(2d) failed: %s%lld", "CUresult ", (long long)r);
+    return 0;
+}
+
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d2, uint64_t d1, uint64_t d0, uint32_t box1,
+                      uint32_t box0) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(LC2IS_ERR_NODEVICE, "cuTensorMapEncodeTiled entry point unavailable%s");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+    cuuint32_t box[3] = {box0, box1, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LC2IS_ERR_ARG, "cuTensorMapEncodeTiled(3d) failed: %s%lld", "CUresult ", (long long)r);
+    return 0;
+}
+
+template <typename T>
+static int launch_rownorm(const T* x, long long n_sets, int rows, int rows_pad, int D, int normalize,
+                          __nv_bfloat16* out, float* inv, cudaStream_t st) {
+    long long total = n_sets * rows_pad;
+    long long blocks = (total + 7) / 8;
+    long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    rownorm_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(x, n_sets, rows, rows_pad, D, normalize, out, inv);
+    return 0;
+}
+
+}  // namespace lc2is
+
+using namespace lc2is;
+
+extern "C" int lc2is_class_pad(int C) { return class_pad(C); }
+
+extern "C" int lc2is_proto_normalize(const float* d_t, int n_sets, int C, int D, int normalize,
+                                     void* d_t_hat, float* d_inv_norm, lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (!d_t || !d_t_hat) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (n_sets <= 0 || C <= 0 || D <= 0 || D % 8) return fail(LC2IS_ERR_SHAPE, "need n_sets,C > 0 and D %% 8 == 0%s");
+    launch_rownorm<float>(d_t, n_sets, C, class_pad(C), D, normalize, (__nv_bfloat16*)d_t_hat, d_inv_norm,
+                          (cudaStream_t)stream);
+    LC2IS_CHECK_LAUNCH("rownorm_kernel(t)");
+    return 0;
+}
+
+extern "C" int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int hw, int D,
+                                       const void* d_t_hat, int n_sets, int C,
+                                       int normalize, float logit_scale,
+                                       void* d_v_hat, float* d_inv_norm_v, float* d_logits,
+                                       lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (!d_v || !d_t_hat || !d_v_hat || !d_logits) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (B < 0 || hw <= 0 || C <= 0 || D <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (D % K1_BK) return fail(LC2IS_ERR_SHAPE, "D must be a multiple of 64 (got %s%lld)", "", D);
+    if (n_sets != 1 && n_sets != B) return fail(LC2IS_ERR_SHAPE, "n_sets must be 1 or B%s");
+    if (((uintptr_t)d_v_hat | (uintptr_t)d_t_hat | (uintptr_t)d_v) % 16) return fail(LC2IS_ERR_ARG, "pointers must be 16-byte aligned%s");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long M = (long long)B * hw;
+    // ---- K1a: normalise rows, round to bf16 -------------------------------------------------------
+    if (v_dtype == LC2IS_F32)
+        launch_rownorm<float>((const float*)d_v, 1, (int)M, (int)M, D, normalize, (__nv_bfloat16*)d_v_hat, d_inv_norm_v, st);
+    else if (v_dtype == LC2IS_BF16)
+        launch_rownorm<__nv_bfloat16>((const __nv_bfloat16*)d_v, 1, (int)M, (int)M, D, normalize, (__nv_bfloat16*)d_v_hat, d_inv_norm_v, st);
+    else
+        return fail(LC2IS_ERR_ARG, "v_dtype must be LC2IS_F32 or LC2IS_BF16%s");
+    LC2IS_CHECK_LAUNCH("rownorm_kernel(v)");
+
+    // ---- K1: GEMM ------------------------------------------------------------------------------------
+    K1Params P;
+    P.out = d_logits; P.B = B; P.hw = hw; P.C = C; P.C_pad = class_pad(C); P.n_sets = n_sets;
+    const int n_ntiles0 = (P.C_pad + 255) / 256;
+    P.NB = ((P.C_pad + n_ntiles0 - 1) / n_ntiles0 + 15) / 16 * 16;
+    P.n_ntiles = (P.C_pad + P.NB - 1) / P.NB;
+    P.tiles_per_img = (hw + K1_BM - 1) / K1_BM;
+    P.num_kb = D / K1_BK;
+    P.scale = logit_scale;
+    const int stage_bytes = K1_A_BYTES + P.NB * 128;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > K1_MAX_STAGES) stages = K1_MAX_STAGES;
+    if (stages > P.num_kb * 2) stages = P.num_kb * 2;
+    if (stages < 2) stages = 2;
+    P.stages = stages;
+    size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: it owns all 512 TMEM columns
+    CUtensorMap tmA, tmB;
+    if (int e = make_tmap_2d_bf16(&tmA, d_v_hat, (uint64_t)M, (uint64_t)D, K1_BM, K1_BK)) return e;
+    if (int e = make_tmap_2d_bf16(&tmB, d_t_hat, (uint64_t)n_sets * P.C_pad, (uint64_t)D, P.NB, K1_BK)) return e;
+    LC2IS_CUDA(cudaFuncSetAttribute(k1_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int total_tiles = B * P.tiles_per_img * P.n_ntiles;
+    int grid = sm_count();
+    if (grid > total_tiles) grid = total_tiles;
+    k1_logits_kernel<<<grid, K1_THREADS, smem, st>>>(tmA, tmB, P);
+    LC2IS_CHECK_LAUNCH("k1_logits_kernel");
+    return 0;
+}

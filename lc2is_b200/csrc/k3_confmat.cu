@@ -1,0 +1,510 @@
+// K3: per-pixel argmax + confusion matrix (int64, rows = target, cols = prediction).
+//
+// Replaces reference metrics.py:84-92 / :63-69 / :127-134 and utils.py:15-22:
+//   F.interpolate(bicubic|bilinear) -> Softmax2d -> JaccardIndex (argmax + bincount).
+// softmax is strictly monotone, so the argmax is taken on the logits (first index wins ties,
+// like torch.argmax); NaN / +inf anywhere in a pixel's class vector gives class 0, which is
+// what argmax(softmax(x)) returns for an all-NaN row.
+//
+// Three kernels:
+//   k3_full    - logits materialised at mask resolution.  HBM-bound stream: 128-bit loads,
+//                8 classes in flight per thread, C x C int32 histogram privatised in shared
+//                memory (warp-aggregated with match.any), flushed with int64 global atomics.
+//   k3_low_fast- logits at low resolution, power-of-two scale >= 4: each thread owns a 4x4
+//                pixel block that shares one set of bilinear (2x2) / bicubic (4x4) taps.
+//   k3_low_gen - any output size (compute_gt_mIOU's per-image original sizes): 1 pixel/thread.
+#include "common.cuh"
+
+namespace lc2is {
+
+constexpr int K3_THREADS = 256;
+constexpr int K3_SMEM_HIST_MAX_C = 224;   // 224*224*4 = 200,704 B
+
+struct ArgmaxState {
+    float best;
+    int idx;
+    bool bad;
+};
+__device__ __forceinline__ void am_init(ArgmaxState& s) { s.best = -INFINITY; s.idx = 0; s.bad = false; }
+__device__ __forceinline__ void am_update(ArgmaxState& s, float v, int c) {
+    s.bad |= !(v < INFINITY);                 // NaN or +inf
+    if (v > s.best) { s.best = v; s.idx = c; }
+}
+__device__ __forceinline__ int am_result(const ArgmaxState& s) { return s.bad ? 0 : s.idx; }
+
+// Add one (target, pred) observation.  Shared histogram when hist != nullptr, else global.
+__device__ __forceinline__ void hist_add(int* hist, unsigned long long* confmat,
+                                         unsigned long long* per_img, int C, bool valid, int t, int p) {
+    unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) return;
+    int key = t * C + p;
+    unsigned m = __match_any_sync(act, key);
+    int leader = __ffs(m) - 1;
+    if ((int)(threadIdx.x & 31) == leader) {
+        int cnt = __popc(m);
+        if (hist) {
+            atomicAdd(&hist[key], cnt);
+        } else {
+            atomicAdd(&confmat[key], (unsigned long long)cnt);
+            if (per_img) {
+                if (t == p) atomicAdd(&per_img[t], (unsigned long long)cnt);
+                atomicAdd(&per_img[C + t], (unsigned long long)cnt);
+                atomicAdd(&per_img[2 * C + p], (unsigned long long)cnt);
+            }
+        }
+    }
+}
+
+// Flush the shared histogram of ONE image into the global matrix / per-image stats and zero it.
+__device__ __forceinline__ void hist_flush(int* hist, unsigned long long* confmat,
+                                           unsigned long long* per_img, int C) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+        int v = hist[i];
+        if (v) {
+            hist[i] = 0;
+            atomicAdd(&confmat[i], (unsigned long long)v);
+            if (per_img) {
+                int t = i / C, p = i - t * C;
+                if (t == p) atomicAdd(&per_img[t], (unsigned long long)v);
+                atomicAdd(&per_img[C + t], (unsigned long long)v);
+                atomicAdd(&per_img[2 * C + p], (unsigned long long)v);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+    static constexpr int PIX = 4;
+    using V = float4;
+    __device__ static __forceinline__ void load(const float* p, float (&o)[4]) {
+        float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    __device__ static __forceinline__ float load1(const float* p) { return __ldcs(p); }
+};
+template <> struct Vec<__nv_bfloat16> {
+    static constexpr int PIX = 8;
+    __device__ static __forceinline__ void load(const __nv_bfloat16* p, float (&o)[8]) {
+        uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+        unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            o[2 * i] = __uint_as_float(w[i] << 16);
+            o[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ static __forceinline__ float load1(const __nv_bfloat16* p) {
+        return __bfloat162float(*p);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// k3_full: grid-stride over (image, chunk) items, contiguous range per CTA.
+// VEC: vector path (HW % PIX == 0) or scalar path.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(K3_THREADS)
+k3_full_kernel(const T* __restrict__ logits, int N, int C, int H, int W,
+               const long long* __restrict__ labels, int lh, int lw,
+               unsigned long long* __restrict__ confmat, unsigned long long* __restrict__ per_image,
+               long long* __restrict__ pred_out, int use_smem_hist) {
+    extern __shared__ int hist_smem[];
+    int* hist = use_smem_hist ? hist_smem : nullptr;
+    constexpr int PIX = VEC ? Vec<T>::PIX : 1;
+    constexpr int U = 8;
+    const long long HW = (long long)H * W;
+    const int chunk = K3_THREADS * PIX;
+    const int chunks_per_img = (int)((HW + chunk - 1) / chunk);
+    const long long items = (long long)N * chunks_per_img;
+    const long long per_cta = (items + gridDim.x - 1) / gridDim.x;
+    const long long it0 = (long long)blockIdx.x * per_cta;
+    const long long it1 = it0 + per_cta < items ? it0 + per_cta : items;
+    const int ry = H / lh, rx = W / lw;
+
+    if (hist) {
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+    }
+    int cur_img = -1;
+    for (long long it = it0; it < it1; ++it) {
+        const int n = (int)(it / chunks_per_img);
+        const int k = (int)(it - (long long)n * chunks_per_img);
+        if (n != cur_img) {
+            if (hist && cur_img >= 0)
+                hist_flush(hist, confmat, per_image ? per_image + (size_t)cur_img * 3 * C : nullptr, C);
+            cur_img = n;
+        }
+        const long long p0 = (long long)k * chunk + (long long)threadIdx.x * PIX;
+        const bool in = p0 < HW;
+        ArgmaxState st[PIX];
+#pragma unroll
+        for (int j = 0; j < PIX; ++j) am_init(st[j]);
+        if (in) {
+            const T* base = logits + (size_t)n * C * HW + p0;
+            int c0 = 0;
+            for (; c0 + U <= C; c0 += U) {
+                float v[U][PIX];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if constexpr (VEC) Vec<T>::load(base + (size_t)(c0 + u) * HW, v[u]);
+                    else v[u][0] = Vec<T>::load1(base + (size_t)(c0 + u) * HW);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < PIX; ++j) am_update(st[j], v[u][j], c0 + u);
+            }
+            for (; c0 < C; ++c0) {
+                float v[PIX];
+                if constexpr (VEC) Vec<T>::load(base + (size_t)c0 * HW, v);
+                else v[0] = Vec<T>::load1(base + (size_t)c0 * HW);
+#pragma unroll
+                for (int j = 0; j < PIX; ++j) am_update(st[j], v[j], c0);
+            }
+        }
+        unsigned long long* pimg = per_image ? per_image + (size_t)n * 3 * C : nullptr;
+#pragma unroll
+        for (int j = 0; j < PIX; ++j) {
+            const long long p = p0 + j;
+            bool valid = in && p < HW;
+            int t = 0, pr = am_result(st[j]);
+            if (valid) {
+                int y = (int)(p / W), x = (int)(p - (long long)y * W);
+                long long tl = labels[((size_t)n * lh + y / ry) * lw + x / rx];
+                if (pred_out) pred_out[(size_t)n * HW + p] = pr;
+                valid = tl >= 0 && tl < C;
+                t = (int)tl;
+            }
+            hist_add(hist, confmat, pimg, C, valid, t, pr);
+        }
+    }
+    if (hist && cur_img >= 0)
+        hist_flush(hist, confmat, per_image ? per_image + (size_t)cur_img * 3 * C : nullptr, C);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Interpolation weights (torch ATen/native/UpSample.h).
+// bicubic: A = -0.75, src = scale*(dst+0.5)-0.5 NOT clamped, taps floor(src)-1..+2 index-clamped
+// (UpSample.h:398-438, upsample_get_value_bounded).  bilinear: src clamped to >= 0
+// (UpSample.h:289-312), taps idx0, min(idx0+1, in-1).
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+    const float A = -0.75f;
+    c[0] = cubic2(t + 1.f, A);
+    c[1] = cubic1(t, A);
+    c[2] = cubic1(1.f - t, A);
+    c[3] = cubic2(2.f - t, A);
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ---------------------------------------------------------------------------------------------
+// k3_low_fast: one thread = one 4x4 pixel block sharing its taps.  CTA = 16x16 blocks of one
+// image (64x64 px).  grid = (ceil(nbx/16), ceil(nby/16), N).
+template <int MODE>   // 0 bilinear, 1 bicubic
+__global__ void __launch_bounds__(K3_THREADS)
+k3_low_fast_kernel(const float* __restrict__ low, int C, int h, int w, int H, int W,
+                   int s, int off, int nby, int nbx, float rs,
+                   const long long* __restrict__ labels, int lh, int lw,
+                   unsigned long long* __restrict__ confmat, unsigned long long* __restrict__ per_image,
+                   long long* __restrict__ pred_out, int use_smem_hist) {
+    extern __shared__ int hist_smem[];
+    int* hist = use_smem_hist ? hist_smem : nullptr;
+    const int n = blockIdx.z;
+    if (hist) {
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+    }
+    const int bx = blockIdx.x * 16 + (threadIdx.x & 15);
+    const int by = blockIdx.y * 16 + (threadIdx.x >> 4);
+    const bool active = bx < nbx && by < nby;
+    const int y0 = 4 * by - off, x0 = 4 * bx - off;
+    constexpr int NT = MODE == 0 ? 2 : 4;
+    ArgmaxState st[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) am_init(st[j]);
+
+    if (active) {
+        // shared tap indices: floor(src) is the same for the 4 rows / 4 cols of the block
+        const int yc = y0 < 0 ? 0 : y0, xc = x0 < 0 ? 0 : x0;        // any in-range pixel of the block
+        const int ky = (int)floorf(((float)yc + 0.5f) * rs - 0.5f);
+        const int kx = (int)floorf(((float)xc + 0.5f) * rs - 0.5f);
+        int iy[NT], ix[NT];
+        float wy[4][NT], wx[4][NT];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float sy = ((float)(y0 + i) + 0.5f) * rs - 0.5f;
+            float sx = ((float)(x0 + i) + 0.5f) * rs - 0.5f;
+            if (MODE == 0) {
+                // bilinear: clamp src at 0 -> lambda 0 at the top/left border
+                float ty = sy < 0.f ? 0.f : sy - (float)ky;
+                float tx = sx < 0.f ? 0.f : sx - (float)kx;
+                if (sy < 0.f) ty = (ky < 0) ? 1.f : 0.f;   // taps (clamp(-1)=0, 0): either weight picks row 0
+                if (sx < 0.f) tx = (kx < 0) ? 1.f : 0.f;
+                wy[i][0] = 1.f - ty; wy[i][1] = ty;
+                wx[i][0] = 1.f - tx; wx[i][1] = tx;
+            } else {
+                float cy[4], cx[4];
+                cubic_coeffs(sy - (float)ky, cy);
+                cubic_coeffs(sx - (float)kx, cx);
+#pragma unroll
+                for (int t = 0; t < NT; ++t) { wy[i][t] = cy[t]; wx[i][t] = cx[t]; }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            int o = MODE == 0 ? t : t - 1;
+            iy[t] = clampi(ky + o, 0, h - 1);
+            ix[t] = clampi(kx + o, 0, w - 1);
+        }
+        const float* base = low + (size_t)n * C * h * w;
+        for (int c = 0; c < C; ++c) {
+            const float* pc = base + (size_t)c * h * w;
+            float tap[NT][NT];
+#pragma unroll
+            for (int a = 0; a < NT; ++a)
+#pragma unroll
+                for (int b = 0; b < NT; ++b) tap[a][b] = __ldg(pc + iy[a] * w + ix[b]);
+            // horizontal interpolation of every tap row at the 4 output columns
+            float hrow[NT][4];
+#pragma unroll
+            for (int a = 0; a < NT; ++a)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float acc = tap[a][0] * wx[j][0];
+#pragma unroll
+                    for (int b = 1; b < NT; ++b) acc = fmaf(tap[a][b], wx[j][b], acc);
+                    hrow[a][j] = acc;
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float acc = hrow[0][j] * wy[i][0];
+#pragma unroll
+                    for (int a = 1; a < NT; ++a) acc = fmaf(hrow[a][j], wy[i][a], acc);
+                    am_update(st[i * 4 + j], acc, c);
+                }
+        }
+    }
+    const int ry = H / lh, rx = W / lw;
+    unsigned long long* pimg = per_image ? per_image + (size_t)n * 3 * C : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int y = y0 + i, x = x0 + j;
+            bool valid = active && y >= 0 && y < H && x >= 0 && x < W;
+            int t = 0, pr = am_result(st[i * 4 + j]);
+            if (valid) {
+                long long tl = labels[((size_t)n * lh + y / ry) * lw + x / rx];
+                if (pred_out) pred_out[((size_t)n * H + y) * W + x] = pr;
+                valid = tl >= 0 && tl < C;
+                t = (int)tl;
+            }
+            hist_add(hist, confmat, pimg, C, valid, t, pr);
+        }
+    if (hist) hist_flush(hist, confmat, pimg, C);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k3_low_gen: arbitrary output size, one pixel per thread, taps from global (L1/L2 cached).
+// scale_y/scale_x = the ATen source scale (in/out as float, or 1/scale_factor).
+template <int MODE>
+__global__ void __launch_bounds__(K3_THREADS)
+k3_low_gen_kernel(const float* __restrict__ low, int C, int h, int w, int H, int W,
+                  float scale_y, float scale_x,
+                  const long long* __restrict__ labels, int lh, int lw,
+                  unsigned long long* __restrict__ confmat, unsigned long long* __restrict__ per_image,
+                  long long* __restrict__ pred_out, int use_smem_hist) {
+    extern __shared__ int hist_smem[];
+    int* hist = use_smem_hist ? hist_smem : nullptr;
+    const int n = blockIdx.y;
+    if (hist) {
+        for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+    }
+    constexpr int NT = MODE == 0 ? 2 : 4;
+    const long long HW = (long long)H * W;
+    const int ry = H / lh, rx = W / lw;
+    unsigned long long* pimg = per_image ? per_image + (size_t)n * 3 * C : nullptr;
+    for (long long p0 = (long long)blockIdx.x * K3_THREADS; p0 < HW; p0 += (long long)gridDim.x * K3_THREADS) {
+        const long long p = p0 + threadIdx.x;
+        bool valid = p < HW;
+        int pr = 0, t = 0;
+        if (valid) {
+            const int y = (int)(p / W), x = (int)(p - (long long)y * W);
+            float sy = scale_y * ((float)y + 0.5f) - 0.5f;
+            float sx = scale_x * ((float)x + 0.5f) - 0.5f;
+            int iy[NT], ix[NT];
+            float wy[NT], wx[NT];
+            if (MODE == 0) {
+                if (sy < 0.f) sy = 0.f;
+                if (sx < 0.f) sx = 0.f;
+                int ky = (int)sy, kx = (int)sx;
+                ky = ky > h - 1 ? h - 1 : ky;
+                kx = kx > w - 1 ? w - 1 : kx;
+                float ty = sy - (float)ky, tx = sx - (float)kx;
+                ty = ty < 0.f ? 0.f : (ty > 1.f ? 1.f : ty);
+                tx = tx < 0.f ? 0.f : (tx > 1.f ? 1.f : tx);
+                iy[0] = ky; iy[1] = ky + 1 < h ? ky + 1 : h - 1;
+                ix[0] = kx; ix[1] = kx + 1 < w ? kx + 1 : w - 1;
+                wy[0] = 1.f - ty; wy[1] = ty;
+                wx[0] = 1.f - tx; wx[1] = tx;
+            } else {
+                int ky = (int)floorf(sy), kx = (int)floorf(sx);
+                float cy[4], cx[4];
+                cubic_coeffs(sy - (float)ky, cy);
+                cubic_coeffs(sx - (float)kx, cx);
+#pragma unroll
+                for (int a = 0; a < NT; ++a) {
+                    iy[a] = clampi(ky - 1 + a, 0, h - 1);
+                    ix[a] = clampi(kx - 1 + a, 0, w - 1);
+                    wy[a] = cy[a]; wx[a] = cx[a];
+                }
+            }
+            ArgmaxState st;
+            am_init(st);
+            const float* base = low + (size_t)n * C * h * w;
+            for (int c = 0; c < C; ++c) {
+                const float* pc = base + (size_t)c * h * w;
+                float acc = 0.f;
+#pragma unroll
+                for (int a = 0; a < NT; ++a) {
+                    float r = __ldg(pc + iy[a] * w + ix[0]) * wx[0];
+#pragma unroll
+                    for (int b = 1; b < NT; ++b) r = fmaf(__ldg(pc + iy[a] * w + ix[b]), wx[b], r);
+                    acc = a == 0 ? r * wy[0] : fmaf(r, wy[a], acc);
+                }
+                am_update(st, acc, c);
+            }
+            pr = am_result(st);
+            long long tl = labels[((size_t)n * lh + y / ry) * lw + x / rx];
+            if (pred_out) pred_out[(size_t)n * HW + p] = pr;
+            valid = tl >= 0 && tl < C;
+            t = (int)tl;
+        }
+        hist_add(hist, confmat, pimg, C, valid, t, pr);
+    }
+    if (hist) hist_flush(hist, confmat, pimg, C);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename K>
+static int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(smem)");
+    }
+    return 0;
+}
+
+static int check_labels_ratio(int H, int W, int lh, int lw) {
+    if (lh <= 0 || lw <= 0 || H % lh || W % lw)
+        return fail(LC2IS_ERR_SHAPE, "labels [%s] must divide the mask size (%lld x %lld)", "lh,lw", H, W);
+    return 0;
+}
+
+}  // namespace lc2is
+
+using namespace lc2is;
+
+extern "C" int lc2is_argmax_confmat(const void* d_logits, int dtype, int N, int C, int H, int W,
+                                    const int64_t* d_labels, int lh, int lw,
+                                    int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                                    lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (!d_logits || !d_labels || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (N < 0 || C <= 0 || H <= 0 || W <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (int e = check_labels_ratio(H, W, lh, lw)) return e;
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int use_hist = C <= K3_SMEM_HIST_MAX_C;
+    const size_t smem = use_hist ? (size_t)C * C * sizeof(int) : 0;
+    const long long HW = (long long)H * W;
+    const int ctas_per_sm = smem > 100 * 1024 ? 1 : 2;
+    auto launch = [&](auto kernel, int pix, auto ptr) -> int {
+        if (int e = set_smem(kernel, smem)) return e;
+        long long chunk = (long long)K3_THREADS * pix;
+        long long items = (long long)N * ((HW + chunk - 1) / chunk);
+        long long grid = (long long)sm_count() * ctas_per_sm;
+        if (grid > items) grid = items;
+        kernel<<<(unsigned)grid, K3_THREADS, smem, st>>>(ptr, N, C, H, W, (const long long*)d_labels, lh, lw,
+                                                         (unsigned long long*)d_confmat,
+                                                         (unsigned long long*)d_per_image,
+                                                         (long long*)d_pred, use_hist);
+        return 0;
+    };
+    int e = 0;
+    if (dtype == LC2IS_F32) {
+        const float* p = (const float*)d_logits;
+        bool vec = HW % 4 == 0 && ((uintptr_t)p % 16 == 0);
+        e = vec ? launch(k3_full_kernel<float, true>, 4, p) : launch(k3_full_kernel<float, false>, 1, p);
+    } else if (dtype == LC2IS_BF16) {
+        const __nv_bfloat16* p = (const __nv_bfloat16*)d_logits;
+        bool vec = HW % 8 == 0 && ((uintptr_t)p % 16 == 0);
+        e = vec ? launch(k3_full_kernel<__nv_bfloat16, true>, 8, p)
+                : launch(k3_full_kernel<__nv_bfloat16, false>, 1, p);
+    } else {
+        return fail(LC2IS_ERR_ARG, "dtype must be LC2IS_F32 or LC2IS_BF16%s");
+    }
+    if (e) return e;
+    LC2IS_CHECK_LAUNCH("k3_full_kernel");
+    return 0;
+}
+
+extern "C" int lc2is_argmax_confmat_lowres(const float* d_low, int N, int C, int h, int w, int H, int W,
+                                           int mode, const int64_t* d_labels, int lh, int lw,
+                                           int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                                           lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (!d_low || !d_labels || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (N < 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (mode != LC2IS_BILINEAR && mode != LC2IS_BICUBIC) return fail(LC2IS_ERR_ARG, "bad mode%s");
+    if (int e = check_labels_ratio(H, W, lh, lw)) return e;
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int use_hist = C <= K3_SMEM_HIST_MAX_C;
+    const size_t smem = use_hist ? (size_t)C * C * sizeof(int) : 0;
+    int s = 0;
+    if (fast_scale(h, w, H, W, &s)) {
+        BlockGeom g = make_geom(H, W, s);
+        dim3 grid((g.nbx + 15) / 16, (g.nby + 15) / 16, N);
+        if (mode == LC2IS_BILINEAR) {
+            if (int e = set_smem(k3_low_fast_kernel<0>, smem)) return e;
+            k3_low_fast_kernel<0><<<grid, K3_THREADS, smem, st>>>(
+                d_low, C, h, w, H, W, s, g.off, g.nby, g.nbx, g.rs, (const long long*)d_labels, lh, lw,
+                (unsigned long long*)d_confmat, (unsigned long long*)d_per_image, (long long*)d_pred, use_hist);
+        } else {
+            if (int e = set_smem(k3_low_fast_kernel<1>, smem)) return e;
+            k3_low_fast_kernel<1><<<grid, K3_THREADS, smem, st>>>(
+                d_low, C, h, w, H, W, s, g.off, g.nby, g.nbx, g.rs, (const long long*)d_labels, lh, lw,
+                (unsigned long long*)d_confmat, (unsigned long long*)d_per_image, (long long*)d_pred, use_hist);
+        }
+        LC2IS_CHECK_LAUNCH("k3_low_fast_kernel");
+        return 0;
+    }
+    // generic: ATen scale for size= mode is (float)in / out
+    const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+    long long HW = (long long)H * W;
+    long long gx = (HW + K3_THREADS - 1) / K3_THREADS;
+    long long cap = (long long)sm_count() * 2;
+    if (N > 0 && gx > (cap + N - 1) / N) gx = (cap + N - 1) / N;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, N);
+    if (mode == LC2IS_BILINEAR) {
+        if (int e = set_smem(k3_low_gen_kernel<0>, smem)) return e;
+        k3_low_gen_kernel<0><<<grid, K3_THREADS, smem, st>>>(
+            d_low, C, h, w, H, W, sy, sx, (const long long*)d_labels, lh, lw,
+            (unsigned long long*)d_confmat, (unsigned long long*)d_per_image, (long long*)d_pred, use_hist);
+    } else {
+        if (int e = set_smem(k3_low_gen_kernel<1>, smem)) return e;
+        k3_low_gen_kernel<1><<<grid, K3_THREADS, smem, st>>>(
+            d_low, C, h, w, H, W, sy, sx, (const long long*)d_labels, lh, lw,
+            (unsigned long long*)d_confmat, (unsigned long long*)d_per_image, (long long*)d_pred, use_hist);
+    }
+    LC2IS_CHECK_LAUNCH("k3_low_gen_kernel");
+    return 0;
+}

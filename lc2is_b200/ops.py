@@ -1,0 +1,169 @@
+"""Tensor-level wrappers over the C ABI.  PyTorch is plumbing only here: it owns device
+memory and the current stream; all arithmetic happens in ``liblc2is_b200.so``."""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import BF16, BICUBIC, BILINEAR, F32, check, lib, ptr, stream_ptr
+
+_MODE = {"bilinear": BILINEAR, "bicubic": BICUBIC}
+
+
+def _req(t: Tensor, dtype, name: str) -> Tensor:
+    if not t.is_cuda:
+        raise _lib.Lc2isError(f"{name} must be a CUDA tensor (lc2is_b200 has no CPU fallback)")
+    if t.dtype != dtype:
+        raise _lib.Lc2isError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.contiguous()
+
+
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise _lib.Lc2isError(f"unsupported dtype {t.dtype} (float32 / bfloat16 only)")
+
+
+# ---- K0 -----------------------------------------------------------------------------------
+def proto_normalize(t: Tensor, normalize: bool = True) -> Tuple[Tensor, Tensor]:
+    """t [C,D] or [n_sets,C,D] fp32 -> (t_hat bf16 [n_sets,C_pad,D], inv_norm fp32 [n_sets,C])."""
+    t = _req(t, torch.float32, "t")
+    if t.dim() == 2:
+        t = t.unsqueeze(0)
+    n_sets, C, D = t.shape
+    Cp = _lib.class_pad(C)
+    t_hat = torch.empty(n_sets, Cp, D, dtype=torch.bfloat16, device=t.device)
+    inv = torch.empty(n_sets, C, dtype=torch.float32, device=t.device)
+    check(lib.lc2is_proto_normalize(ptr(t), n_sets, C, D, int(normalize), ptr(t_hat), ptr(inv), stream_ptr()),
+          "lc2is_proto_normalize")
+    return t_hat, inv
+
+
+# ---- K1 -----------------------------------------------------------------------------------
+def cosine_logits_fwd(v: Tensor, t_hat: Tensor, C: int, hw_shape: Tuple[int, int], normalize: bool = True,
+                      logit_scale: float = 1.0) -> Tuple[Tensor, Tensor, Tensor]:
+    """v [B,hw,D] fp32/bf16, t_hat from K0 -> (logits fp32 [B,C,h,w], v_hat bf16 [B*hw,D], inv_norm_v)."""
+    if not v.is_cuda:
+        raise _lib.Lc2isError("v must be a CUDA tensor (lc2is_b200 has no CPU fallback)")
+    v = v.contiguous()
+    B, hw, D = v.shape
+    h, w = hw_shape
+    assert h * w == hw
+    n_sets = t_hat.shape[0]
+    v_hat = torch.empty(B * hw, D, dtype=torch.bfloat16, device=v.device)
+    inv_v = torch.empty(B * hw, dtype=torch.float32, device=v.device)
+    logits = torch.empty(B, C, h, w, dtype=torch.float32, device=v.device)
+    check(lib.lc2is_cosine_logits_fwd(ptr(v), _dt(v), B, hw, D, ptr(t_hat), n_sets, C, int(normalize),
+                                      float(logit_scale), ptr(v_hat), ptr(inv_v), ptr(logits), stream_ptr()),
+          "lc2is_cosine_logits_fwd")
+    return logits, v_hat, inv_v
+
+
+def grad_to_bf16(grad: Tensor) -> Tensor:
+    """fp32 [B,C,h,w] -> bf16 [B,C_pad,h*w]."""
+    grad = _req(grad, torch.float32, "grad")
+    B, C = grad.shape[:2]
+    hw = grad[0, 0].numel()
+    out = torch.empty(B, _lib.class_pad(C), hw, dtype=torch.bfloat16, device=grad.device)
+    check(lib.lc2is_grad_to_bf16(ptr(grad), B, C, hw, ptr(out), stream_ptr()), "lc2is_grad_to_bf16")
+    return out
+
+
+def cosine_logits_bwd(grad_bf16: Tensor, logits: Tensor, v_hat: Tensor, inv_v: Tensor, t_hat: Tensor,
+                      inv_t: Tensor, C: int, normalize: bool = True, logit_scale: float = 1.0,
+                      grad_scale: Optional[Tensor] = None, grad_v_dtype=torch.float32,
+                      grad_t: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """-> (grad_v [B,hw,D], grad_t fp32 [n_sets,C,D]); grad_t is accumulated into if given."""
+    B = logits.shape[0]
+    hw = logits[0, 0].numel()
+    D = v_hat.shape[1]
+    n_sets = t_hat.shape[0]
+    dev = logits.device
+    grad_v = torch.empty(B, hw, D, dtype=grad_v_dtype, device=dev)
+    if grad_t is None:
+        grad_t = torch.zeros(n_sets, C, D, dtype=torch.float32, device=dev)
+    nbytes = int(lib.lc2is_cosine_logits_bwd_workspace(B, hw, D, n_sets, C))
+    ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+    check(lib.lc2is_cosine_logits_bwd(ptr(grad_bf16), ptr(logits), ptr(v_hat), ptr(inv_v), ptr(t_hat), ptr(inv_t),
+                                      B, hw, D, n_sets, C, int(normalize), float(logit_scale), ptr(grad_scale),
+                                      ptr(grad_v), _dt(grad_v), ptr(grad_t), ptr(ws), stream_ptr()),
+          "lc2is_cosine_logits_bwd")
+    return grad_v, grad_t
+
+
+# ---- K2 -----------------------------------------------------------------------------------
+def count_valid(labels: Tensor, ignore_index: int, out: Optional[Tensor] = None) -> Tensor:
+    labels = _req(labels, torch.int64, "labels")
+    if out is None:
+        out = torch.zeros(1, dtype=torch.int64, device=labels.device)
+    check(lib.lc2is_count_valid(ptr(labels), labels.numel(), int(ignore_index), ptr(out), stream_ptr()),
+          "lc2is_count_valid")
+    return out
+
+
+def mean_scale(n_valid: Tensor, mult: float = 1.0) -> Tensor:
+    out = torch.empty(1, dtype=torch.float32, device=n_valid.device)
+    check(lib.lc2is_mean_scale(ptr(n_valid), float(mult), ptr(out), stream_ptr()), "lc2is_mean_scale")
+    return out
+
+
+def finalize_loss(loss_sum: Tensor, n_valid: Tensor) -> Tensor:
+    out = torch.empty(1, dtype=torch.float32, device=n_valid.device)
+    check(lib.lc2is_finalize_loss(ptr(loss_sum), ptr(n_valid), ptr(out), stream_ptr()), "lc2is_finalize_loss")
+    return out
+
+
+def upsample_ce(low: Tensor, labels: Tensor, ignore_index: int = -100, grad_scale: Optional[Tensor] = None,
+                want_grad: bool = True, want_bf16: bool = False,
+                loss_sum: Optional[Tensor] = None) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor]]:
+    """low [B,C,h,w] fp32, labels [B,H,W] int64 -> (loss_sum double[1], grad_low fp32, grad_low_bf16)."""
+    low = _req(low, torch.float32, "low")
+    labels = _req(labels, torch.int64, "labels")
+    B, C, h, w = low.shape
+    Bl, H, W = labels.shape
+    if Bl != B:
+        raise _lib.Lc2isError("batch mismatch between logits and labels")
+    if loss_sum is None:
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=low.device)
+    grad = torch.empty_like(low) if (want_grad or want_bf16) else None
+    gbf = torch.empty(B, _lib.class_pad(C), h * w, dtype=torch.bfloat16, device=low.device) if want_bf16 else None
+    check(lib.lc2is_upsample_ce_fwd_bwd(ptr(low), ptr(labels), B, C, h, w, H, W, int(ignore_index),
+                                        ptr(grad_scale), ptr(loss_sum), ptr(grad), ptr(gbf), stream_ptr()),
+          "lc2is_upsample_ce_fwd_bwd")
+    return loss_sum, grad, gbf
+
+
+# ---- K3 -----------------------------------------------------------------------------------
+def argmax_confmat(logits: Tensor, labels: Tensor, confmat: Optional[Tensor] = None, per_image: bool = False,
+                   want_pred: bool = False, size: Optional[Tuple[int, int]] = None, mode: Optional[str] = None):
+    """logits [N,C,h,w] (fp32/bf16), labels [N,lh,lw] int64.
+    size=None: logits are at mask resolution.  size=(H,W)+mode: fused bilinear/bicubic resize.
+    Returns (confmat int64 [C,C] (accumulated), per_image int64 [N,3,C] | None, pred int64 [N,H,W] | None)."""
+    if not logits.is_cuda:
+        raise _lib.Lc2isError("logits must be a CUDA tensor (lc2is_b200 has no CPU fallback)")
+    logits = logits.contiguous()
+    labels = _req(labels, torch.int64, "labels")
+    N, C, h, w = logits.shape
+    Nl, lh, lw = labels.shape
+    if Nl != N:
+        raise _lib.Lc2isError("batch mismatch between logits and labels")
+    dev = logits.device
+    H, W = (h, w) if size is None else (int(size[0]), int(size[1]))
+    if confmat is None:
+        confmat = torch.zeros(C, C, dtype=torch.int64, device=dev)
+    pi = torch.zeros(N, 3, C, dtype=torch.int64, device=dev) if per_image else None
+    pred = torch.empty(N, H, W, dtype=torch.int64, device=dev) if want_pred else None
+    if size is None:
+        check(lib.lc2is_argmax_confmat(ptr(logits), _dt(logits), N, C, H, W, ptr(labels), lh, lw, ptr(confmat),
+                                       ptr(pi), ptr(pred), stream_ptr()), "lc2is_argmax_confmat")
+    else:
+        logits = _req(logits, torch.float32, "logits")
+        check(lib.lc2is_argmax_confmat_lowres(ptr(logits), N, C, h, w, H, W, _MODE[mode], ptr(labels), lh, lw,
+                                              ptr(confmat), ptr(pi), ptr(pred), stream_ptr()),
+              "lc2is_argmax_confmat_lowres")
+    return confmat, pi, pred

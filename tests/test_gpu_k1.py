@@ -1,0 +1,129 @@
+"""K0/K1/K1b parity: cosine-logits tensor-core GEMM (tcgen05/TMEM/TMA) and its backward.
+
+Tolerances:
+  v_hat / t_hat : bf16(fp32 normalise) - at most 1 bf16 ulp from the oracle's rounding (fp32 norm
+                  summation order differs), on < 0.5 % of the elements
+  logits        : vs fp32 matmul of the kernel's OWN bf16 operands: |d| <= 2e-6 * scale (fp32
+                  accumulation order only); vs the full-fp32 reference: |d| <= 4e-3 * scale
+                  (bf16 unit round-off 2^-9)
+  grad_v/grad_t : rel 2e-2 of max|grad| vs the fp32 autograd oracle (bf16 operands and bf16 dL/dlogits)
+"""
+import os
+
+import pytest
+import torch
+
+from oracle import head_oracle as O
+from lc2is_b200 import head, ops, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _bf16_ulp_check(got, ref32):
+    """got: bf16 tensor; ref32: fp32 values before rounding."""
+    ref = ref32.to(torch.bfloat16)
+    diff = (got.float() - ref.float()).abs()
+    ulp = torch.maximum(ref.float().abs(), torch.tensor(1e-30)) * 2.0 ** -7
+    assert bool((diff <= ulp).all())
+    assert float((diff > 0).float().mean()) < 5e-3
+
+
+@pytest.mark.parametrize("B,hw,C,dtype,normalize,scale", [
+    (2, 64, 151, torch.float32, True, 1.0),       # golden geometry
+    (2, 1024, 150, torch.bfloat16, True, 1.0),    # 32^2 grid
+    (1, 16384, 151, torch.bfloat16, True, 14.285714),   # 128^2 grid, temperature 1/0.07
+    (3, 200, 19, torch.float32, True, 1.0),       # ragged: hw not a multiple of 128
+    (2, 256, 847, torch.bfloat16, True, 1.0),     # open-vocab: 4 N-tiles
+    (2, 128, 151, torch.float32, False, 1.0),     # un-normalised (model.py:50)
+    (1, 1, 3, torch.float32, True, 1.0),
+])
+def test_logits(B, hw, C, dtype, normalize, scale):
+    D = 512
+    v = synthetic.make_patch_embeddings(B, hw, D, dtype=dtype)
+    t = synthetic.make_prototypes(C, D)
+    t_hat, inv_t = ops.proto_normalize(t.to(DEV), normalize)
+    h = int(hw ** 0.5); hw_shape = (h, hw // h) if h * (hw // h) == hw else (1, hw)
+    logits, v_hat, inv_v = ops.cosine_logits_fwd(v.to(DEV), t_hat, C, hw_shape, normalize, scale)
+    Cp = ops._lib.class_pad(C)
+    assert t_hat.shape == (1, Cp, D) and float(t_hat[0, C:].float().abs().max() if Cp > C else 0.0) == 0.0
+    v32, t32 = v.float(), t.float()
+    if normalize:
+        _bf16_ulp_check(v_hat.cpu(), torch.nn.functional.normalize(v32, dim=2).reshape(-1, D))
+        _bf16_ulp_check(t_hat[0, :C].cpu(), torch.nn.functional.normalize(t32, dim=1))
+        torch.testing.assert_close(inv_v.cpu(), 1 / v32.norm(dim=2).reshape(-1).clamp_min(1e-12), rtol=1e-5, atol=0)
+    else:
+        assert torch.equal(v_hat.cpu(), v32.to(torch.bfloat16).reshape(-1, D))
+    # exact-operand check
+    ref_same = scale * torch.einsum("bpd,cd->bcp", v_hat.float().reshape(B, hw, D), t_hat[0, :C].float()).cpu()
+    got = logits.reshape(B, C, hw).cpu()
+    mag = float(ref_same.abs().max())
+    assert float((got - ref_same).abs().max()) <= 2e-6 * max(mag, scale), float((got - ref_same).abs().max())
+    # reference (fp32) check
+    ref = O.cosine_logits(v32, t32, normalize=normalize, logit_scale=scale, hw_shape=hw_shape).reshape(B, C, hw)
+    tol = 4e-3 * (scale if normalize else float(ref.abs().max()))
+    assert float((got - ref).abs().max()) <= tol
+
+
+def test_golden_final_py(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "head_final.pt"))
+    t = synthetic.load_prototypes()
+    low = head.cosine_logits(g["v"].to(DEV), t.to(DEV))
+    assert low.shape == g["score_low"].shape
+    assert float((low.cpu() - g["score_low"]).abs().max()) <= 4e-3
+    raw = head.cosine_logits(g["v"].to(DEV), t.to(DEV), normalize=False)
+    assert float((raw.cpu() - g["raw"]).abs().max()) <= 4e-3 * float(g["raw"].abs().max())
+
+
+def test_per_image_prompts():
+    """final.py:129-130: text embeddings differ per image ([B,K,D])."""
+    B, hw, C, D = 3, 256, 151, 512
+    v = synthetic.make_patch_embeddings(B, hw, D, dtype=torch.float32)
+    t = torch.stack([synthetic.make_prototypes(C, D) + 0.3 * i for i in range(B)])
+    got = head.cosine_logits(v.to(DEV), t.to(DEV))
+    ref = O.cosine_logits(v, t)
+    assert float((got.cpu() - ref).abs().max()) <= 4e-3
+
+
+@pytest.mark.parametrize("B,hw,C,normalize,per_image", [
+    (2, 256, 151, True, False),
+    (1, 1024, 150, True, False),
+    (2, 200, 19, True, False),
+    (2, 128, 151, False, False),
+    (2, 128, 40, True, True),
+    (1, 256, 847, True, False),
+])
+def test_backward(B, hw, C, normalize, per_image):
+    D = 512
+    g = torch.Generator().manual_seed(31)
+    v = synthetic.make_patch_embeddings(B, hw, D, dtype=torch.float32)
+    t = synthetic.make_prototypes(C, D)
+    if per_image:
+        t = torch.stack([t + 0.2 * i for i in range(B)])
+    h = int(hw ** 0.5); hw_shape = (h, hw // h) if h * (hw // h) == hw else (1, hw)
+    G = torch.randn(B, C, *hw_shape, generator=g) * 1e-3
+    gv_ref, gt_ref = O.cosine_logits_backward(v, t, G, normalize=normalize)
+    vd = v.to(DEV).requires_grad_(True)
+    td = t.to(DEV).requires_grad_(True)
+    out = head.cosine_logits(vd, td, normalize=normalize, hw_shape=hw_shape)
+    out.backward(G.to(DEV))
+    ev = float((vd.grad.cpu() - gv_ref).abs().max() / gv_ref.abs().max())
+    et = float((td.grad.cpu() - gt_ref).abs().max() / gt_ref.abs().max())
+    assert ev < 2e-2 and et < 2e-2, (ev, et)
+
+
+def test_fused_head_loss_matches_oracle():
+    B, h, H, C, D = 2, 32, 128, 151, 512
+    v = synthetic.make_patch_embeddings(B, h * h, D, dtype=torch.float32)
+    t = synthetic.make_prototypes(C, D)
+    labels = synthetic.make_labels(B, H, H, C, block=8, ignore_frac=0.1)
+    ref = O.head_step(v, t, labels, ignore_index=0, n_cls=C)
+    vd = v.to(DEV).requires_grad_(True)
+    td = t.to(DEV).requires_grad_(True)
+    loss, low, n_valid = head.SegHeadLoss(ignore_index=0)(vd, td, labels.to(DEV))
+    (0.4 * loss).backward()
+    assert abs(float(loss) - float(ref["loss"])) <= 1e-4 * float(ref["loss"])
+    assert int(n_valid) == int((labels != 0).sum())
+    ev = float((vd.grad.cpu() - 0.4 * ref["grad_v"]).abs().max() / (0.4 * ref["grad_v"]).abs().max())
+    et = float((td.grad.cpu() - 0.4 * ref["grad_t"]).abs().max() / (0.4 * ref["grad_t"]).abs().max())
+    assert ev < 3e-2 and et < 3e-2, (ev, et)

@@ -1,0 +1,153 @@
+"""K3 parity (bit-exact integer work) through the C ABI, against the CPU oracle."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import head_oracle as O
+from lc2is_b200 import metrics, ops, synthetic, utils
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _per_image_ref(pred, lab, C):
+    out = torch.zeros(pred.shape[0], 3, C, dtype=torch.int64)
+    for n in range(pred.shape[0]):
+        cm = O.confusion_matrix(pred[n], lab[n], C)
+        out[n, 0] = torch.diag(cm); out[n, 1] = cm.sum(1); out[n, 2] = cm.sum(0)
+    return out
+
+
+@pytest.mark.parametrize("N,C,H,W,dtype", [
+    (3, 151, 64, 64, torch.float32),
+    (2, 150, 128, 96, torch.float32),
+    (2, 151, 64, 64, torch.bfloat16),
+    (1, 7, 33, 31, torch.float32),        # ragged: HW not a multiple of 4 -> scalar path
+    (1, 7, 33, 31, torch.bfloat16),
+    (2, 300, 32, 32, torch.float32),      # C*C too large for the shared histogram -> global atomics
+    (1, 1, 16, 16, torch.float32),
+])
+def test_full_res_confmat_bit_exact(N, C, H, W, dtype):
+    g = torch.Generator().manual_seed(5)
+    logits = torch.randn(N, C, H, W, generator=g).to(dtype)
+    labels = torch.randint(0, C, (N, H, W), generator=g)
+    labels[0, :2] = C + 3                                    # out-of-range targets are skipped
+    labels[0, 2, :4] = -1
+    pred_ref = O.argmax_logits(logits.float())
+    cm, pi, pred = ops.argmax_confmat(logits.to(DEV), labels.to(DEV), per_image=True, want_pred=True)
+    assert torch.equal(pred.cpu(), pred_ref)
+    assert torch.equal(cm.cpu(), O.confusion_matrix(pred_ref, labels, C))
+    assert torch.equal(pi.cpu(), _per_image_ref(pred_ref, labels, C))
+
+
+def test_ties_first_index_and_nan():
+    C = 9
+    x = torch.zeros(1, C, 8, 8)
+    x[0, 4] = 1.0; x[0, 6] = 1.0                              # tie -> first index (4)
+    x[0, :, 0, 0] = float("nan")                               # NaN row -> class 0 (argmax(softmax) of all-NaN)
+    x[0, 2, 1, 1] = float("inf")                               # +inf -> softmax is NaN everywhere -> class 0
+    x[0, :, 2, 2] = float("-inf")                              # all -inf -> NaN -> 0
+    labels = torch.full((1, 8, 8), 4, dtype=torch.int64)
+    _, _, pred = ops.argmax_confmat(x.to(DEV), labels.to(DEV), want_pred=True)
+    assert torch.equal(pred.cpu(), O.argmax_reference(x))
+
+
+def test_accumulates_and_empty_batch():
+    C = 5
+    g = torch.Generator().manual_seed(6)
+    logits = torch.randn(2, C, 16, 16, generator=g)
+    labels = torch.randint(0, C, (2, 16, 16), generator=g)
+    cm, _, _ = ops.argmax_confmat(logits.to(DEV), labels.to(DEV))
+    cm, _, _ = ops.argmax_confmat(logits.to(DEV), labels.to(DEV), confmat=cm)
+    assert torch.equal(cm.cpu(), 2 * O.confusion_matrix(O.argmax_logits(logits), labels, C))
+    cm0, _, _ = ops.argmax_confmat(torch.zeros(0, C, 4, 4, device=DEV), torch.zeros(0, 4, 4, dtype=torch.int64, device=DEV))
+    assert int(cm0.sum()) == 0
+
+
+@pytest.mark.parametrize("s,h", [(4, 16), (16, 4), (8, 8)])
+def test_fused_bilinear_dyadic_bit_exact(s, h):
+    """Exactness set: bilinear xs of k/256 logits is exact in fp32 in any order -> bit-exact argmax."""
+    N, C = 2, 151
+    low = synthetic.make_dyadic_logits(N, C, h, h)
+    H = s * h
+    labels = synthetic.make_labels(N, H, H, C, block=8)
+    up = F.interpolate(low, mode="bilinear", scale_factor=s)
+    pred_ref = O.argmax_reference(up)
+    cm, pi, pred = ops.argmax_confmat(low.to(DEV), labels.to(DEV), per_image=True, want_pred=True,
+                                      size=(H, H), mode="bilinear")
+    assert torch.equal(pred.cpu(), pred_ref)
+    assert torch.equal(cm.cpu(), O.confusion_matrix(pred_ref, labels, C))
+    assert torch.equal(pi.cpu(), _per_image_ref(pred_ref, labels, C))
+
+
+def _safe_mask(up, tol):
+    top2 = up.topk(2, dim=1).values
+    return (top2[:, 0] - top2[:, 1]) > tol
+
+
+@pytest.mark.parametrize("mode,s,h,H", [("bicubic", 4, 16, 64), ("bilinear", 4, 16, 64), ("bicubic", 16, 4, 64),
+                                         ("bicubic", None, 13, 37), ("bilinear", None, 13, 37),
+                                         ("bicubic", None, 16, 32)])
+def test_fused_resize_argmax_tie_safe(mode, s, h, H):
+    """Random fp32 logits: the fused kernel may differ from ATen only in fp32 evaluation order, so the
+    argmax must agree on every pixel whose top-2 gap exceeds 1e-4 ('bit-exact argmax')."""
+    N, C = 2, 23
+    g = torch.Generator().manual_seed(8)
+    low = torch.randn(N, C, h, h, generator=g)
+    up = F.interpolate(low, mode=mode, size=(H, H))
+    labels = torch.randint(0, C, (N, H, H), generator=g)
+    pred_ref = O.argmax_reference(up)
+    _, _, pred = ops.argmax_confmat(low.to(DEV), labels.to(DEV), want_pred=True, size=(H, H), mode=mode)
+    safe = _safe_mask(up, 1e-4)
+    assert safe.float().mean() > 0.99
+    assert torch.equal(pred.cpu()[safe], pred_ref[safe])
+
+
+def test_labels_nearest_upsampled_in_kernel():
+    """metrics.py:90: labels at the low grid, nearest x4."""
+    N, C, h = 2, 11, 8
+    low = synthetic.make_dyadic_logits(N, C, h, h)
+    lab = torch.randint(0, C, (N, h, h), generator=torch.Generator().manual_seed(2))
+    up = F.interpolate(low, mode="bilinear", scale_factor=4)
+    labu = F.interpolate(lab.view(-1, 1, h, h).float(), mode="nearest", scale_factor=4).squeeze(1).long()
+    cm, _, _ = ops.argmax_confmat(low.to(DEV), lab.to(DEV), size=(4 * h, 4 * h), mode="bilinear")
+    assert torch.equal(cm.cpu(), O.confusion_matrix(O.argmax_reference(up), labu, C))
+
+
+def test_metrics_api_matches_oracle_and_golden(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "metrics_small.pt"))
+    C = g["outputs"].shape[1]
+    got = metrics.compute_mIOU(g["outputs"], g["labels"], n_cls=C, ignore_index=0)     # CPU tensors in
+    assert abs(got["mIOU_label"] - g["miou_label"]) < 1e-6
+    up = F.interpolate(g["outputs"], mode="bicubic", scale_factor=4)
+    lab = g["labels"].repeat_interleave(4, 1).repeat_interleave(4, 2)
+    assert abs(metrics.compute_mIOU_tensor(up, lab, C, 0) - g["miou_global"]) < 1e-6
+    cm = metrics.confusion_matrix(up.to(DEV), lab.to(DEV))
+    assert torch.equal(cm.cpu(), g["confmats"].sum(0))
+    # ragged ground truth (compute_gt_mIOU / segmentation_metrics / generate_masks)
+    sizes = torch.tensor([[20, 28], [31, 17], [24, 24]])
+    gt = [torch.randint(0, C, (int(a), int(b)), generator=torch.Generator().manual_seed(i)) for i, (a, b) in enumerate(sizes)]
+    ref = O.compute_gt_mIOU(g["outputs"], gt, sizes, n_cls=C, ignore_index=0)["mIOU_gt"]
+    got = metrics.segmentation_metrics(g["outputs"], g["labels"], gt, sizes, n_clas=C, ignore_index=0)
+    assert abs(got["mIOU_gt"] - ref) < 1e-6 and abs(got["mIOU_label"] - g["miou_label"]) < 1e-6
+    masks = utils.generate_masks(g["outputs"], sizes)
+    for m, r in zip(masks, O.generate_masks(g["outputs"], sizes)):
+        assert m.dtype == torch.int64 and torch.equal(m.cpu(), r)
+
+
+def test_full_size_property_checksum():
+    """BASELINE size (512^2, C=150): row sums of the confusion matrix == label histogram, column sums ==
+    prediction histogram, total == pixel count; fused-from-low == materialised on dyadic logits."""
+    N, C, h, H = 4, 150, 128, 512
+    low = synthetic.make_dyadic_logits(N, C, h, h).to(DEV)
+    labels = synthetic.make_labels(N, H, H, C).to(DEV)
+    cm_f, _, pred = ops.argmax_confmat(low, labels, want_pred=True, size=(H, H), mode="bilinear")
+    up = F.interpolate(low, mode="bilinear", scale_factor=4)
+    cm_m, _, pred_m = ops.argmax_confmat(up, labels, want_pred=True)
+    assert torch.equal(cm_f, cm_m) and torch.equal(pred, pred_m)
+    assert torch.equal(pred_m, up.argmax(1))
+    assert int(cm_f.sum()) == N * H * H
+    assert torch.equal(cm_f.sum(1), torch.bincount(labels.flatten(), minlength=C))
+    assert torch.equal(cm_f.sum(0), torch.bincount(pred.flatten(), minlength=C))

@@ -1,0 +1,85 @@
+"""Host-side mirror of the reference interface, CPU-checkable parts."""
+import os
+
+import pytest
+import torch
+
+from oracle import head_oracle as O
+from lc2is_b200 import metrics, synthetic
+from lc2is_b200.model import TextToPatch, AuxiliaryLoss, ContrastiveLoss, NPairLoss
+from lc2is_b200.model.decoder import DecoderLayer, DecoderBlock, PromptLayer, PromptDecoder
+
+
+def test_text_to_patch_matches_reference(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "text_patch.pt"))
+    m = TextToPatch(img_in=48, text_in=32, out=64)
+    m.load_state_dict(g["state"])                                # reference parameter names load
+    tf, vf = m(g["img"], g["text"])                              # text first (text_patch.py:18)
+    assert torch.equal(tf, g["t_feature"]) and torch.equal(vf, g["v_feature"])
+    assert sum(p.numel() for p in TextToPatch(768, 512, 512).parameters()) == 656384
+
+
+def test_miou_helpers_match_oracle():
+    g = torch.Generator().manual_seed(3)
+    cm = torch.randint(0, 50, (7, 7), generator=g)
+    cm[:, 5] = 0; cm[5, :] = 0                                   # an absent class
+    for ign in (0, 3, None):
+        a = metrics.miou_from_confmat(cm, ign).item()
+        b = O.jaccard_macro(cm, ign).item()
+        assert abs(a - b) < 1e-7
+        assert abs(metrics.pixel_accuracy_from_confmat(cm, ign).item() - O.pixel_accuracy(cm, ign)) < 1e-12
+
+
+def test_per_image_miou_matches_oracle():
+    g = torch.Generator().manual_seed(4)
+    C = 6
+    pred = torch.randint(0, C, (3, 10, 10), generator=g)
+    lab = torch.randint(0, C, (3, 10, 10), generator=g)
+    lab[1][lab[1] == 4] = 2                                       # class 4 absent from image 1's label
+    per = torch.zeros(3, 3, C, dtype=torch.int64)
+    ref = []
+    for n in range(3):
+        cm = O.confusion_matrix(pred[n], lab[n], C)
+        per[n, 0] = torch.diag(cm); per[n, 1] = cm.sum(1); per[n, 2] = cm.sum(0)
+        ref.append(O.per_image_miou_from_cm(cm, lab[n], 0))
+    got = metrics._per_image_miou(per, 0)
+    torch.testing.assert_close(got, torch.cat(ref), rtol=0, atol=1e-7)
+
+
+def test_auxiliary_loss_rejects_unsupported_options():
+    with pytest.raises(NotImplementedError):
+        AuxiliaryLoss(weight=torch.ones(3))
+    with pytest.raises(NotImplementedError):
+        AuxiliaryLoss(label_smoothing=0.1)
+    with pytest.raises(NotImplementedError):
+        AuxiliaryLoss(reduction="none")
+    assert AuxiliaryLoss(ignore_index=0).ignore_index == 0
+
+
+def test_passthrough_losses_run():
+    out = torch.randn(2, 16, 151)
+    lab = torch.randint(0, 4, (2, 4, 4))
+    l, lv, lt = ContrastiveLoss()(out, lab)
+    assert l.shape == () and torch.isfinite(l)
+    r = NPairLoss()(torch.rand(4, 8), torch.rand(3, 8), torch.rand(5, 8))
+    assert r.shape == ()
+
+
+def test_decoder_surface():
+    layer = DecoderLayer(d_model=32, d_kv=16, nhead=4, dim_feedforward=64, batch_first=True, norm_first=True)
+    blk = DecoderBlock(layer, num_layers=1)
+    y = blk(tgt=torch.randn(2, 5, 32), memory=torch.randn(2, 3, 16))
+    assert y.shape == (2, 5, 32)
+    p = PromptDecoder(PromptLayer(d_model=32, d_kv=16, nhead=4, dim_feedforward=64, batch_first=True), 1)
+    assert p(torch.randn(2, 5, 32), torch.randn(2, 3, 16)).shape == (2, 5, 32)
+
+
+def test_synthetic_inputs_are_seeded():
+    a = synthetic.make_labels(2, 64, 64, 151)
+    b = synthetic.make_labels(2, 64, 64, 151)
+    assert torch.equal(a, b) and a.dtype == torch.int64 and int(a.max()) < 151 and int(a.min()) >= 0
+    assert synthetic.make_prototypes(150).shape == (150, 512)
+    assert torch.equal(synthetic.make_prototypes(150), synthetic.load_prototypes()[1:])
+    assert synthetic.make_prototypes(847).shape == (847, 512)
+    d = synthetic.make_dyadic_logits(1, 5, 4, 4)
+    assert torch.equal(d * 256, (d * 256).round())
