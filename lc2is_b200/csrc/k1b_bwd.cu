@@ -1,9 +1,462 @@
-// placeholder (replaced below)
+// K1b: backward of the cosine-logits GEMM (autograd of model/final.py:41-43; engine.py:100).
+//
+// With  logits[m,c] = s * <vhat_m, that_c>,  G = dL/dlogits  and  g = upstream scalar:
+//   dVhat = s*g * G  That         [M,C] x [C,D]     (K = classes)
+//   dThat = s*g * G^T Vhat        [C,M] x [M,D]     (K = pixels, split-K over CTAs)
+// and the normalise-backward  dx = (dxhat - xhat <xhat, dxhat>) / ||x||  needs only
+//   <vhat_m, dVhat_m> = g * sum_c G[m,c] logits[m,c] =: g * r[m]
+//   <that_c, dThat_c> = g * sum_m G[m,c] logits[m,c] =: g * rt[c]
+// i.e. row / column sums of G (.) logits (k1b_prep_kernel) - no second pass over D.
+//
+// Both GEMMs run on tcgen05 straight from the forward's layouts - no transposes in memory:
+//   dV : A = G  [b][c][p] (p contiguous)  -> MN-major A,   B = That [c][d] -> MN-major B
+//   dT : A = Vhat [m][d] (d contiguous)   -> MN-major A,   B = G [b][c][p]  -> K-major B
+// MN-major 128B-swizzled operand tiles are [K rows][64 elements] boxes written by TMA: 8 K-rows
+// form one 1024-B swizzle atom (stride-byte-offset 1024 between atoms along K), 64-element
+// groups along M/N are `box bytes` apart (leading-byte-offset).
 #include "common.cuh"
+#include "tc_common.cuh"
+
+namespace lc2is {
+
+constexpr int KB_THREADS = 192;
+
+// ---------------------------------------------------------------------------------------------
+// r[m] = sum_c G[m,c]*L[m,c]   ;   rt[set][c] += sum_m G[m,c]*L[m,c]
+__global__ void __launch_bounds__(256)
+k1b_prep_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ L, int B, int C, int C_pad, int hw,
+                int n_sets, float* __restrict__ r, float* __restrict__ rt) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * 256 + threadIdx.x;
+    const bool in = p < hw;
+    const __nv_bfloat16* g = G + (size_t)b * C_pad * hw + p;
+    const float* l = L + (size_t)b * C * hw + p;
+    float acc = 0.f;
+    __shared__ float part[8];
+    float* rts = rt + (size_t)(n_sets > 1 ? b : 0) * C;
+    for (int c = 0; c < C; ++c) {
+        float v = in ? __bfloat162float(g[(size_t)c * hw]) * __ldg(l + (size_t)c * hw) : 0.f;
+        acc += v;
+        float w = warp_sum(v);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t += part[i];
+            if (t != 0.f) atomicAdd(rts + c, t);
+        }
+        __syncthreads();
+    }
+    if (in) r[(size_t)b * hw + p] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dV GEMM.  Tile = 128 pixels x 256 channels (2 n-tiles of D=512 ...), K = C_pad in steps of 16.
+struct DvParams {
+    void* grad_v;               // [M, D] bf16 or fp32
+    const __nv_bfloat16* v_hat; // [M, D]
+    const float* inv_v;         // [M]
+    const float* r;             // [M]
+    const float* grad_scale;    // device scalar or null
+    int B, hw, D, C_pad, n_sets;
+    int tiles_per_img, n_ntiles, num_kb, stages;
+    int normalize, out_f32;
+    float scale;
+};
+constexpr int DV_BM = 128, DV_BN = 256, DV_KB = 16;
+constexpr int DV_A_BYTES = 2 * DV_KB * 128;            // 2 boxes [16 k][64 p]
+constexpr int DV_B_BYTES = (DV_BN / 64) * DV_KB * 128; // 4 boxes [16 k][64 d]
+constexpr int DV_STAGE = DV_A_BYTES + DV_B_BYTES;      // 12 KB
+constexpr int DV_MAX_STAGES = 12;
+
+__global__ void __launch_bounds__(KB_THREADS, 1)
+k1b_dv_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmT, const DvParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base_u32 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base_u32 - tc::smem_u32(smem_raw));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * DV_STAGE);
+    uint64_t* empty = full + DV_MAX_STAGES;
+    uint64_t* tfull = empty + DV_MAX_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = P.B * P.tiles_per_img * P.n_ntiles;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmG);
+        tc::prefetch_tmap(&tmT);
+        for (int i = 0; i < P.stages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % P.n_ntiles, mt = tile / P.n_ntiles;
+                const int b = mt / P.tiles_per_img, ti = mt - b * P.tiles_per_img;
+                const int trow0 = (P.n_sets > 1 ? b : 0) * P.C_pad;
+                for (int kb = 0; kb < P.num_kb; ++kb) {
+                    tc::mbar_wait(empty + stage, phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * DV_STAGE;
+                    tc::mbar_arrive_expect_tx(full + stage, DV_STAGE);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)     // A: G[b][kb*16 .. +16][ti*128 + j*64 .. +64]
+                        tc::tma_load_3d(sa + j * DV_KB * 128, &tmG, full + stage, ti * DV_BM + j * 64, kb * DV_KB, b);
+#pragma unroll
+                    for (int j = 0; j < DV_BN / 64; ++j)   // B: That[trow0 + kb*16 .. +16][nt*256 + j*64 .. +64]
+                        tc::tma_load_2d(sa + DV_A_BYTES + j * DV_KB * 128, &tmT, full + stage,
+                                        nt * DV_BN + j * 64, trow0 + kb * DV_KB);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(DV_BM, DV_BN, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t bphase = (it >> 1) & 1;
+                tc::mbar_wait(tempty + buf, bphase ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kb = 0; kb < P.num_kb; ++kb) {
+                    tc::mbar_wait(full + stage, phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = base_u32 + stage * DV_STAGE;
+                    // MN-major: LBO = bytes between 64-element M/N groups, SBO = 1024 (8 K-rows)
+                    const uint64_t adesc = tc::make_smem_desc(sa, DV_KB * 128, 1024);
+                    const uint64_t bdesc = tc::make_smem_desc(sa + DV_A_BYTES, DV_KB * 128, 1024);
+                    tc::umma_bf16(d_tmem, adesc, bdesc, idesc, kb != 0);
+                    tc::umma_commit(empty + stage);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(tfull + buf);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const float gs = P.grad_scale ? __ldg(P.grad_scale) : 1.f;
+        const float sg = P.scale * gs;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            const uint32_t bphase = (it >> 1) & 1;
+            const int nt = tile % P.n_ntiles, mt = tile / P.n_ntiles;
+            const int b = mt / P.tiles_per_img, ti = mt - b * P.tiles_per_img;
+            const int p = ti * DV_BM + q * 32 + lane;
+            const bool rvalid = p < P.hw;
+            const size_t m = (size_t)b * P.hw + (rvalid ? p : 0);
+            const float inv = rvalid ? __ldg(P.inv_v + m) : 0.f;
+            const float rr = (rvalid && P.normalize) ? __ldg(P.r + m) * gs : 0.f;
+            tc::mbar_wait(tfull + buf, bphase);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+            const int d0 = nt * DV_BN;
+            for (int col = 0; col < DV_BN; col += 16) {
+                if (d0 + col >= P.D) break;
+                uint32_t acc[16];
+                tc::tmem_ld16(taddr + col, acc);
+                tc::tmem_ld_wait();
+                if (rvalid) {
+                    float o[16];
+                    if (P.normalize) {
+                        const uint4* vp = reinterpret_cast<const uint4*>(P.v_hat + m * P.D + d0 + col);
+                        uint4 v0 = __ldg(vp), v1 = __ldg(vp + 1);
+                        unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float va = __uint_as_float(w[j] << 16), vb = __uint_as_float(w[j] & 0xffff0000u);
+                            o[2 * j] = (__uint_as_float(acc[2 * j]) * sg - va * rr) * inv;
+                            o[2 * j + 1] = (__uint_as_float(acc[2 * j + 1]) * sg - vb * rr) * inv;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(acc[j]) * sg;
+                    }
+                    if (P.out_f32) {
+                        float4* op = reinterpret_cast<float4*>((float*)P.grad_v + m * P.D + d0 + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    } else {
+                        __nv_bfloat162 pk[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pk[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+                        uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)P.grad_v + m * P.D + d0 + col);
+                        op[0] = *reinterpret_cast<uint4*>(&pk[0]);
+                        op[1] = *reinterpret_cast<uint4*>(&pk[4]);
+                    }
+                }
+            }
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(tempty + buf);
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dT GEMM (split-K).  Work item = (set, d-tile of 128, class tile of NB, K range of 64-pixel blocks);
+// the partial [128 x NB] accumulator is added to dT_raw[set][c][d] with fp32 L2 reductions.
+struct DtParams {
+    float* dt_raw;              // [n_sets, C, D] fp32, pre-zeroed
+    int B, hw, D, C, C_pad, n_sets;
+    int NB, n_ntiles, n_dtiles, ksplit, kb_per_img, stages;
+};
+constexpr int DT_BM = 128, DT_KB = 64;
+constexpr int DT_A_BYTES = 2 * DT_KB * 128;           // 2 boxes [64 p][64 d] = 16 KB
+constexpr int DT_MAX_STAGES = 8;
+
+__global__ void __launch_bounds__(KB_THREADS, 1)
+k1b_dt_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmG, const DtParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base_u32 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base_u32 - tc::smem_u32(smem_raw));
+    const int stage_bytes = DT_A_BYTES + P.NB * 128;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+    uint64_t* empty = full + DT_MAX_STAGES;
+    uint64_t* tfull = empty + DT_MAX_STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tfull + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // decode the work item of this CTA
+    int w = blockIdx.x;
+    const int ks = w % P.ksplit; w /= P.ksplit;
+    const int nt = w % P.n_ntiles; w /= P.n_ntiles;
+    const int dt = w % P.n_dtiles; w /= P.n_dtiles;
+    const int set = w;                                   // 0 when the prototypes are shared
+    // K blocks: shared prototypes -> all images concatenated; per-image prompts -> image `set` only
+    const int total_kb = (P.n_sets > 1 ? 1 : P.B) * P.kb_per_img;
+    const int kb_lo = (int)((long long)total_kb * ks / P.ksplit);
+    const int kb_hi = (int)((long long)total_kb * (ks + 1) / P.ksplit);
+    const int nkb = kb_hi - kb_lo;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmV);
+        tc::prefetch_tmap(&tmG);
+        for (int i = 0; i < P.stages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+        tc::mbar_init(tfull, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, 256);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (nkb > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                int stage = 0; uint32_t phase = 0;
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
+                    const int b = P.n_sets > 1 ? set : kb / P.kb_per_img;
+                    const int kl = P.n_sets > 1 ? kb : kb - b * P.kb_per_img;
+                    tc::mbar_wait(empty + stage, phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    tc::mbar_arrive_expect_tx(full + stage, (uint32_t)stage_bytes);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)   // A: Vhat[b*hw + kl*64 .. +64][dt*128 + j*64 .. +64]
+                        tc::tma_load_2d(sa + j * DT_KB * 128, &tmV, full + stage, dt * DT_BM + j * 64,
+                                        b * P.hw + kl * DT_KB);
+                    // B: G[b][nt*NB .. +NB][kl*64 .. +64]   (K-major; OOB pixels / classes read as 0)
+                    tc::tma_load_3d(sa + DT_A_BYTES, &tmG, full + stage, kl * DT_KB, nt * P.NB, b);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = tc::make_idesc_bf16(DT_BM, P.NB, 1, 0);
+                int stage = 0; uint32_t phase = 0;
+                for (int kb = kb_lo; kb < kb_hi; ++kb) {
+                    tc::mbar_wait(full + stage, phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = base_u32 + stage * stage_bytes;
+                    const uint64_t adesc = tc::make_smem_desc(sa, DT_KB * 128, 1024);        // MN-major A
+                    const uint64_t bdesc = tc::make_smem_desc(sa + DT_A_BYTES, 16, 1024);    // K-major B
+#pragma unroll
+                    for (int k = 0; k < DT_KB / 16; ++k)   // A: +16 K-rows = 2 atoms = 2048 B; B: +32 B
+                        tc::umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(2 * k), idesc,
+                                      (kb != kb_lo) || (k != 0));
+                    tc::umma_commit(empty + stage);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+                tc::umma_commit(tfull);
+            }
+        } else {
+            const int q = warp & 3;
+            const int d = dt * DT_BM + q * 32 + lane;
+            tc::mbar_wait(tfull, 0);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            float* out = P.dt_raw + (size_t)set * P.C * P.D + d;
+            const int c0 = nt * P.NB;
+            for (int col = 0; col < P.NB; col += 16) {
+                if (c0 + col >= P.C) break;
+                uint32_t acc[16];
+                tc::tmem_ld16(taddr + col, acc);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = c0 + col + j;
+                    if (c < P.C && d < P.D) atomicAdd(out + (size_t)c * P.D, __uint_as_float(acc[j]));
+                }
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, 256);
+    }
+}
+
+// dT[set][c][:] += inv_t * g * (s * dT_raw - that * rt)      (normalise-backward of the prototypes)
+__global__ void __launch_bounds__(256)
+k1b_dt_finish_kernel(const float* __restrict__ dt_raw, const float* __restrict__ rt,
+                     const __nv_bfloat16* __restrict__ t_hat, const float* __restrict__ inv_t,
+                     const float* __restrict__ grad_scale, int n_sets, int C, int C_pad, int D, int normalize,
+                     float scale, float* __restrict__ grad_t) {
+    const float gs = grad_scale ? __ldg(grad_scale) : 1.f;
+    const long long total = (long long)n_sets * C * D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int d = (int)(i % D);
+        const long long sc = i / D;
+        const int c = (int)(sc % C);
+        const int set = (int)(sc / C);
+        float v = scale * dt_raw[i];
+        if (normalize) {
+            const float th = __bfloat162float(t_hat[((size_t)set * C_pad + c) * D + d]);
+            v = (v - th * rt[(size_t)set * C + c]) * inv_t[(size_t)set * C + c];
+        }
+        grad_t[i] += gs * v;
+    }
+}
+
+struct BwdWs { size_t r, rt, dt_raw, total; };
+static BwdWs bwd_layout(int B, int hw, int D, int n_sets, int C) {
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    BwdWs w; size_t o = 0;
+    w.r = o; o += al((size_t)B * hw * 4);
+    w.rt = o; o += al((size_t)n_sets * C * 4);
+    w.dt_raw = o; o += al((size_t)n_sets * C * D * 4);
+    w.total = o;
+    return w;
+}
+
+}  // namespace lc2is
+
 using namespace lc2is;
-extern "C" int64_t lc2is_cosine_logits_bwd_workspace(int, int, int, int, int) { return 256; }
-extern "C" int lc2is_cosine_logits_bwd(const void*, const float*, const void*, const float*, const void*, const float*,
-                                       int, int, int, int, int, int, float, const float*, void*, int, float*, void*,
-                                       lc2is_stream_t) {
-    return fail(LC2IS_ERR_UNSUPPORTED, "cosine_logits_bwd not built yet%s");
+
+extern "C" int64_t lc2is_cosine_logits_bwd_workspace(int B, int hw, int D, int n_sets, int C) {
+    return (int64_t)bwd_layout(B, hw, D, n_sets, C).total;
+}
+
+extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits_bf16, const float* d_logits,
+                                       const void* d_v_hat, const float* d_inv_norm_v,
+                                       const void* d_t_hat, const float* d_inv_norm_t,
+                                       int B, int hw, int D, int n_sets, int C,
+                                       int normalize, float logit_scale, const float* d_grad_scale,
+                                       void* d_grad_v, int gv_dtype, float* d_grad_t,
+                                       void* d_ws, lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (B < 0 || hw <= 0 || C <= 0 || D <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (B == 0) return 0;
+    if (!d_grad_logits_bf16 || !d_logits || !d_v_hat || !d_inv_norm_v || !d_t_hat || !d_ws)
+        return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (normalize && !d_inv_norm_t) return fail(LC2IS_ERR_ARG, "inv_norm_t required when normalize%s");
+    if (D % 64) return fail(LC2IS_ERR_SHAPE, "D must be a multiple of 64%s");
+    if (hw % 8) return fail(LC2IS_ERR_SHAPE, "hw must be a multiple of 8 for the backward (TMA 16-byte strides); got %s%lld", "", hw);
+    if (n_sets != 1 && n_sets != B) return fail(LC2IS_ERR_SHAPE, "n_sets must be 1 or B%s");
+    if (gv_dtype != LC2IS_F32 && gv_dtype != LC2IS_BF16) return fail(LC2IS_ERR_ARG, "gv_dtype%s");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int C_pad = class_pad(C);
+    const BwdWs L = bwd_layout(B, hw, D, n_sets, C);
+    uint8_t* ws = (uint8_t*)d_ws;
+    float* d_r = (float*)(ws + L.r);
+    float* d_rt = (float*)(ws + L.rt);
+    float* d_dtraw = (float*)(ws + L.dt_raw);
+    LC2IS_CUDA(cudaMemsetAsync(ws + L.rt, 0, L.total - L.rt, st));          // rt and dt_raw
+
+    // ---- projections r, rt -----------------------------------------------------------------------
+    if (normalize) {
+        dim3 grid((hw + 255) / 256, B);
+        k1b_prep_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)d_grad_logits_bf16, d_logits, B, C, C_pad, hw,
+                                              n_sets, d_r, d_rt);
+        LC2IS_CHECK_LAUNCH("k1b_prep_kernel");
+    }
+    // ---- dV ----------------------------------------------------------------------------------------
+    if (d_grad_v) {
+        DvParams P;
+        P.grad_v = d_grad_v; P.v_hat = (const __nv_bfloat16*)d_v_hat; P.inv_v = d_inv_norm_v; P.r = d_r;
+        P.grad_scale = d_grad_scale; P.B = B; P.hw = hw; P.D = D; P.C_pad = C_pad; P.n_sets = n_sets;
+        P.tiles_per_img = (hw + DV_BM - 1) / DV_BM;
+        P.n_ntiles = (D + DV_BN - 1) / DV_BN;
+        P.num_kb = C_pad / DV_KB;
+        P.stages = P.num_kb * 2 < DV_MAX_STAGES ? P.num_kb * 2 : DV_MAX_STAGES;
+        if (P.stages < 2) P.stages = 2;
+        P.normalize = normalize; P.out_f32 = gv_dtype == LC2IS_F32; P.scale = logit_scale;
+        CUtensorMap tmG, tmT;
+        if (int e = make_tmap_3d_bf16(&tmG, d_grad_logits_bf16, B, C_pad, hw, DV_KB, 64)) return e;
+        if (int e = make_tmap_2d_bf16(&tmT, d_t_hat, (uint64_t)n_sets * C_pad, D, DV_KB, 64)) return e;
+        size_t smem = (size_t)P.stages * DV_STAGE + 1024 + 256;
+        if (smem < 120 * 1024) smem = 120 * 1024;
+        LC2IS_CUDA(cudaFuncSetAttribute(k1b_dv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int total_tiles = B * P.tiles_per_img * P.n_ntiles;
+        int grid = sm_count() < total_tiles ? sm_count() : total_tiles;
+        k1b_dv_kernel<<<grid, KB_THREADS, smem, st>>>(tmG, tmT, P);
+        LC2IS_CHECK_LAUNCH("k1b_dv_kernel");
+    }
+    // ---- dT ----------------------------------------------------------------------------------------
+    if (d_grad_t) {
+        DtParams P;
+        P.dt_raw = d_dtraw; P.B = B; P.hw = hw; P.D = D; P.C = C; P.C_pad = C_pad; P.n_sets = n_sets;
+        const int n0 = (C_pad + 255) / 256;
+        P.NB = ((C_pad + n0 - 1) / n0 + 15) / 16 * 16;
+        P.n_ntiles = (C_pad + P.NB - 1) / P.NB;
+        P.n_dtiles = (D + DT_BM - 1) / DT_BM;
+        P.kb_per_img = (hw + DT_KB - 1) / DT_KB;
+        const int base_items = n_sets * P.n_dtiles * P.n_ntiles;
+        const int total_kb = (n_sets > 1 ? 1 : B) * P.kb_per_img;
+        int ksplit = sm_count() / base_items;
+        if (ksplit < 1) ksplit = 1;
+        if (ksplit > total_kb) ksplit = total_kb;
+        P.ksplit = ksplit;
+        const int stage_bytes = DT_A_BYTES + P.NB * 128;
+        int stages = (200 * 1024) / stage_bytes;
+        if (stages > DT_MAX_STAGES) stages = DT_MAX_STAGES;
+        P.stages = stages;
+        CUtensorMap tmV, tmG;
+        if (int e = make_tmap_2d_bf16(&tmV, d_v_hat, (uint64_t)B * hw, D, DT_KB, 64)) return e;
+        if (int e = make_tmap_3d_bf16(&tmG, d_grad_logits_bf16, B, C_pad, hw, P.NB, 64)) return e;
+        size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+        if (smem < 120 * 1024) smem = 120 * 1024;
+        LC2IS_CUDA(cudaFuncSetAttribute(k1b_dt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1b_dt_kernel<<<base_items * ksplit, KB_THREADS, smem, st>>>(tmV, tmG, P);
+        LC2IS_CHECK_LAUNCH("k1b_dt_kernel");
+        long long total = (long long)n_sets * C * D;
+        long long blocks = (total + 255) / 256;
+        if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+        k1b_dt_finish_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_dtraw, d_rt, (const __nv_bfloat16*)d_t_hat,
+                                                               d_inv_norm_t, d_grad_scale, n_sets, C, C_pad, D,
+                                                               normalize, logit_scale, d_grad_t);
+        LC2IS_CHECK_LAUNCH("k1b_dt_finish_kernel");
+    }
+    return 0;
 }

@@ -450,9 +450,9 @@ using namespace lc2is;
 extern "C" int lc2is_count_valid(const int64_t* d_labels, int64_t n, int64_t ignore_index,
                                  int64_t* d_n_valid, lc2is_stream_t stream) {
     if (int e = ensure_device()) return e;
-    if (!d_labels || !d_n_valid) return fail(LC2IS_ERR_ARG, "null pointer%s");
     if (n < 0) return fail(LC2IS_ERR_SHAPE, "negative n%s");
     if (n == 0) return 0;
+    if (!d_labels || !d_n_valid) return fail(LC2IS_ERR_ARG, "null pointer%s");
     if ((uintptr_t)d_labels % 16) return fail(LC2IS_ERR_ARG, "labels must be 16-byte aligned%s");
     long long blocks = (n / 2 + 255) / 256;
     long long cap = (long long)sm_count() * 8;
@@ -486,8 +486,9 @@ extern "C" int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_la
                                          double* d_loss_sum, float* d_grad_low, void* d_grad_low_bf16,
                                          lc2is_stream_t stream) {
     if (int e = ensure_device()) return e;
-    if (!d_low || !d_labels || !d_loss_sum) return fail(LC2IS_ERR_ARG, "null pointer%s");
     if (B < 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (B == 0) return 0;
+    if (!d_low || !d_labels || !d_loss_sum) return fail(LC2IS_ERR_ARG, "null pointer%s");
     if (d_grad_low_bf16 && !d_grad_low)
         return fail(LC2IS_ERR_ARG, "grad_low_bf16 needs the fp32 grad_low buffer as well%s");
     if (B == 0) return 0;

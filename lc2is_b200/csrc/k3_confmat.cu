@@ -416,10 +416,10 @@ extern "C" int lc2is_argmax_confmat(const void* d_logits, int dtype, int N, int 
                                     int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                     lc2is_stream_t stream) {
     if (int e = ensure_device()) return e;
-    if (!d_logits || !d_labels || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
     if (N < 0 || C <= 0 || H <= 0 || W <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
-    if (int e = check_labels_ratio(H, W, lh, lw)) return e;
     if (N == 0) return 0;
+    if (!d_logits || !d_labels || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (int e = check_labels_ratio(H, W, lh, lw)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int use_hist = C <= K3_SMEM_HIST_MAX_C;
     const size_t smem = use_hist ? (size_t)C * C * sizeof(int) : 0;
@@ -460,11 +460,11 @@ extern "C" int lc2is_argmax_confmat_lowres(const float* d_low, int N, int C, int
                                            int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                            lc2is_stream_t stream) {
     if (int e = ensure_device()) return e;
-    if (!d_low || !d_labels || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
     if (N < 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
     if (mode != LC2IS_BILINEAR && mode != LC2IS_BICUBIC) return fail(LC2IS_ERR_ARG, "bad mode%s");
-    if (int e = check_labels_ratio(H, W, lh, lw)) return e;
     if (N == 0) return 0;
+    if (!d_low || !d_labels || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (int e = check_labels_ratio(H, W, lh, lw)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int use_hist = C <= K3_SMEM_HIST_MAX_C;
     const size_t smem = use_hist ? (size_t)C * C * sizeof(int) : 0;
