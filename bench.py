@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py - the head hot path on N B200s (one process per GPU; torchrun for N > 1).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle)
+
+A "step" is one pass of the hot path over one synthetic batch (BASELINE.json configs[1]):
+B=16 images per GPU at 512^2, D=512, C=150, bf16 GEMM operands / fp32 accumulate:
+cosine logits (K0+K1) -> fused bilinear-upsample + softmax-CE fwd/bwd (K2) -> logits backward
+(K1b) -> argmax / confusion matrix / mIoU (K3); with N > 1 the valid-pixel count, the head-gradient
+bucket and the int64 confusion matrix are all-reduced over NCCL every step (weak scaling).
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ADE20K-shape 512^2 images/sec (logits+loss+mIoU)"
+UNIT = "images/s"
+GEOM = {"A": (32, 32), "B": (128, 128)}          # low-res grid; SURVEY 8: G-A aux head x16, G-B main head x4
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=None)
+    p.add_argument("--warmup", type=int, default=None)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--geometry", default="A", choices=list(GEOM))
+    p.add_argument("--batch", type=int, default=16, help="images per GPU")
+    p.add_argument("--classes", type=int, default=150)
+    p.add_argument("--no-backward", action="store_true")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def workload_name(a, h, w):
+    return (f"cfg2: text_patch logits + fused upsample/softmax-CE fwd/bwd + argmax/confmat mIoU, "
+            f"B={a.batch}/GPU, {h}x{w}->512x512 (x{512 // h}), D=512, C={a.classes}, ignore_index=0")
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Polls NVML (SM clock, throttle reasons) while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:  # noqa: BLE001
+            return local_rank
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_reference_time(B, h, w, C, steps, warmup, threads=None):
+    """Times oracle.head_step (the reference's lines on CPU, fp32) on a B-image sample."""
+    import torch
+    from lc2is_b200 import synthetic
+    from oracle import head_oracle as O
+    if threads:
+        torch.set_num_threads(threads)
+    v = synthetic.make_patch_embeddings(B, h * w, 512, dtype=torch.float32)
+    t = synthetic.make_prototypes(C, 512)
+    labels = synthetic.make_labels(B, 512, 512, C)
+    for _ in range(warmup):
+        O.head_step(v, t, labels, ignore_index=0, n_cls=C, hw_shape=(h, w))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.head_step(v, t, labels, ignore_index=0, n_cls=C, hw_shape=(h, w))
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dt, torch.get_num_threads()
+
+
+def run_reference(a):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle: reference lines
+    restated with live torch ops; the reference is pure Python and cannot run as shipped - SURVEY 0) on
+    all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    h, w = GEOM[a.geometry]
+    steps = a.steps if a.steps is not None else 5
+    warmup = a.warmup if a.warmup is not None else 1
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = 2
+    t1, _ = cpu_reference_time(Bs, h, w, a.classes, 1, 0, cores)          # probe
+    if t1 * (steps + warmup) > 150 and Bs > 1:
+        Bs = 1
+    dt, thr = cpu_reference_time(Bs, h, w, a.classes, steps, warmup, cores)
+    val = Bs / dt
+    sample = f"{Bs} images per step of the same workload (oracle.head_step, fp32, torch CPU)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a, h, w), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from lc2is_b200 import _lib, dp, synthetic
+    from lc2is_b200.step import HeadStep, HostStep
+
+    rank, world, local_rank = dp.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lc2is_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    steps = a.steps if a.steps is not None else 200
+    warmup = a.warmup if a.warmup is not None else 20
+    warmup = max(warmup, 3)
+    h, w = GEOM[a.geometry]
+    B, C, D, H, W = a.batch, a.classes, 512, 512, 512
+    backward = not a.no_backward
+
+    # ---- inputs: rotate over enough distinct sets that a step's inputs never sit in the 126 MB L2
+    set_bytes = B * h * w * D * 2 + B * H * W * 8
+    nset = max(2, -(-2 * L2_BYTES // set_bytes))
+    t_host = synthetic.make_prototypes(C, D)
+    host_sets = []
+    for i in range(nset):
+        hv = synthetic.make_patch_embeddings(B, h * w, D, seed=synthetic.SEED + 97 * (rank * nset + i)).pin_memory()
+        hl = synthetic.make_labels(B, H, W, C, seed=synthetic.SEED + 97 * (rank * nset + i), ignore_frac=0.1).pin_memory()
+        host_sets.append((hv, hl))
+    dev_sets = [(hv.to(dev), hl.to(dev)) for hv, hl in host_sets]
+    t_dev = t_host.to(dev)
+    t_pin = t_host.pin_memory()
+
+    step = HeadStep(B, h, w, H, W, C, D, ignore_index=0, backward=backward, device=dev, distributed=world > 1)
+    k2_pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident timing -----------------------------------------------------------------------
+    for i in range(warmup):
+        step(dev_sets[i % nset][0], t_dev, dev_sets[i % nset][1])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    barrier()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    ev0.record()
+    for i in range(steps):
+        step.k2_events = k2_pairs[i]
+        v_i, l_i = dev_sets[(warmup + i) % nset]
+        step(v_i, t_dev, l_i)
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    barrier()
+    step.k2_events = None
+    launches = _lib.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    k2_ms = statistics.mean(s.elapsed_time(e) for s, e in k2_pairs)
+    tm = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total = float(tm)
+    ms_per_step = ms_total / steps
+    value = world * B * steps / (ms_total * 1e-3)
+    loss_val = float(step.loss)
+    miou = None
+    try:
+        from lc2is_b200 import metrics
+        miou = float(metrics.miou_from_confmat(step.confmat, 0))
+    except Exception:  # noqa: BLE001
+        pass
+    sampler.join(timeout=1)
+    clocks = sampler.result()
+
+    # ---- end to end: host (pinned) buffers through the C-ABI host entry, H2D/D2H inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        hstep = HostStep(B, h, w, H, W, C, D, ignore_index=0, backward=backward, device=dev)
+        cm_dev = torch.zeros(C, C, dtype=torch.int64, device=dev)
+        e_steps = max(3, min(steps, 50))
+
+        def host_iter(i):
+            hv, hl = host_sets[i % nset]
+            hstep(hv, t_pin, hl)
+            if world > 1:                                   # DP: all-reduce the step's integer results
+                cm_dev.copy_(hstep.out_confmat, non_blocking=True)
+                dist.all_reduce(cm_dev)
+        for i in range(3):
+            host_iter(i)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(e_steps):
+            host_iter(3 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        ms = max(e0.elapsed_time(e1), wall * 1e3)            # the call blocks the host: take the larger clock
+        tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * e_steps / (float(tm) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": hstep.h2d_bytes, "d2h_bytes_per_step": hstep.d2h_bytes,
+               "steps": e_steps, "ms_per_step": float(tm) / e_steps,
+               "api": "lc2is_head_step_host (pinned host buffers in, loss/n_valid/confmat out)"}
+        assert int(hstep.out_n_valid) > 0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K2: fused upsample + CE fwd/bwd) ------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    k2_bytes = 2 * B * C * h * w * 4 + B * H * W * 8 + 8
+    achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
+    roofline = {"kernel": "k2_fast_kernel (lc2is_upsample_ce_fwd_bwd: memset + fused upsample/CE fwd+bwd)",
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": k2_bytes, "kernel_us": k2_ms * 1e3,
+                "note": "K2 is instruction-bound (ex2 + fp32 issue), not HBM-bound: see DESIGN.md; "
+                        f"{B * C * H * W / (k2_ms * 1e-3) / 1e12:.3f} T softmax-elements/s"}
+
+    cpu_baseline = None
+    if not a.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        dt, thr = cpu_reference_time(2, h, w, C, 2, 1, cores)
+        cpu_baseline = {"value": 2 / dt, "unit": UNIT, "cores": thr, "kind": "port",
+                        "sample": "2 images per step of the same workload, 2 timed steps after 1 warm-up "
+                                  "(oracle.head_step: reference lines on torch CPU, fp32)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": workload_name(a, h, w), "global_batch": world * B, "parallelism": f"dp{world}",
+                   "backward": backward,
+                   "l2": f"inputs rotate over {nset} distinct sets ({nset * set_bytes / 2**20:.0f} MiB) > 126 MiB L2; no flush"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "check": {"loss": loss_val, "mIoU": miou, "n_valid": int(step.n_valid)},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,6 @@ namespace lc2is {
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
-constexpr int K2_TBY = 8;             // 4x4 blocks per CTA in y
 constexpr float S_MIN = 1e-30f;       // below this the shared shift lost precision -> slow path
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
@@ -66,51 +65,72 @@ __global__ void k2_count_valid_kernel(const long long* __restrict__ labels, long
 }
 
 // ---------------------------------------------------------------------------------------------
+// Geometry of the fast path.  A GROUP is the set of bps x bps 4x4-pixel blocks (bps = s/4) that
+// interpolate between the same 2x2 source cells: group (gy,gx) has taps (ky,kx) = (gy-1, gx-1)
+// .. (ky+1, kx+1), index-clamped to the image.  There are (h+1) x (w+1) groups per image.  The
+// bps*bps threads of a group are consecutive lanes of one warp, so their four tap contributions
+// are summed with a butterfly of warp shuffles and leave the SM as four L2 float reductions.
 struct K2Params {
     const float* low;            // [B,C,h,w]
     const long long* labels;     // [B,H,W]
-    float* grad_low;             // [B,C,h,w] (pre-zeroed; accumulated with global atomics) or null
+    float* grad_low;             // [B,C,h,w] (pre-zeroed; accumulated with global reductions) or null
     double* loss_sum;
     const float* grad_scale;     // device scalar or null
     long long ignore_index;
     int B, C, h, w, H, W;
-    int s, off, nby, nbx, q, bps; // block geometry
-    int tbx;                      // blocks per CTA in x (8 or 16); threads = K2_TBY * tbx
-    int ncy, ncx;                 // cells per tile
+    int s, off, q;                // scale, pixel offset of the block grid, block offset of group 0
+    int tgy, tgx;                 // groups per CTA
     float rs;
 };
 
-constexpr int K2_CH = 8;          // classes per scatter chunk
-
-__device__ __forceinline__ int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 __device__ __forceinline__ int clampi2(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// Shared fp32 atomics are CAS loops on sm_100 (SASS: ATOMS.CAST.SPIN), so the gradient scatter
-// avoids them: for a chunk of K2_CH classes every thread stores its four tap contributions into
-// PRIVATE slots priv[class][tap][thread]; after a barrier each (class, cell) of the tile is
-// summed by one thread from the slots of the blocks that touch it (known from the geometry)
-// and added to global memory with one native L2 float reduction.
+// Sum (a,b,c,d) over the LPG consecutive lanes of a group.  After the call lane u of the group
+// holds in `a` the total of value number (u * 4 / LPG) [LPG >= 4], i.e. the first quarter of the
+// lanes hold sum(a), the second sum(b), ... ; for LPG == 1 nothing happens.
+template <int LPG>
+__device__ __forceinline__ void group_reduce4(float& a, float& b, float& c, float& d, int u) {
+    if constexpr (LPG >= 4) {
+        // step 1: halves exchange pairs -> lower half keeps (a,b), upper half keeps (c,d)
+        const bool up = u & (LPG / 2);
+        float s0 = up ? a : c, s1 = up ? b : d;          // what this lane gives away
+        float k0 = up ? c : a, k1 = up ? d : b;          // what it keeps
+        k0 += __shfl_xor_sync(0xffffffffu, s0, LPG / 2);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, LPG / 2);
+        // step 2: quarters -> one value per lane
+        const bool up2 = u & (LPG / 4);
+        float g = up2 ? k0 : k1;
+        float k = up2 ? k1 : k0;
+        k += __shfl_xor_sync(0xffffffffu, g, LPG / 4);
+#pragma unroll
+        for (int o = LPG / 8; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
+        a = k;
+    }
+}
+
+template <int BPS>
 __global__ void __launch_bounds__(128)
 k2_fast_kernel(const K2Params P) {
+    constexpr int LPG = BPS * BPS;                          // lanes (threads) per group
     extern __shared__ float smem[];
     const int C = P.C;
-    const int ncell = P.ncy * P.ncx;
-    const int cs = ncell;                                  // class stride in the tile
+    const int ncx = P.tgx + 1, ncy = P.tgy + 1;
+    const int ncell = ncy * ncx;
+    const int cs = ncell;                                   // class stride in the tile
     const int nthr = blockDim.x;
-    float* st = smem;                                      // source tile  [C][ncy][ncx]
-    float* priv = smem + (size_t)C * cs;                   // [K2_CH][4][nthr]
-    float* cellmax = priv + (size_t)K2_CH * 4 * nthr;      // [ncell]
+    float* st = smem;                                       // source tile  [C][ncy][ncx]
+    float* cellmax = smem + (size_t)C * cs;                 // [ncell]
     __shared__ float red[4];
 
     const int n = blockIdx.z;
-    const int BY0 = blockIdx.y * K2_TBY, BX0 = blockIdx.x * P.tbx;
-    const int cy0 = floordiv(BY0 - P.q, P.bps), cx0 = floordiv(BX0 - P.q, P.bps);
+    const int GY0 = blockIdx.y * P.tgy, GX0 = blockIdx.x * P.tgx;
+    const int cy0 = GY0 - 1, cx0 = GX0 - 1;                 // first cell of the tile (may be -1)
     const float* lowb = P.low + (size_t)n * C * P.h * P.w;
 
     // ---- stage the source tile ------------------------------------------------------------------
     for (int idx = threadIdx.x; idx < C * ncell; idx += nthr) {
         int c = idx / ncell, r = idx - c * ncell;
-        int i = r / P.ncx, j = r - i * P.ncx;
+        int i = r / ncx, j = r - i * ncx;
         int gy = cy0 + i, gx = cx0 + j;
         if (gy >= 0 && gy < P.h && gx >= 0 && gx < P.w)
             cp_async4(st + idx, lowb + ((size_t)c * P.h + gy) * P.w + gx);
@@ -127,11 +147,15 @@ k2_fast_kernel(const K2Params P) {
     __syncthreads();
 
     // ---- per-thread block setup -------------------------------------------------------------------
-    const int tbx = threadIdx.x % P.tbx, tby = threadIdx.x / P.tbx;
-    const int bx = BX0 + tbx, by = BY0 + tby;
+    const int g = threadIdx.x / LPG, u = threadIdx.x % LPG;
+    const int tgy = g / P.tgx, tgx = g - tgy * P.tgx;
+    const int uy = u / BPS, ux = u % BPS;
+    const int ky = GY0 + tgy - 1, kx = GX0 + tgx - 1;       // top-left tap of the group (-1 .. h-1)
+    const int by = ky * BPS + P.q + uy, bx = kx * BPS + P.q + ux;
     const int y0 = 4 * by - P.off, x0 = 4 * bx - P.off;
     const float gs = P.grad_scale ? __ldg(P.grad_scale) : 1.f;
     const float rs = P.rs;
+    const bool group_in = ky < P.h && kx < P.w;             // group exists in this image
     int lab[16];
     bool any = false;
 #pragma unroll
@@ -140,20 +164,21 @@ k2_fast_kernel(const K2Params P) {
         for (int j = 0; j < 4; ++j) {
             int y = y0 + i, x = x0 + j;
             int l = -1;
-            if (bx < P.nbx && by < P.nby && y >= 0 && y < P.H && x >= 0 && x < P.W) {
+            if (group_in && y >= 0 && y < P.H && x >= 0 && x < P.W) {
                 long long t = __ldg(P.labels + ((size_t)n * P.H + y) * P.W + x);
                 if (t != P.ignore_index && t >= 0 && t < C) l = (int)t;
             }
             lab[i * 4 + j] = l;
             any |= l >= 0;
         }
-    const int ky = floordiv(by - P.q, P.bps), kx = floordiv(bx - P.q, P.bps);
+    // clamped tap cells (global) and their offsets in the tile
+    const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
+    const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);
     int oa = 0, ob = 0, oc = 0, od = 0;
     float ly0 = 0.f, lx0 = 0.f, M = 0.f;
-    if (any) {
-        const int ya = clampi2(ky, 0, P.h - 1) - cy0, yb = clampi2(ky + 1, 0, P.h - 1) - cy0;
-        const int xa = clampi2(kx, 0, P.w - 1) - cx0, xb = clampi2(kx + 1, 0, P.w - 1) - cx0;
-        oa = ya * P.ncx + xa; ob = ya * P.ncx + xb; oc = yb * P.ncx + xa; od = yb * P.ncx + xb;
+    if (group_in) {
+        oa = (Ya - cy0) * ncx + (Xa - cx0); ob = (Ya - cy0) * ncx + (Xb - cx0);
+        oc = (Yb - cy0) * ncx + (Xa - cx0); od = (Yb - cy0) * ncx + (Xb - cx0);
         // lambda of the block's first row / column ((y0+0.5)*rs-0.5-ky is exact for power-of-2 s)
         ly0 = ((float)y0 + 0.5f) * rs - 0.5f - (float)ky;
         lx0 = ((float)x0 + 0.5f) * rs - 0.5f - (float)kx;
@@ -164,12 +189,11 @@ k2_fast_kernel(const K2Params P) {
 
     // ---- pass A: S(i,j) = sum_c exp(l_c(i,j) - M) ----------------------------------------------------
     float S[16];                      // becomes U = g / S after pass A
-    float Mp[16];                     // per-pixel shift (slow path only; otherwise all = M)
     bool slow = false;
     float loss = 0.f;
-    if (any) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) S[i] = 0.f;
+    for (int i = 0; i < 16; ++i) S[i] = 0.f;
+    if (any) {
 #pragma unroll 2
         for (int c = 0; c < C; ++c) {
             const float* p = st + c * cs;
@@ -197,156 +221,150 @@ k2_fast_kernel(const K2Params P) {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
             if (lab[i] >= 0) slow |= !((S[i] >= S_MIN) && (S[i] <= 3.0e38f));
-        if (slow) {
-            // exact per-pixel max and sum (logits spanning > ~80 inside one cell, inf/NaN, ...)
-            for (int pix = 0; pix < 16; ++pix) {
-                const float ly = ly0 + (float)(pix >> 2) * rs, lx = lx0 + (float)(pix & 3) * rs;
-                float m = -INFINITY;
-                for (int c = 0; c < C; ++c) {
-                    const float* p = st + c * cs;
-                    float L = fmaf(ly, p[oc] - p[oa], p[oa]), R = fmaf(ly, p[od] - p[ob], p[ob]);
-                    m = fmaxf(m, fmaf(lx, R - L, L));
-                }
-                float sum = 0.f;
-                for (int c = 0; c < C; ++c) {
-                    const float* p = st + c * cs;
-                    float L = fmaf(ly, p[oc] - p[oa], p[oa]), R = fmaf(ly, p[od] - p[ob], p[ob]);
-                    sum += ex2f((fmaf(lx, R - L, L) - m) * LOG2E);
-                }
+    }
+    // The exact fallback is taken by the whole warp (the scatter pass below is warp-collective).
+    slow = __any_sync(0xffffffffu, slow);
+    float Mp[16];                     // per-pixel softmax shift (only differs from M on the slow path)
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                    if (i == pix) { Mp[i] = m; S[i] = sum; }
+    for (int i = 0; i < 16; ++i) Mp[i] = M;
+    if (slow && any) {
+        // exact per-pixel max and sum (logits spanning > ~80 inside one cell, inf/NaN, ...)
+#pragma unroll 1
+        for (int pix = 0; pix < 16; ++pix) {
+            const float ly = ly0 + (float)(pix >> 2) * rs, lx = lx0 + (float)(pix & 3) * rs;
+            float m = -INFINITY;
+            for (int c = 0; c < C; ++c) {
+                const float* p = st + c * cs;
+                float L = fmaf(ly, p[oc] - p[oa], p[oa]), R = fmaf(ly, p[od] - p[ob], p[ob]);
+                m = fmaxf(m, fmaf(lx, R - L, L));
             }
-        } else {
+            float sum = 0.f;
+            for (int c = 0; c < C; ++c) {
+                const float* p = st + c * cs;
+                float L = fmaf(ly, p[oc] - p[oa], p[oa]), R = fmaf(ly, p[od] - p[ob], p[ob]);
+                sum += ex2f((fmaf(lx, R - L, L) - m) * LOG2E);
+            }
 #pragma unroll
-            for (int i = 0; i < 16; ++i) Mp[i] = M;
+            for (int i = 0; i < 16; ++i)
+                if (i == pix) { Mp[i] = m; S[i] = sum; }
         }
-        // ---- loss and per-pixel gradient scale U = g / S ----------------------------------------------
+    }
+    // ---- loss and per-pixel gradient scale U = g / S --------------------------------------------------
+    if (any) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int t = lab[i * 4 + j];
-                float u = 0.f;
+                float uu = 0.f;
                 if (t >= 0) {
                     const float ly = ly0 + (float)i * rs, lx = lx0 + (float)j * rs;
                     const float* p = st + t * cs;
                     const float L = fmaf(ly, p[oc] - p[oa], p[oa]), R = fmaf(ly, p[od] - p[ob], p[ob]);
                     const float lt = fmaf(lx, R - L, L);
                     loss += logf(S[i * 4 + j]) + Mp[i * 4 + j] - lt;
-                    u = gs / S[i * 4 + j];
+                    uu = gs / S[i * 4 + j];
                 }
-                S[i * 4 + j] = u;
+                S[i * 4 + j] = uu;
             }
     }
 
-    // ---- pass B: scatter (softmax - onehot) * g through the taps, K2_CH classes at a time -----------
+    // ---- pass B: scatter (softmax - onehot) * g through the taps ---------------------------------------
+    // Warp-collective: every lane runs the class loop (lanes without valid pixels contribute zeros).
     float* gb = P.grad_low ? P.grad_low + (size_t)n * C * P.h * P.w : nullptr;
-    if (gb) {
-        for (int c0 = 0; c0 < C; c0 += K2_CH) {
-            const int chn = min(K2_CH, C - c0);
+    const bool warp_any = __any_sync(0xffffffffu, any);
+    if (gb && warp_any) {
+        // which of the four totals this lane writes after the butterfly, and where
+        const int role = LPG >= 4 ? (u * 4) / LPG : 0;
+        const bool writer = LPG >= 4 ? (u % (LPG / 4 > 0 ? LPG / 4 : 1)) == 0 : true;
+        const int cellY = (role & 2) ? Yb : Ya, cellX = (role & 1) ? Xb : Xa;
+        float* gcell = gb + (size_t)cellY * P.w + cellX;
+        const size_t plane = (size_t)P.h * P.w;
+        int cur = 0x7fffffff;                              // smallest label among this thread's valid pixels
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (lab[i] >= 0) cur = min(cur, lab[i]);
+        for (int c = 0; c < C; ++c) {
+            float A = 0.f, Bv = 0.f, Cv = 0.f, Dv = 0.f;
             if (any) {
-                for (int cl = 0; cl < chn; ++cl) {
-                    const float* p = st + (c0 + cl) * cs;
-                    const float a = p[oa], b = p[ob], cc = p[oc], d = p[od];
-                    float G, Gx, Gy, Gxy;
-                    if (!slow) {
-                        const float da = cc - a, db = d - b, dd = db - da;
-                        const float L0 = fmaf(ly0, da, a), R0 = fmaf(ly0, db, b);
-                        const float rl = R0 - L0;
-                        const float l00 = fmaf(lx0, rl, L0);
-                        const float q0 = ex2f(rl * k1);
-                        const float pp = ex2f(fmaf(lx0, dd, da) * k1);
-                        const float tt = ex2f(dd * k2);
-                        float e0 = ex2f(fmaf(l00, LOG2E, -Mk));
-                        float qi = q0;
-                        float r[4], rx[4];
+                const float* p = st + c * cs;
+                const float a = p[oa], b = p[ob], cc = p[oc], d = p[od];
+                float G, Gx, Gy, Gxy;
+                if (!slow) {
+                    const float da = cc - a, db = d - b, dd = db - da;
+                    const float L0 = fmaf(ly0, da, a), R0 = fmaf(ly0, db, b);
+                    const float rl = R0 - L0;
+                    const float l00 = fmaf(lx0, rl, L0);
+                    const float q0 = ex2f(rl * k1);
+                    const float pp = ex2f(fmaf(lx0, dd, da) * k1);
+                    const float tt = ex2f(dd * k2);
+                    float e0 = ex2f(fmaf(l00, LOG2E, -Mk));
+                    float qi = q0;
+                    float r[4], rx[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float e = e0;
-                            const float g0 = e * S[i * 4 + 0];
-                            e *= qi; const float g1 = e * S[i * 4 + 1];
-                            e *= qi; const float g2 = e * S[i * 4 + 2];
-                            e *= qi; const float g3 = e * S[i * 4 + 3];
-                            r[i] = (g0 + g1) + (g2 + g3);
-                            rx[i] = fmaf(3.f, g3, fmaf(2.f, g2, g1));
-                            e0 *= pp;
-                            qi *= tt;
-                        }
-                        G = (r[0] + r[1]) + (r[2] + r[3]);
-                        Gy = fmaf(3.f, r[3], fmaf(2.f, r[2], r[1]));
-                        Gx = (rx[0] + rx[1]) + (rx[2] + rx[3]);
-                        Gxy = fmaf(3.f, rx[3], fmaf(2.f, rx[2], rx[1]));
-                    } else {
-                        G = Gx = Gy = Gxy = 0.f;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float ly = ly0 + (float)i * rs, lx = lx0 + (float)j * rs;
-                                const float L = fmaf(ly, cc - a, a), R = fmaf(ly, d - b, b);
-                                const float g = ex2f((fmaf(lx, R - L, L) - Mp[i * 4 + j]) * LOG2E) * S[i * 4 + j];
-                                G += g; Gx += (float)j * g; Gy += (float)i * g; Gxy += (float)(i * j) * g;
-                            }
+                    for (int i = 0; i < 4; ++i) {
+                        float e = e0;
+                        const float g0 = e * S[i * 4 + 0];
+                        e *= qi; const float g1 = e * S[i * 4 + 1];
+                        e *= qi; const float g2 = e * S[i * 4 + 2];
+                        e *= qi; const float g3 = e * S[i * 4 + 3];
+                        r[i] = (g0 + g1) + (g2 + g3);
+                        rx[i] = fmaf(3.f, g3, fmaf(2.f, g2, g1));
+                        e0 *= pp;
+                        qi *= tt;
                     }
-                    const float X = fmaf(rs, Gx, lx0 * G);                        // sum lambda_x g
-                    const float Y = fmaf(rs, Gy, ly0 * G);                        // sum lambda_y g
-                    const float XY = fmaf(ly0, X, rs * fmaf(rs, Gxy, lx0 * Gy));  // sum lambda_x lambda_y g
-                    float* pv = priv + (size_t)cl * 4 * nthr + threadIdx.x;
-                    pv[0] = (G - X) - (Y - XY);
-                    pv[nthr] = X - XY;
-                    pv[2 * nthr] = Y - XY;
-                    pv[3 * nthr] = XY;
-                }
-                // - g * onehot: thread-private read-modify-write of its own slots
+                    G = (r[0] + r[1]) + (r[2] + r[3]);
+                    Gy = fmaf(3.f, r[3], fmaf(2.f, r[2], r[1]));
+                    Gx = (rx[0] + rx[1]) + (rx[2] + rx[3]);
+                    Gxy = fmaf(3.f, rx[3], fmaf(2.f, rx[2], rx[1]));
+                } else {
+                    G = Gx = Gy = Gxy = 0.f;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int t = lab[i * 4 + j] - c0;
-                        if (t >= 0 && t < chn) {
+                        for (int j = 0; j < 4; ++j) {
                             const float ly = ly0 + (float)i * rs, lx = lx0 + (float)j * rs;
-                            float* pv = priv + (size_t)t * 4 * nthr + threadIdx.x;
-                            pv[0] -= gs * (1.f - ly) * (1.f - lx);
-                            pv[nthr] -= gs * (1.f - ly) * lx;
-                            pv[2 * nthr] -= gs * ly * (1.f - lx);
-                            pv[3 * nthr] -= gs * ly * lx;
+                            const float L = fmaf(ly, cc - a, a), R = fmaf(ly, d - b, b);
+                            const float gg = ex2f((fmaf(lx, R - L, L) - Mp[i * 4 + j]) * LOG2E) * S[i * 4 + j];
+                            G += gg; Gx += (float)j * gg; Gy += (float)i * gg; Gxy += (float)(i * j) * gg;
                         }
-                    }
-            } else {
-                for (int cl = 0; cl < chn; ++cl) {
-                    float* pv = priv + (size_t)cl * 4 * nthr + threadIdx.x;
-                    pv[0] = 0.f; pv[nthr] = 0.f; pv[2 * nthr] = 0.f; pv[3 * nthr] = 0.f;
+                }
+                const float X = fmaf(rs, Gx, lx0 * G);                        // sum lambda_x g
+                const float Y = fmaf(rs, Gy, ly0 * G);                        // sum lambda_y g
+                const float XY = fmaf(ly0, X, rs * fmaf(rs, Gxy, lx0 * Gy));  // sum lambda_x lambda_y g
+                A = (G - X) - (Y - XY); Bv = X - XY; Cv = Y - XY; Dv = XY;
+                // - g * onehot for the pixels whose target is this class.  `cur` is the smallest
+                // not-yet-handled label of this thread: one compare per class, the 16-way scan only on a hit.
+                if (c == cur) {
+                    int nxt = 0x7fffffff;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int t = lab[i * 4 + j];
+                            if (t == c) {
+                                const float ly = ly0 + (float)i * rs, lx = lx0 + (float)j * rs;
+                                A -= gs * (1.f - ly) * (1.f - lx); Bv -= gs * (1.f - ly) * lx;
+                                Cv -= gs * ly * (1.f - lx);        Dv -= gs * ly * lx;
+                            } else if (t > c) {
+                                nxt = min(nxt, t);
+                            }
+                        }
+                    cur = nxt;
                 }
             }
-            __syncthreads();
-            // reduction: one (class, cell) per work item
-            for (int it = threadIdx.x; it < chn * ncell; it += nthr) {
-                const int cl = it / ncell, r = it - cl * ncell;
-                const int i = r / P.ncx, j = r - i * P.ncx;
-                const int Yc = cy0 + i, Xc = cx0 + j;
-                if (Yc < 0 || Yc >= P.h || Xc < 0 || Xc >= P.w) continue;
-                float sum = 0.f;
-                const float* pc = priv + (size_t)cl * 4 * nthr;
-                for (int kyy = Yc - 1; kyy <= Yc; ++kyy)
-                    for (int dy = 0; dy < 2; ++dy) {
-                        if (clampi2(kyy + dy, 0, P.h - 1) != Yc) continue;
-                        const int b0 = max(max(kyy * P.bps + P.q, BY0), 0);
-                        const int b1 = min(min(kyy * P.bps + P.q + P.bps, BY0 + K2_TBY), P.nby);
-                        for (int kxx = Xc - 1; kxx <= Xc; ++kxx)
-                            for (int dx = 0; dx < 2; ++dx) {
-                                if (clampi2(kxx + dx, 0, P.w - 1) != Xc) continue;
-                                const int a0 = max(max(kxx * P.bps + P.q, BX0), 0);
-                                const int a1 = min(min(kxx * P.bps + P.q + P.bps, BX0 + P.tbx), P.nbx);
-                                const float* pr = pc + (dy * 2 + dx) * nthr;
-                                for (int bb = b0; bb < b1; ++bb)
-                                    for (int aa = a0; aa < a1; ++aa)
-                                        sum += pr[(bb - BY0) * P.tbx + (aa - BX0)];
-                            }
-                    }
-                if (sum != 0.f) atomicAdd(gb + ((size_t)(c0 + cl) * P.h + Yc) * P.w + Xc, sum);
+            group_reduce4<LPG>(A, Bv, Cv, Dv, u);
+            if constexpr (LPG >= 4) {
+                if (writer && A != 0.f) atomicAdd(gcell + (size_t)c * plane, A);
+            } else {
+                float* gp = gb + (size_t)c * plane;
+                if (any) {
+                    if (A != 0.f) atomicAdd(gp + (size_t)Ya * P.w + Xa, A);
+                    if (Bv != 0.f) atomicAdd(gp + (size_t)Ya * P.w + Xb, Bv);
+                    if (Cv != 0.f) atomicAdd(gp + (size_t)Yb * P.w + Xa, Cv);
+                    if (Dv != 0.f) atomicAdd(gp + (size_t)Yb * P.w + Xb, Dv);
+                }
             }
-            __syncthreads();
         }
     }
     // ---- loss reduction: warp -> CTA -> one double atomic ----------------------------------------------
@@ -496,7 +514,7 @@ extern "C" int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_la
     if (d_grad_low) LC2IS_CUDA(cudaMemsetAsync(d_grad_low, 0, (size_t)B * C * h * w * sizeof(float), st));
 
     int s = 0;
-    bool fast = fast_scale(h, w, H, W, &s);
+    bool fast = fast_scale(h, w, H, W, &s) && s <= 16;
     K2Params P;
     size_t smem = 0;
     if (fast) {
@@ -504,22 +522,23 @@ extern "C" int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_la
         P.low = d_low; P.labels = (const long long*)d_labels; P.grad_low = d_grad_low;
         P.loss_sum = d_loss_sum; P.grad_scale = d_grad_scale; P.ignore_index = ignore_index;
         P.B = B; P.C = C; P.h = h; P.w = w; P.H = H; P.W = W;
-        P.s = s; P.off = g.off; P.nby = g.nby; P.nbx = g.nbx; P.rs = g.rs;
-        P.bps = s / 4; P.q = (g.off + s / 2) / 4;
-        const int extra = (P.q % P.bps == 0) ? 1 : 2;
-        fast = false;
-        for (int tbx : {16, 8}) {
-            P.tbx = tbx;
-            P.ncy = (K2_TBY + P.bps - 1) / P.bps + extra;
-            P.ncx = (tbx + P.bps - 1) / P.bps + extra;
-            smem = (((size_t)C + 1) * P.ncy * P.ncx + (size_t)K2_CH * 4 * K2_TBY * tbx) * sizeof(float);
-            if (smem <= 110 * 1024 || (tbx == 8 && smem <= 220 * 1024)) { fast = true; break; }
-        }
+        P.s = s; P.off = g.off; P.rs = g.rs;
+        const int bps = s / 4;
+        P.q = (g.off + s / 2) / 4;
+        // 128 threads = tgy*tgx groups of bps*bps threads; tile = 32 x 64 pixels for every scale
+        P.tgy = 8 / bps; P.tgx = 16 / bps;
+        smem = ((size_t)C + 1) * (P.tgy + 1) * (P.tgx + 1) * sizeof(float);
+        if (smem > 110 * 1024) fast = false;
     }
     if (fast) {
-        LC2IS_CUDA(cudaFuncSetAttribute(k2_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        dim3 grid((P.nbx + P.tbx - 1) / P.tbx, (P.nby + K2_TBY - 1) / K2_TBY, B);
-        k2_fast_kernel<<<grid, K2_TBY * P.tbx, smem, st>>>(P);
+        dim3 grid((w + 1 + P.tgx - 1) / P.tgx, (h + 1 + P.tgy - 1) / P.tgy, B);
+        auto launch = [&](auto kernel) -> int {
+            LC2IS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<grid, 128, smem, st>>>(P);
+            return 0;
+        };
+        int e = s == 4 ? launch(k2_fast_kernel<1>) : s == 8 ? launch(k2_fast_kernel<2>) : launch(k2_fast_kernel<4>);
+        if (e) return e;
         LC2IS_CHECK_LAUNCH("k2_fast_kernel");
     } else {
         const float sy = (float)h / (float)H, sx = (float)w / (float)W;

@@ -1,0 +1,123 @@
+"""One pre-allocated pass of the whole head hot path (what ``Engine.train_loop`` /
+``eval_loop`` do around the head, engine.py:75-101 and :145-163), chained through the C ABI on
+the current stream with no host synchronisation and no allocation inside the step:
+
+    count_valid -> [DP: all-reduce n_valid] -> mean_scale -> K0 proto_normalize ->
+    K1 cosine_logits_fwd -> K2 upsample+CE fwd/bwd -> K1b cosine_logits_bwd ->
+    K3 argmax/confusion matrix (fused bilinear, the 'outputs' map of final.py:44) ->
+    finalize_loss -> [DP: all-reduce gradient bucket + confusion matrix]
+
+Used by bench.py and usable as the data-parallel engine shim.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib, dp
+from ._lib import BF16, BILINEAR, F32, check, lib, ptr, stream_ptr
+
+
+class HeadStep:
+
+    def __init__(self, B: int, h: int, w: int, H: int, W: int, C: int, D: int = 512, ignore_index: int = 0,
+                 logit_scale: float = 1.0, normalize: bool = True, backward: bool = True,
+                 v_dtype=torch.bfloat16, device: Optional[torch.device] = None, distributed: bool = False) -> None:
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.B, self.h, self.w, self.H, self.W, self.C, self.D = B, h, w, H, W, C, D
+        self.hw = h * w
+        self.ignore_index, self.logit_scale, self.normalize, self.backward = ignore_index, logit_scale, normalize, backward
+        self.v_dtype = v_dtype
+        self.distributed = distributed and dp.is_dist()
+        Cp = _lib.class_pad(C)
+        M = B * self.hw
+        e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        self.t_hat = e(1, Cp, D, dt=torch.bfloat16)
+        self.inv_t = e(1, C)
+        self.v_hat = e(M, D, dt=torch.bfloat16)
+        self.inv_v = e(M)
+        self.logits = e(B, C, h, w)
+        self.grad_low = e(B, C, h, w)
+        self.grad_bf16 = e(B, Cp, self.hw, dt=torch.bfloat16)
+        self.grad_v = e(B, self.hw, D, dt=torch.bfloat16)
+        # flat all-reduce bucket: [grad_t (C*D) | loss_sum as fp32 (1)]
+        self.bucket = dp.GradBucket([(1, C, D), (1,)], dev)
+        self.grad_t = self.bucket.views[0]
+        self.confmat = torch.zeros(C, C, dtype=torch.int64, device=dev)
+        # scalars: [0:8] double loss_sum | [8:16] int64 n_valid | [16:20] float gscale | [20:24] float loss
+        self.scalars = torch.zeros(32, dtype=torch.uint8, device=dev)
+        self.loss_sum = self.scalars[0:8].view(torch.float64)
+        self.n_valid = self.scalars[8:16].view(torch.int64)
+        self.gscale = self.scalars[16:20].view(torch.float32)
+        self.loss = self.scalars[20:24].view(torch.float32)
+        nbytes = int(lib.lc2is_cosine_logits_bwd_workspace(B, self.hw, D, 1, C))
+        self.bwd_ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+        self.k2_events = None          # optional (start, stop) CUDA events around the K2 call
+
+    def __call__(self, v: torch.Tensor, t: torch.Tensor, labels: torch.Tensor) -> None:
+        """v [B,hw,D] (bf16/fp32), t [C,D] fp32, labels [B,H,W] int64 - all on the device."""
+        st = stream_ptr()
+        B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
+        self.scalars.zero_()
+        self.confmat.zero_()
+        if self.backward:
+            self.bucket.zero_()
+        check(lib.lc2is_count_valid(ptr(labels), labels.numel(), self.ignore_index, ptr(self.n_valid), st), "count_valid")
+        if self.distributed:
+            dp.global_valid_count_(self.n_valid)
+        check(lib.lc2is_mean_scale(ptr(self.n_valid), 1.0, ptr(self.gscale), st), "mean_scale")
+        check(lib.lc2is_proto_normalize(ptr(t), 1, C, D, int(self.normalize), ptr(self.t_hat), ptr(self.inv_t), st),
+              "proto_normalize")
+        check(lib.lc2is_cosine_logits_fwd(ptr(v), BF16 if v.dtype == torch.bfloat16 else F32, B, hw, D,
+                                          ptr(self.t_hat), 1, C, int(self.normalize), self.logit_scale,
+                                          ptr(self.v_hat), ptr(self.inv_v), ptr(self.logits), st), "cosine_logits_fwd")
+        if self.k2_events is not None:
+            self.k2_events[0].record()
+        check(lib.lc2is_upsample_ce_fwd_bwd(ptr(self.logits), ptr(labels), B, C, h, w, H, W, self.ignore_index,
+                                            ptr(self.gscale), ptr(self.loss_sum),
+                                            ptr(self.grad_low) if self.backward else None, None, st),
+              "upsample_ce_fwd_bwd")
+        if self.k2_events is not None:
+            self.k2_events[1].record()
+        if self.backward:
+            check(lib.lc2is_grad_to_bf16(ptr(self.grad_low), B, C, hw, ptr(self.grad_bf16), st), "grad_to_bf16")
+            check(lib.lc2is_cosine_logits_bwd(ptr(self.grad_bf16), ptr(self.logits), ptr(self.v_hat), ptr(self.inv_v),
+                                              ptr(self.t_hat), ptr(self.inv_t), B, hw, D, 1, C, int(self.normalize),
+                                              self.logit_scale, None, ptr(self.grad_v), BF16, ptr(self.grad_t),
+                                              ptr(self.bwd_ws), st), "cosine_logits_bwd")
+        check(lib.lc2is_argmax_confmat_lowres(ptr(self.logits), B, C, h, w, H, W, BILINEAR, ptr(labels), H, W,
+                                              ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
+        if self.distributed:
+            self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
+            self.bucket.allreduce_()
+            dp.allreduce_confmat_(self.confmat)
+            self.loss.copy_(self.bucket.views[1] / self.n_valid)
+        else:
+            check(lib.lc2is_finalize_loss(ptr(self.loss_sum), ptr(self.n_valid), ptr(self.loss), st), "finalize_loss")
+
+
+class HostStep:
+    """The same pass through ``lc2is_head_step_host``: HOST (pinned) buffers in, host results out,
+    H2D / D2H copies inside the call (bench.py's `e2e`)."""
+
+    def __init__(self, B: int, h: int, w: int, H: int, W: int, C: int, D: int = 512, ignore_index: int = 0,
+                 logit_scale: float = 1.0, backward: bool = True, device: Optional[torch.device] = None) -> None:
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.args = (B, h, w, D, C, H, W)
+        self.ignore_index, self.logit_scale, self.backward = ignore_index, logit_scale, backward
+        nbytes = int(lib.lc2is_head_step_workspace(B, h * w, D, C, H, W))
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.out_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.out_n_valid = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.out_confmat = torch.zeros(C, C, dtype=torch.int64).pin_memory()
+        self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + B * H * W * 8
+        self.d2h_bytes = 4 + 8 + C * C * 8
+
+    def __call__(self, h_v: torch.Tensor, h_t: torch.Tensor, h_labels: torch.Tensor) -> None:
+        B, h, w, D, C, H, W = self.args
+        assert h_v.dtype == torch.bfloat16 and not h_v.is_cuda and not h_labels.is_cuda
+        check(lib.lc2is_head_step_host(ptr(h_v), ptr(h_t), ptr(h_labels), B, h, w, D, C, H, W, self.ignore_index,
+                                       self.logit_scale, int(self.backward), ptr(self.out_loss),
+                                       ptr(self.out_n_valid), ptr(self.out_confmat), ptr(self.ws), stream_ptr()),
+              "lc2is_head_step_host")
