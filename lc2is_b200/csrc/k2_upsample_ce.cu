@@ -83,7 +83,37 @@ struct K2Params {
     float rs;
 };
 
+constexpr float K2_FAST_RANGE = 40.f;   // max logit range inside a group for the shared-shift fast path
+
 __device__ __forceinline__ int clampi2(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 - two fp32 ops per issue slot) ------
+__device__ __forceinline__ unsigned long long pk2(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 up2(unsigned long long r) {
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+    return up2(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
+    return up2(d);
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+    return up2(d);
+}
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
 
 // Sum (a,b,c,d) over the LPG consecutive lanes of a group.  After the call lane u of the group
 // holds in `a` the total of value number (u * 4 / LPG) [LPG >= 4], i.e. the first quarter of the
@@ -91,13 +121,11 @@ __device__ __forceinline__ int clampi2(int v, int lo, int hi) { return v < lo ? 
 template <int LPG>
 __device__ __forceinline__ void group_reduce4(float& a, float& b, float& c, float& d, int u) {
     if constexpr (LPG >= 4) {
-        // step 1: halves exchange pairs -> lower half keeps (a,b), upper half keeps (c,d)
         const bool up = u & (LPG / 2);
         float s0 = up ? a : c, s1 = up ? b : d;          // what this lane gives away
         float k0 = up ? c : a, k1 = up ? d : b;          // what it keeps
         k0 += __shfl_xor_sync(0xffffffffu, s0, LPG / 2);
         k1 += __shfl_xor_sync(0xffffffffu, s1, LPG / 2);
-        // step 2: quarters -> one value per lane
         const bool up2 = u & (LPG / 4);
         float g = up2 ? k0 : k1;
         float k = up2 ? k1 : k0;
@@ -108,45 +136,72 @@ __device__ __forceinline__ void group_reduce4(float& a, float& b, float& c, floa
     }
 }
 
+// exp-polynomial of one class inside a 4x4 block: exp(l(i,j) - M) = E * p^i * q^j * t^(i*j)
+struct Poly { float E, p, q, t; };
+__device__ __forceinline__ Poly k2_poly(float a, float b, float cc, float d, float ly0, float lx0, float k1,
+                                        float k2, float Mk) {
+    const float da = cc - a, db = d - b, dd = db - da;
+    const float L0 = fmaf(ly0, da, a), R0 = fmaf(ly0, db, b);
+    const float rl = R0 - L0;
+    const float l00 = fmaf(lx0, rl, L0);
+    Poly P;
+    P.q = ex2f(rl * k1);
+    P.p = ex2f(fmaf(lx0, dd, da) * k1);
+    P.t = ex2f(dd * k2);
+    P.E = ex2f(fmaf(l00, LOG2E, -Mk));
+    return P;
+}
+
 template <int BPS>
 __global__ void __launch_bounds__(128)
 k2_fast_kernel(const K2Params P) {
     constexpr int LPG = BPS * BPS;                          // lanes (threads) per group
+    constexpr bool QUAD = LPG >= 4;                         // tile layout: per-group tap quads vs cells
     extern __shared__ float smem[];
     const int C = P.C;
+    const int ngr = P.tgy * P.tgx;
     const int ncx = P.tgx + 1, ncy = P.tgy + 1;
-    const int ncell = ncy * ncx;
-    const int cs = ncell;                                   // class stride in the tile
+    const int cs = QUAD ? ngr * 4 : ncy * ncx;              // class stride (floats) in the tile
     const int nthr = blockDim.x;
-    float* st = smem;                                       // source tile  [C][ncy][ncx]
-    float* cellmax = smem + (size_t)C * cs;                 // [ncell]
-    __shared__ float red[4];
+    float* st = smem;
 
     const int n = blockIdx.z;
     const int GY0 = blockIdx.y * P.tgy, GX0 = blockIdx.x * P.tgx;
     const int cy0 = GY0 - 1, cx0 = GX0 - 1;                 // first cell of the tile (may be -1)
     const float* lowb = P.low + (size_t)n * C * P.h * P.w;
 
-    // ---- stage the source tile ------------------------------------------------------------------
-    for (int idx = threadIdx.x; idx < C * ncell; idx += nthr) {
-        int c = idx / ncell, r = idx - c * ncell;
-        int i = r / ncx, j = r - i * ncx;
-        int gy = cy0 + i, gx = cx0 + j;
-        if (gy >= 0 && gy < P.h && gx >= 0 && gx < P.w)
-            cp_async4(st + idx, lowb + ((size_t)c * P.h + gy) * P.w + gx);
-        else
-            st[idx] = -INFINITY;
+    // ---- stage the source tile --------------------------------------------------------------------
+    // QUAD: st[c][group][4] = the group's four index-clamped taps (one LDS.128 per class later);
+    // cells: st[c][ncy][ncx].  Groups / cells outside the image hold 0.
+    if (QUAD) {
+        // cs = 4 * groups divides the 128 threads: thread -> fixed (group, tap), strided over classes
+        const int r = threadIdx.x % cs, cstep = nthr / cs;
+        const int gq = r >> 2, tap = r & 3;
+        const int ty = gq / P.tgx, tx = gq - ty * P.tgx;
+        const int kyy = GY0 + ty - 1, kxx = GX0 + tx - 1;
+        const bool ok = kyy < P.h && kxx < P.w;
+        const int gy = clampi2(kyy + (tap >> 1), 0, P.h - 1), gx = clampi2(kxx + (tap & 1), 0, P.w - 1);
+        const float* src = lowb + (size_t)gy * P.w + gx;
+        const size_t plane = (size_t)P.h * P.w;
+        for (int c = threadIdx.x / cs; c < C; c += cstep) {
+            if (ok) cp_async4(st + c * cs + r, src + (size_t)c * plane);
+            else st[c * cs + r] = 0.f;
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < C * cs; idx += nthr) {
+            const int c = idx / cs, r = idx - c * cs;
+            const int i = r / ncx, j = r - i * ncx;
+            const int gy = cy0 + i, gx = cx0 + j;
+            if (gy >= 0 && gy < P.h && gx >= 0 && gx < P.w)
+                cp_async4(st + idx, lowb + ((size_t)c * P.h + gy) * P.w + gx);
+            else
+                st[idx] = 0.f;
+        }
     }
     cp_async_wait_all();
     __syncthreads();
-    for (int r = threadIdx.x; r < ncell; r += nthr) {
-        float m = -INFINITY;
-        for (int c = 0; c < C; ++c) m = fmaxf(m, st[c * cs + r]);
-        cellmax[r] = m;
-    }
-    __syncthreads();
 
-    // ---- per-thread block setup -------------------------------------------------------------------
+    // ---- per-thread block setup ---------------------------------------------------------------------
     const int g = threadIdx.x / LPG, u = threadIdx.x % LPG;
     const int tgy = g / P.tgx, tgx = g - tgy * P.tgx;
     const int uy = u / BPS, ux = u % BPS;
@@ -171,85 +226,113 @@ k2_fast_kernel(const K2Params P) {
             lab[i * 4 + j] = l;
             any |= l >= 0;
         }
-    // clamped tap cells (global) and their offsets in the tile
+    // clamped tap cells (global)
     const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
     const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);
-    int oa = 0, ob = 0, oc = 0, od = 0;
-    float ly0 = 0.f, lx0 = 0.f, M = 0.f;
-    if (group_in) {
+    // tile offsets of the four taps
+    int oa, ob, oc, od;
+    if (QUAD) { oa = g * 4; ob = oa + 1; oc = oa + 2; od = oa + 3; }
+    else {
         oa = (Ya - cy0) * ncx + (Xa - cx0); ob = (Ya - cy0) * ncx + (Xb - cx0);
         oc = (Yb - cy0) * ncx + (Xa - cx0); od = (Yb - cy0) * ncx + (Xb - cx0);
-        // lambda of the block's first row / column ((y0+0.5)*rs-0.5-ky is exact for power-of-2 s)
-        ly0 = ((float)y0 + 0.5f) * rs - 0.5f - (float)ky;
-        lx0 = ((float)x0 + 0.5f) * rs - 0.5f - (float)kx;
-        M = fmaxf(fmaxf(cellmax[oa], cellmax[ob]), fmaxf(cellmax[oc], cellmax[od]));
+        if (!group_in) oa = ob = oc = od = 0;
     }
+    auto taps = [&](int c, float& a, float& b, float& cc, float& d) {
+        if (QUAD) {
+            const float4 v = *reinterpret_cast<const float4*>(st + (size_t)c * cs + oa);
+            a = v.x; b = v.y; cc = v.z; d = v.w;
+        } else {
+            const float* p = st + (size_t)c * cs;
+            a = p[oa]; b = p[ob]; cc = p[oc]; d = p[od];
+        }
+    };
+    // lambda of the block's first row / column ((y0+0.5)*rs-0.5-ky is exact for power-of-2 s)
+    const float ly0 = ((float)y0 + 0.5f) * rs - 0.5f - (float)ky;
+    const float lx0 = ((float)x0 + 0.5f) * rs - 0.5f - (float)kx;
+
+    // ---- softmax shift: M = max over classes of the group's taps (>= every pixel's max) -----------
+    float mx = -INFINITY, mn = INFINITY;
+    for (int c = u; c < C; c += LPG) {                      // the group's lanes split the classes
+        float a, b, cc, d;
+        taps(c, a, b, cc, d);
+        mx = fmaxf(mx, fmaxf(fmaxf(a, b), fmaxf(cc, d)));
+        mn = fminf(mn, fminf(fminf(a, b), fminf(cc, d)));
+    }
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    const float M = mx;
+    // fast path needs a bounded logit range inside the group (no under/overflow of the shared-shift
+    // polynomial); otherwise - or on inf/NaN - the whole warp takes the exact per-pixel path.
+    bool slow = any && !((mx - mn) < K2_FAST_RANGE);
+    slow = __any_sync(0xffffffffu, slow);
+    const bool warp_any = __any_sync(0xffffffffu, any);
     const float Mk = M * LOG2E;
     const float k1 = rs * LOG2E, k2 = rs * rs * LOG2E;
 
-    // ---- pass A: S(i,j) = sum_c exp(l_c(i,j) - M) ----------------------------------------------------
-    float S[16];                      // becomes U = g / S after pass A
-    bool slow = false;
+    float U[16];                      // pass A: S(i,j) = sum_c exp(l_c - shift); then U = g / S
+    float Mp[16];                     // per-pixel shift (== M on the fast path)
     float loss = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) S[i] = 0.f;
-    if (any) {
+    for (int i = 0; i < 16; ++i) { U[i] = 0.f; Mp[i] = M; }
+
+    if (warp_any && !slow) {
+        // ---- pass A (fast): rows (0,1) and (2,3) packed; S(i,j) += e_i * q_i^j -------------------------
+        float2 S01[4], S23[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { S01[j] = make_float2(0.f, 0.f); S23[j] = make_float2(0.f, 0.f); }
 #pragma unroll 2
         for (int c = 0; c < C; ++c) {
-            const float* p = st + c * cs;
-            const float a = p[oa], b = p[ob], cc = p[oc], d = p[od];
-            const float da = cc - a, db = d - b, dd = db - da;
-            const float L0 = fmaf(ly0, da, a), R0 = fmaf(ly0, db, b);
-            const float rl = R0 - L0;
-            const float l00 = fmaf(lx0, rl, L0);
-            const float q0 = ex2f(rl * k1);
-            const float pp = ex2f(fmaf(lx0, dd, da) * k1);
-            const float tt = ex2f(dd * k2);
-            float e0 = ex2f(fmaf(l00, LOG2E, -Mk));
-            float qi = q0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float e = e0;
-                S[i * 4 + 0] += e;
-                e *= qi; S[i * 4 + 1] += e;
-                e *= qi; S[i * 4 + 2] += e;
-                e *= qi; S[i * 4 + 3] += e;
-                e0 *= pp;
-                qi *= tt;
-            }
+            float a, b, cc, d;
+            taps(c, a, b, cc, d);
+            const Poly y = k2_poly(a, b, cc, d, ly0, lx0, k1, k2, Mk);
+            const float2 e01 = make_float2(y.E, y.E * y.p), q01 = make_float2(y.q, y.q * y.t);
+            const float2 e23 = fmul2(e01, bc2(y.p * y.p)), q23 = fmul2(q01, bc2(y.t * y.t));
+            const float2 qq01 = fmul2(q01, q01), qq23 = fmul2(q23, q23);
+            const float2 q301 = fmul2(qq01, q01), q323 = fmul2(qq23, q23);
+            S01[0] = fadd2(S01[0], e01);           S23[0] = fadd2(S23[0], e23);
+            S01[1] = ffma2(e01, q01, S01[1]);      S23[1] = ffma2(e23, q23, S23[1]);
+            S01[2] = ffma2(e01, qq01, S01[2]);     S23[2] = ffma2(e23, qq23, S23[2]);
+            S01[3] = ffma2(e01, q301, S01[3]);     S23[3] = ffma2(e23, q323, S23[3]);
         }
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (lab[i] >= 0) slow |= !((S[i] >= S_MIN) && (S[i] <= 3.0e38f));
-    }
-    // The exact fallback is taken by the whole warp (the scatter pass below is warp-collective).
-    slow = __any_sync(0xffffffffu, slow);
-    float Mp[16];                     // per-pixel softmax shift (only differs from M on the slow path)
+        for (int j = 0; j < 4; ++j) {
+            U[0 * 4 + j] = S01[j].x; U[1 * 4 + j] = S01[j].y;
+            U[2 * 4 + j] = S23[j].x; U[3 * 4 + j] = S23[j].y;
+        }
+        bool bad = false;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) Mp[i] = M;
-    if (slow && any) {
-        // exact per-pixel max and sum (logits spanning > ~80 inside one cell, inf/NaN, ...)
+        for (int i = 0; i < 16; ++i)
+            if (lab[i] >= 0) bad |= !((U[i] >= S_MIN) && (U[i] <= 3.0e38f));
+        slow = __any_sync(0xffffffffu, bad);
+    }
+    if (warp_any && slow) {
+        // ---- pass A (exact): per-pixel max and sum -----------------------------------------------------
 #pragma unroll 1
         for (int pix = 0; pix < 16; ++pix) {
             const float ly = ly0 + (float)(pix >> 2) * rs, lx = lx0 + (float)(pix & 3) * rs;
             float m = -INFINITY;
             for (int c = 0; c < C; ++c) {
-                const float* p = st + c * cs;
-                float L = fmaf(ly, p[oc] - p[oa], p[oa]), R = fmaf(ly, p[od] - p[ob], p[ob]);
+                float a, b, cc, d;
+                taps(c, a, b, cc, d);
+                const float L = fmaf(ly, cc - a, a), R = fmaf(ly, d - b, b);
                 m = fmaxf(m, fmaf(lx, R - L, L));
             }
             float sum = 0.f;
             for (int c = 0; c < C; ++c) {
-                const float* p = st + c * cs;
-                float L = fmaf(ly, p[oc] - p[oa], p[oa]), R = fmaf(ly, p[od] - p[ob], p[ob]);
+                float a, b, cc, d;
+                taps(c, a, b, cc, d);
+                const float L = fmaf(ly, cc - a, a), R = fmaf(ly, d - b, b);
                 sum += ex2f((fmaf(lx, R - L, L) - m) * LOG2E);
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-                if (i == pix) { Mp[i] = m; S[i] = sum; }
+                if (i == pix) { Mp[i] = m; U[i] = sum; }
         }
     }
-    // ---- loss and per-pixel gradient scale U = g / S --------------------------------------------------
+    // ---- loss and per-pixel gradient scale U = g / S ----------------------------------------------------
     if (any) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -259,123 +342,133 @@ k2_fast_kernel(const K2Params P) {
                 float uu = 0.f;
                 if (t >= 0) {
                     const float ly = ly0 + (float)i * rs, lx = lx0 + (float)j * rs;
-                    const float* p = st + t * cs;
-                    const float L = fmaf(ly, p[oc] - p[oa], p[oa]), R = fmaf(ly, p[od] - p[ob], p[ob]);
-                    const float lt = fmaf(lx, R - L, L);
-                    loss += logf(S[i * 4 + j]) + Mp[i * 4 + j] - lt;
-                    uu = gs / S[i * 4 + j];
+                    float a, b, cc, d;
+                    taps(t, a, b, cc, d);
+                    const float L = fmaf(ly, cc - a, a), R = fmaf(ly, d - b, b);
+                    loss += logf(U[i * 4 + j]) + Mp[i * 4 + j] - fmaf(lx, R - L, L);
+                    uu = gs / U[i * 4 + j];
                 }
-                S[i * 4 + j] = uu;
+                U[i * 4 + j] = uu;
             }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) U[i] = 0.f;
     }
 
-    // ---- pass B: scatter (softmax - onehot) * g through the taps ---------------------------------------
-    // Warp-collective: every lane runs the class loop (lanes without valid pixels contribute zeros).
+    // ---- pass B: scatter softmax * U through the taps (warp-collective) ---------------------------------
     float* gb = P.grad_low ? P.grad_low + (size_t)n * C * P.h * P.w : nullptr;
-    const bool warp_any = __any_sync(0xffffffffu, any);
     if (gb && warp_any) {
         // which of the four totals this lane writes after the butterfly, and where
-        const int role = LPG >= 4 ? (u * 4) / LPG : 0;
-        const bool writer = LPG >= 4 ? (u % (LPG / 4 > 0 ? LPG / 4 : 1)) == 0 : true;
+        const int role = QUAD ? (u * 4) / LPG : 0;
+        const bool writer = QUAD ? (u % (LPG / 4)) == 0 : true;
         const int cellY = (role & 2) ? Yb : Ya, cellX = (role & 1) ? Xb : Xa;
-        float* gcell = gb + (size_t)cellY * P.w + cellX;
         const size_t plane = (size_t)P.h * P.w;
-        int cur = 0x7fffffff;                              // smallest label among this thread's valid pixels
+        float* gcell = gb + (size_t)cellY * P.w + cellX;
+        float* gA = gb + (size_t)Ya * P.w + Xa; float* gB = gb + (size_t)Ya * P.w + Xb;
+        float* gC = gb + (size_t)Yb * P.w + Xa; float* gD = gb + (size_t)Yb * P.w + Xb;
+        auto emit = [&](int c, float G, float Gx, float Gy, float Gxy) {
+            const float X = fmaf(rs, Gx, lx0 * G);                        // sum lambda_x g
+            const float Y = fmaf(rs, Gy, ly0 * G);                        // sum lambda_y g
+            const float XY = fmaf(ly0, X, rs * fmaf(rs, Gxy, lx0 * Gy));  // sum lambda_x lambda_y g
+            float A = (G - X) - (Y - XY), Bv = X - XY, Cv = Y - XY, Dv = XY;
+            group_reduce4<LPG>(A, Bv, Cv, Dv, u);
+            if (QUAD) {
+                if (writer) atomicAdd(gcell + (size_t)c * plane, A);
+            } else if (any) {
+                atomicAdd(gA + (size_t)c * plane, A);  atomicAdd(gB + (size_t)c * plane, Bv);
+                atomicAdd(gC + (size_t)c * plane, Cv); atomicAdd(gD + (size_t)c * plane, Dv);
+            }
+        };
+        if (!slow) {
+            // Horner form.  With e(i,j) = E p^i q_i^j (q_i = q t^i) and weights U(i,j):
+            //   h_i  = sum_j q_i^j U(i,j)        hx_i = sum_j j q_i^j U(i,j)
+            //   G = E sum_i p^i h_i,  Gy = E sum_i i p^i h_i,  Gx / Gxy the same with hx.
+            // (h_i, hx_i) are evaluated together as one packed fp32x2 Horner chain per row.
+            float2 K3[4], K2v[4], K1v[4], K0[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                K3[i] = make_float2(U[i * 4 + 3], 3.f * U[i * 4 + 3]);
+                K2v[i] = make_float2(U[i * 4 + 2], 2.f * U[i * 4 + 2]);
+                K1v[i] = make_float2(U[i * 4 + 1], U[i * 4 + 1]);
+                K0[i] = make_float2(U[i * 4 + 0], 0.f);
+            }
+#pragma unroll 2
+            for (int c = 0; c < C; ++c) {
+                float a, b, cc, d;
+                taps(c, a, b, cc, d);
+                const Poly y = k2_poly(a, b, cc, d, ly0, lx0, k1, k2, Mk);
+                float2 hh[4];
+                float2 qi = bc2(y.q);
+                const float2 tt = bc2(y.t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float2 v = ffma2(qi, K3[i], K2v[i]);
+                    v = ffma2(qi, v, K1v[i]);
+                    hh[i] = ffma2(qi, v, K0[i]);                 // (h_i, hx_i)
+                    if (i < 3) qi = fmul2(qi, tt);
+                }
+                const float2 pp = bc2(y.p);
+                float2 v0 = ffma2(pp, hh[3], hh[2]);
+                v0 = ffma2(pp, v0, hh[1]);
+                v0 = ffma2(pp, v0, hh[0]);
+                const float2 GG = fmul2(v0, bc2(y.E));              // (G, Gx)
+                float2 v1 = ffma2(hh[2], bc2(2.f), fmul2(hh[3], bc2(3.f * y.p)));
+                v1 = ffma2(pp, v1, hh[1]);
+                const float2 GY = fmul2(v1, bc2(y.E * y.p));        // (Gy, Gxy)
+                emit(c, GG.x, GG.y, GY.x, GY.y);
+            }
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                float a, b, cc, d;
+                taps(c, a, b, cc, d);
+                float G = 0.f, Gx = 0.f, Gy = 0.f, Gxy = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float ly = ly0 + (float)i * rs, lx = lx0 + (float)j * rs;
+                        const float L = fmaf(ly, cc - a, a), R = fmaf(ly, d - b, b);
+                        const float gg = ex2f((fmaf(lx, R - L, L) - Mp[i * 4 + j]) * LOG2E) * U[i * 4 + j];
+                        G += gg; Gx += (float)j * gg; Gy += (float)i * gg; Gxy += (float)(i * j) * gg;
+                    }
+                emit(c, G, Gx, Gy, Gxy);
+            }
+        }
+        // ---- - g * onehot: exact integer tap weights (lambda * 2s are odd integers), aggregated per
+        //      distinct label of this thread's 16 pixels (blocky label maps: usually one), 4 reductions each
+        const int S2 = 2 * P.s;
+        const float wscale = -gs / (float)(S2 * S2);
+        const int lyi0 = 2 * y0 + 1 - P.s - S2 * ky, lxi0 = 2 * x0 + 1 - P.s - S2 * kx;
+        int cur = 0x7fffffff;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
             if (lab[i] >= 0) cur = min(cur, lab[i]);
-        for (int c = 0; c < C; ++c) {
-            float A = 0.f, Bv = 0.f, Cv = 0.f, Dv = 0.f;
-            if (any) {
-                const float* p = st + c * cs;
-                const float a = p[oa], b = p[ob], cc = p[oc], d = p[od];
-                float G, Gx, Gy, Gxy;
-                if (!slow) {
-                    const float da = cc - a, db = d - b, dd = db - da;
-                    const float L0 = fmaf(ly0, da, a), R0 = fmaf(ly0, db, b);
-                    const float rl = R0 - L0;
-                    const float l00 = fmaf(lx0, rl, L0);
-                    const float q0 = ex2f(rl * k1);
-                    const float pp = ex2f(fmaf(lx0, dd, da) * k1);
-                    const float tt = ex2f(dd * k2);
-                    float e0 = ex2f(fmaf(l00, LOG2E, -Mk));
-                    float qi = q0;
-                    float r[4], rx[4];
+        while (cur != 0x7fffffff) {
+            int wa = 0, wb = 0, wc = 0, wd = 0, nxt = 0x7fffffff;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float e = e0;
-                        const float g0 = e * S[i * 4 + 0];
-                        e *= qi; const float g1 = e * S[i * 4 + 1];
-                        e *= qi; const float g2 = e * S[i * 4 + 2];
-                        e *= qi; const float g3 = e * S[i * 4 + 3];
-                        r[i] = (g0 + g1) + (g2 + g3);
-                        rx[i] = fmaf(3.f, g3, fmaf(2.f, g2, g1));
-                        e0 *= pp;
-                        qi *= tt;
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = lab[i * 4 + j];
+                    if (t == cur) {
+                        const int lyi = lyi0 + 2 * i, lxi = lxi0 + 2 * j;
+                        wa += (S2 - lyi) * (S2 - lxi); wb += (S2 - lyi) * lxi;
+                        wc += lyi * (S2 - lxi);        wd += lyi * lxi;
+                    } else if (t > cur) {
+                        nxt = min(nxt, t);
                     }
-                    G = (r[0] + r[1]) + (r[2] + r[3]);
-                    Gy = fmaf(3.f, r[3], fmaf(2.f, r[2], r[1]));
-                    Gx = (rx[0] + rx[1]) + (rx[2] + rx[3]);
-                    Gxy = fmaf(3.f, rx[3], fmaf(2.f, rx[2], rx[1]));
-                } else {
-                    G = Gx = Gy = Gxy = 0.f;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float ly = ly0 + (float)i * rs, lx = lx0 + (float)j * rs;
-                            const float L = fmaf(ly, cc - a, a), R = fmaf(ly, d - b, b);
-                            const float gg = ex2f((fmaf(lx, R - L, L) - Mp[i * 4 + j]) * LOG2E) * S[i * 4 + j];
-                            G += gg; Gx += (float)j * gg; Gy += (float)i * gg; Gxy += (float)(i * j) * gg;
-                        }
                 }
-                const float X = fmaf(rs, Gx, lx0 * G);                        // sum lambda_x g
-                const float Y = fmaf(rs, Gy, ly0 * G);                        // sum lambda_y g
-                const float XY = fmaf(ly0, X, rs * fmaf(rs, Gxy, lx0 * Gy));  // sum lambda_x lambda_y g
-                A = (G - X) - (Y - XY); Bv = X - XY; Cv = Y - XY; Dv = XY;
-                // - g * onehot for the pixels whose target is this class.  `cur` is the smallest
-                // not-yet-handled label of this thread: one compare per class, the 16-way scan only on a hit.
-                if (c == cur) {
-                    int nxt = 0x7fffffff;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int t = lab[i * 4 + j];
-                            if (t == c) {
-                                const float ly = ly0 + (float)i * rs, lx = lx0 + (float)j * rs;
-                                A -= gs * (1.f - ly) * (1.f - lx); Bv -= gs * (1.f - ly) * lx;
-                                Cv -= gs * ly * (1.f - lx);        Dv -= gs * ly * lx;
-                            } else if (t > c) {
-                                nxt = min(nxt, t);
-                            }
-                        }
-                    cur = nxt;
-                }
-            }
-            group_reduce4<LPG>(A, Bv, Cv, Dv, u);
-            if constexpr (LPG >= 4) {
-                if (writer && A != 0.f) atomicAdd(gcell + (size_t)c * plane, A);
-            } else {
-                float* gp = gb + (size_t)c * plane;
-                if (any) {
-                    if (A != 0.f) atomicAdd(gp + (size_t)Ya * P.w + Xa, A);
-                    if (Bv != 0.f) atomicAdd(gp + (size_t)Ya * P.w + Xb, Bv);
-                    if (Cv != 0.f) atomicAdd(gp + (size_t)Yb * P.w + Xa, Cv);
-                    if (Dv != 0.f) atomicAdd(gp + (size_t)Yb * P.w + Xb, Dv);
-                }
-            }
+            atomicAdd(gA + (size_t)cur * plane, wscale * (float)wa);
+            atomicAdd(gB + (size_t)cur * plane, wscale * (float)wb);
+            atomicAdd(gC + (size_t)cur * plane, wscale * (float)wc);
+            atomicAdd(gD + (size_t)cur * plane, wscale * (float)wd);
+            cur = nxt;
         }
     }
-    // ---- loss reduction: warp -> CTA -> one double atomic ----------------------------------------------
+    // ---- loss reduction: one double reduction per warp ---------------------------------------------------
     loss = warp_sum(loss);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = loss;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int i = 0; i < (nthr >> 5); ++i) t += red[i];
-        if (t != 0.f) atomicAdd(P.loss_sum, (double)t);
-    }
+    if ((threadIdx.x & 31) == 0 && loss != 0.f) atomicAdd(P.loss_sum, (double)loss);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -527,7 +620,7 @@ extern "C" int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_la
         P.q = (g.off + s / 2) / 4;
         // 128 threads = tgy*tgx groups of bps*bps threads; tile = 32 x 64 pixels for every scale
         P.tgy = 8 / bps; P.tgx = 16 / bps;
-        smem = ((size_t)C + 1) * (P.tgy + 1) * (P.tgx + 1) * sizeof(float);
+        smem = (size_t)C * (bps > 1 ? P.tgy * P.tgx * 4 : (P.tgy + 1) * (P.tgx + 1)) * sizeof(float);
         if (smem > 110 * 1024) fast = false;
     }
     if (fast) {
