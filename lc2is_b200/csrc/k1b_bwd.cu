@@ -23,32 +23,42 @@ constexpr int KB_THREADS = 192;
 
 // ---------------------------------------------------------------------------------------------
 // r[m] = sum_c G[m,c]*L[m,c]   ;   rt[set][c] += sum_m G[m,c]*L[m,c]
+// One thread per pixel (coalesced along pixels for every class); the per-class column sums are
+// reduced with warp shuffles into per-warp shared slots, combined once at the end.
+constexpr int PREP_CMAX = 1024;
 __global__ void __launch_bounds__(256)
 k1b_prep_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ L, int B, int C, int C_pad, int hw,
                 int n_sets, float* __restrict__ r, float* __restrict__ rt) {
+    extern __shared__ float part[];                       // [8 warps][C]
     const int b = blockIdx.y;
     const int p = blockIdx.x * 256 + threadIdx.x;
     const bool in = p < hw;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const __nv_bfloat16* g = G + (size_t)b * C_pad * hw + p;
     const float* l = L + (size_t)b * C * hw + p;
     float acc = 0.f;
-    __shared__ float part[8];
-    float* rts = rt + (size_t)(n_sets > 1 ? b : 0) * C;
-    for (int c = 0; c < C; ++c) {
-        float v = in ? __bfloat162float(g[(size_t)c * hw]) * __ldg(l + (size_t)c * hw) : 0.f;
-        acc += v;
-        float w = warp_sum(v);
-        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = w;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float t = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t += part[i];
-            if (t != 0.f) atomicAdd(rts + c, t);
+    float mine = 0.f;                                     // lane (c & 31) keeps class c's warp sum
+    for (int c0 = 0; c0 < C; c0 += 32) {
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const int c = c0 + k;
+            float v = 0.f;
+            if (c < C && in) v = __bfloat162float(g[(size_t)c * hw]) * __ldg(l + (size_t)c * hw);
+            acc += v;
+            const float w = warp_sum(v);
+            if (lane == k) mine = w;
         }
-        __syncthreads();
+        if (c0 + lane < C) part[warp * C + c0 + lane] = mine;
     }
     if (in) r[(size_t)b * hw + p] = acc;
+    __syncthreads();
+    float* rts = rt + (size_t)(n_sets > 1 ? b : 0) * C;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w * C + c];
+        if (t != 0.f) atomicAdd(rts + c, t);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -397,8 +407,11 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits_bf16, const flo
     // ---- projections r, rt -----------------------------------------------------------------------
     if (normalize) {
         dim3 grid((hw + 255) / 256, B);
-        k1b_prep_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)d_grad_logits_bf16, d_logits, B, C, C_pad, hw,
-                                              n_sets, d_r, d_rt);
+        const size_t psm = (size_t)8 * C * sizeof(float);
+        if (psm > 48 * 1024)
+            LC2IS_CUDA(cudaFuncSetAttribute(k1b_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        k1b_prep_kernel<<<grid, 256, psm, st>>>((const __nv_bfloat16*)d_grad_logits_bf16, d_logits, B, C, C_pad, hw,
+                                                n_sets, d_r, d_rt);
         LC2IS_CHECK_LAUNCH("k1b_prep_kernel");
     }
     // ---- dV ----------------------------------------------------------------------------------------

@@ -201,112 +201,243 @@ __device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // ---------------------------------------------------------------------------------------------
-// k3_low_fast: one thread = one 4x4 pixel block sharing its taps.  CTA = 16x16 blocks of one
-// image (64x64 px).  grid = (ceil(nbx/16), ceil(nby/16), N).
-template <int MODE>   // 0 bilinear, 1 bicubic
-__global__ void __launch_bounds__(K3_THREADS)
-k3_low_fast_kernel(const float* __restrict__ low, int C, int h, int w, int H, int W,
-                   int s, int off, int nby, int nbx, float rs,
-                   const long long* __restrict__ labels, int lh, int lw,
-                   unsigned long long* __restrict__ confmat, unsigned long long* __restrict__ per_image,
-                   long long* __restrict__ pred_out, int use_smem_hist) {
-    extern __shared__ int hist_smem[];
-    int* hist = use_smem_hist ? hist_smem : nullptr;
-    const int n = blockIdx.z;
-    if (hist) {
-        for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
-    }
-    const int bx = blockIdx.x * 16 + (threadIdx.x & 15);
-    const int by = blockIdx.y * 16 + (threadIdx.x >> 4);
-    const bool active = bx < nbx && by < nby;
-    const int y0 = 4 * by - off, x0 = 4 * bx - off;
-    constexpr int NT = MODE == 0 ? 2 : 4;
-    ArgmaxState st[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) am_init(st[j]);
+// k3_low_fast: power-of-two scale s in {4, 8, 16}.  Same geometry as K2 (k2_upsample_ce.cu): a GROUP is
+// the bps x bps (bps = s/4) 4x4-pixel blocks that share one set of taps; one thread owns one block.
+// The CTA stages the index-clamped source cells of its 32 x 64 pixel tile in shared memory once
+// (cp.async), then every thread walks the classes:
+//   bilinear: the 16 values of a block are l00 + i*P + j*Q + i*j*T -> evaluated incrementally with
+//             packed fp32x2 adds (exact for the dyadic exactness set; fp32-order noise otherwise)
+//   bicubic : ATen's evaluation order is kept (horizontal 4-tap fmaf chain, then vertical), packed
+//             as fp32x2 over output-column pairs - bit-identical to the scalar chain.
+// Non-finite taps (inf / NaN) send the warp down the per-pixel path that reproduces
+// argmax(softmax(x)) = 0 for poisoned pixels.  Counts go to global memory with warp-aggregated
+// (match.any) 64-bit atomics: a 32 x 64 tile holds few distinct (target, prediction) pairs.
+__device__ __forceinline__ unsigned long long pk2f(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float2 up2f(unsigned long long r) {
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2f(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2f(a.x, a.y)), "l"(pk2f(b.x, b.y)));
+    return up2f(d);
+}
+__device__ __forceinline__ float2 fmul2f(float2 a, float2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2f(a.x, a.y)), "l"(pk2f(b.x, b.y)));
+    return up2f(d);
+}
+__device__ __forceinline__ float2 ffma2f(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2f(a.x, a.y)), "l"(pk2f(b.x, b.y)), "l"(pk2f(c.x, c.y)));
+    return up2f(d);
+}
+__device__ __forceinline__ void cp_async4_k3(void* smem, const void* gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
+}
 
-    if (active) {
-        // shared tap indices: floor(src) is the same for the 4 rows / 4 cols of the block
-        const int yc = y0 < 0 ? 0 : y0, xc = x0 < 0 ? 0 : x0;        // any in-range pixel of the block
-        const int ky = (int)floorf(((float)yc + 0.5f) * rs - 0.5f);
-        const int kx = (int)floorf(((float)xc + 0.5f) * rs - 0.5f);
-        int iy[NT], ix[NT];
-        float wy[4][NT], wx[4][NT];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float sy = ((float)(y0 + i) + 0.5f) * rs - 0.5f;
-            float sx = ((float)(x0 + i) + 0.5f) * rs - 0.5f;
-            if (MODE == 0) {
-                // bilinear: clamp src at 0 -> lambda 0 at the top/left border
-                float ty = sy < 0.f ? 0.f : sy - (float)ky;
-                float tx = sx < 0.f ? 0.f : sx - (float)kx;
-                if (sy < 0.f) ty = (ky < 0) ? 1.f : 0.f;   // taps (clamp(-1)=0, 0): either weight picks row 0
-                if (sx < 0.f) tx = (kx < 0) ? 1.f : 0.f;
-                wy[i][0] = 1.f - ty; wy[i][1] = ty;
-                wx[i][0] = 1.f - tx; wx[i][1] = tx;
-            } else {
-                float cy[4], cx[4];
-                cubic_coeffs(sy - (float)ky, cy);
-                cubic_coeffs(sx - (float)kx, cx);
-#pragma unroll
-                for (int t = 0; t < NT; ++t) { wy[i][t] = cy[t]; wx[i][t] = cx[t]; }
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            int o = MODE == 0 ? t : t - 1;
-            iy[t] = clampi(ky + o, 0, h - 1);
-            ix[t] = clampi(kx + o, 0, w - 1);
-        }
-        const float* base = low + (size_t)n * C * h * w;
-        for (int c = 0; c < C; ++c) {
-            const float* pc = base + (size_t)c * h * w;
-            float tap[NT][NT];
+struct K3LowParams {
+    const float* low;
+    const long long* labels;
+    unsigned long long* confmat;
+    unsigned long long* per_image;
+    long long* pred_out;
+    int C, h, w, H, W, lh, lw;
+    int s, off, q, tgy, tgx;
+    float rs;
+};
+
+// fast argmax update (values known finite)
+__device__ __forceinline__ void am_upd(float& best, int& idx, float v, int c) {
+    if (v > best) { best = v; idx = c; }
+}
+
+template <int MODE, int BPS>   // MODE 0 bilinear / 1 bicubic
+__global__ void __launch_bounds__(128)
+k3_low_fast_kernel(const K3LowParams P) {
+    constexpr int LPG = BPS * BPS;
+    constexpr int NT = MODE == 0 ? 2 : 4;                   // taps per dimension
+    constexpr int HALO = MODE == 0 ? 0 : 1;                 // extra cells before the first tap
+    extern __shared__ float st[];                           // [C][ncy][ncx] source cells (index-clamped)
+    const int C = P.C;
+    const int ncy = P.tgy + NT - 1, ncx = P.tgx + NT - 1;
+    const int cs = ncy * ncx;
+    const int n = blockIdx.z;
+    const int GY0 = blockIdx.y * P.tgy, GX0 = blockIdx.x * P.tgx;
+    const int cy0 = GY0 - 1 - HALO, cx0 = GX0 - 1 - HALO;   // first (unclamped) cell of the tile
+    const float* lowb = P.low + (size_t)n * C * P.h * P.w;
+
+    // ---- stage: cell (i,j) of the tile holds source pixel (clamp(cy0+i), clamp(cx0+j)) -------------
+    for (int idx = threadIdx.x; idx < C * cs; idx += 128) {
+        const int c = idx / cs, r = idx - c * cs;
+        const int i = r / ncx, j = r - i * ncx;
+        const int gy = clampi(cy0 + i, 0, P.h - 1), gx = clampi(cx0 + j, 0, P.w - 1);
+        cp_async4_k3(st + idx, lowb + ((size_t)c * P.h + gy) * P.w + gx);
+    }
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+
+    const int g = threadIdx.x / LPG, u = threadIdx.x % LPG;
+    const int tgy = g / P.tgx, tgx = g - tgy * P.tgx;
+    const int uy = u / BPS, ux = u % BPS;
+    const int ky = GY0 + tgy - 1, kx = GX0 + tgx - 1;       // floor(src) of the group, -1 .. h-1
+    const int by = ky * BPS + P.q + uy, bx = kx * BPS + P.q + ux;
+    const int y0 = 4 * by - P.off, x0 = 4 * bx - P.off;
+    const bool group_in = ky < P.h && kx < P.w;
+    // offset of tap (0,0) of this group in the tile: cell (ky - HALO, kx - HALO)
+    const int o00 = (ky - HALO - cy0) * ncx + (kx - HALO - cx0);
+    const float rs = P.rs;
+    const float ty0 = ((float)y0 + 0.5f) * rs - 0.5f - (float)ky;     // fractional source position of row 0
+    const float tx0 = ((float)x0 + 0.5f) * rs - 0.5f - (float)kx;
+
+    // ---- non-finite taps?  (lanes of the group split the classes) -----------------------------------
+    bool exotic = false;
+    if (group_in) {
+        for (int c = u; c < C; c += LPG) {
+            const float* p = st + (size_t)c * cs + o00;
 #pragma unroll
             for (int a = 0; a < NT; ++a)
 #pragma unroll
-                for (int b = 0; b < NT; ++b) tap[a][b] = __ldg(pc + iy[a] * w + ix[b]);
-            // horizontal interpolation of every tap row at the 4 output columns
-            float hrow[NT][4];
+                for (int b = 0; b < NT; ++b) exotic |= !(fabsf(p[a * ncx + b]) < INFINITY);
+        }
+    }
+    exotic = __any_sync(0xffffffffu, exotic);
+
+    float best[16];
+    int bidx[16];
 #pragma unroll
-            for (int a = 0; a < NT; ++a)
+    for (int i = 0; i < 16; ++i) { best[i] = -INFINITY; bidx[i] = 0; }
+
+    if (group_in && !exotic) {
+        if constexpr (MODE == 0) {
+            // bilinear; at the clamped borders both taps are the same cell, so any lambda is exact
+#pragma unroll 2
+            for (int c = 0; c < C; ++c) {
+                const float* p = st + (size_t)c * cs + o00;
+                const float a = p[0], b = p[1], cc = p[ncx], d = p[ncx + 1];
+                const float da = cc - a, db = d - b, dd = db - da;
+                const float L0 = fmaf(ty0, da, a), R0 = fmaf(ty0, db, b);
+                const float rl = R0 - L0;
+                const float l00 = fmaf(tx0, rl, L0);
+                const float Pv = fmaf(tx0, dd, da) * rs;        // row step of column 0
+                const float Q0 = rl * rs;                       // column step in row 0
+                const float Tv = dd * rs * rs;                  // growth of the column step per row
+                float2 v01 = make_float2(l00, l00 + Pv), s01 = make_float2(Q0, Q0 + Tv);
+                const float2 P2 = make_float2(Pv + Pv, Pv + Pv), T2 = make_float2(Tv + Tv, Tv + Tv);
+                float2 v23 = fadd2f(v01, P2), s23 = fadd2f(s01, T2);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float acc = tap[a][0] * wx[j][0];
-#pragma unroll
-                    for (int b = 1; b < NT; ++b) acc = fmaf(tap[a][b], wx[j][b], acc);
-                    hrow[a][j] = acc;
+                    am_upd(best[0 * 4 + j], bidx[0 * 4 + j], v01.x, c);
+                    am_upd(best[1 * 4 + j], bidx[1 * 4 + j], v01.y, c);
+                    am_upd(best[2 * 4 + j], bidx[2 * 4 + j], v23.x, c);
+                    am_upd(best[3 * 4 + j], bidx[3 * 4 + j], v23.y, c);
+                    if (j < 3) { v01 = fadd2f(v01, s01); v23 = fadd2f(v23, s23); }
                 }
+            }
+        } else {
+            // bicubic: ATen order  out = sum_a wy[a] * (sum_b wx[b] * tap[a][b]), fmaf chains
+            float2 wxp[2][4];      // (wx[j][b], wx[j+1][b]) for column pairs j = 0, 2
+            float wy[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cubic_coeffs(ty0 + (float)i * rs, wy[i]);
+            {
+                float wx[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cubic_coeffs(tx0 + (float)j * rs, wx[j]);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    wxp[0][b] = make_float2(wx[0][b], wx[1][b]);
+                    wxp[1][b] = make_float2(wx[2][b], wx[3][b]);
+                }
+            }
+#pragma unroll 1
+            for (int c = 0; c < C; ++c) {
+                const float* p = st + (size_t)c * cs + o00;
+                float2 hr[4][2];                                 // horizontal result of tap row a, column pairs
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const float t0 = p[a * ncx], t1 = p[a * ncx + 1], t2 = p[a * ncx + 2], t3 = p[a * ncx + 3];
+#pragma unroll
+                    for (int jp = 0; jp < 2; ++jp) {
+                        float2 acc = fmul2f(make_float2(t0, t0), wxp[jp][0]);
+                        acc = ffma2f(make_float2(t1, t1), wxp[jp][1], acc);
+                        acc = ffma2f(make_float2(t2, t2), wxp[jp][2], acc);
+                        hr[a][jp] = ffma2f(make_float2(t3, t3), wxp[jp][3], acc);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int jp = 0; jp < 2; ++jp) {
+                        float2 acc = fmul2f(hr[0][jp], make_float2(wy[i][0], wy[i][0]));
+                        acc = ffma2f(hr[1][jp], make_float2(wy[i][1], wy[i][1]), acc);
+                        acc = ffma2f(hr[2][jp], make_float2(wy[i][2], wy[i][2]), acc);
+                        acc = ffma2f(hr[3][jp], make_float2(wy[i][3], wy[i][3]), acc);
+                        am_upd(best[i * 4 + jp * 2], bidx[i * 4 + jp * 2], acc.x, c);
+                        am_upd(best[i * 4 + jp * 2 + 1], bidx[i * 4 + jp * 2 + 1], acc.y, c);
+                    }
+            }
+        }
+    } else if (group_in) {
+        // exact per-pixel path with the NaN / +inf rule (rare)
+        ArgmaxState stt[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) am_init(stt[i]);
+        for (int c = 0; c < C; ++c) {
+            const float* p = st + (size_t)c * cs + o00;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float acc = hrow[0][j] * wy[i][0];
+                    float wyv[NT], wxv[NT];
+                    const float ty = ty0 + (float)i * rs, tx = tx0 + (float)j * rs;
+                    if (MODE == 0) { wyv[0] = 1.f - ty; wyv[1] = ty; wxv[0] = 1.f - tx; wxv[1] = tx; }
+                    else {
+                        float cy[4], cx[4];
+                        cubic_coeffs(ty, cy); cubic_coeffs(tx, cx);
 #pragma unroll
-                    for (int a = 1; a < NT; ++a) acc = fmaf(hrow[a][j], wy[i][a], acc);
-                    am_update(st[i * 4 + j], acc, c);
+                        for (int a = 0; a < NT; ++a) { wyv[a] = cy[a]; wxv[a] = cx[a]; }
+                    }
+                    float acc = 0.f;
+#pragma unroll
+                    for (int a = 0; a < NT; ++a) {
+                        float r = p[a * ncx] * wxv[0];
+#pragma unroll
+                        for (int b = 1; b < NT; ++b) r = fmaf(p[a * ncx + b], wxv[b], r);
+                        acc = a == 0 ? r * wyv[0] : fmaf(r, wyv[a], acc);
+                    }
+                    am_update(stt[i * 4 + j], acc, c);
                 }
         }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) bidx[i] = am_result(stt[i]);
     }
-    const int ry = H / lh, rx = W / lw;
-    unsigned long long* pimg = per_image ? per_image + (size_t)n * 3 * C : nullptr;
+
+    // ---- labels, predictions, counts ------------------------------------------------------------------
+    const int ry = P.H / P.lh, rx = P.W / P.lw;
+    unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int y = y0 + i, x = x0 + j;
-            bool valid = active && y >= 0 && y < H && x >= 0 && x < W;
-            int t = 0, pr = am_result(st[i * 4 + j]);
+            const int y = y0 + i, x = x0 + j;
+            bool valid = group_in && y >= 0 && y < P.H && x >= 0 && x < P.W;
+            int t = 0;
+            const int pr = bidx[i * 4 + j];
             if (valid) {
-                long long tl = labels[((size_t)n * lh + y / ry) * lw + x / rx];
-                if (pred_out) pred_out[((size_t)n * H + y) * W + x] = pr;
+                const long long tl = __ldg(P.labels + ((size_t)n * P.lh + y / ry) * P.lw + x / rx);
+                if (P.pred_out) P.pred_out[((size_t)n * P.H + y) * P.W + x] = pr;
                 valid = tl >= 0 && tl < C;
                 t = (int)tl;
             }
-            hist_add(hist, confmat, pimg, C, valid, t, pr);
+            hist_add(nullptr, P.confmat, pimg, C, valid, t, pr);
         }
-    if (hist) hist_flush(hist, confmat, pimg, C);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -469,22 +600,36 @@ extern "C" int lc2is_argmax_confmat_lowres(const float* d_low, int N, int C, int
     const int use_hist = C <= K3_SMEM_HIST_MAX_C;
     const size_t smem = use_hist ? (size_t)C * C * sizeof(int) : 0;
     int s = 0;
-    if (fast_scale(h, w, H, W, &s)) {
+    if (fast_scale(h, w, H, W, &s) && s <= 16) {
         BlockGeom g = make_geom(H, W, s);
-        dim3 grid((g.nbx + 15) / 16, (g.nby + 15) / 16, N);
-        if (mode == LC2IS_BILINEAR) {
-            if (int e = set_smem(k3_low_fast_kernel<0>, smem)) return e;
-            k3_low_fast_kernel<0><<<grid, K3_THREADS, smem, st>>>(
-                d_low, C, h, w, H, W, s, g.off, g.nby, g.nbx, g.rs, (const long long*)d_labels, lh, lw,
-                (unsigned long long*)d_confmat, (unsigned long long*)d_per_image, (long long*)d_pred, use_hist);
-        } else {
-            if (int e = set_smem(k3_low_fast_kernel<1>, smem)) return e;
-            k3_low_fast_kernel<1><<<grid, K3_THREADS, smem, st>>>(
-                d_low, C, h, w, H, W, s, g.off, g.nby, g.nbx, g.rs, (const long long*)d_labels, lh, lw,
-                (unsigned long long*)d_confmat, (unsigned long long*)d_per_image, (long long*)d_pred, use_hist);
+        K3LowParams P;
+        P.low = d_low; P.labels = (const long long*)d_labels; P.confmat = (unsigned long long*)d_confmat;
+        P.per_image = (unsigned long long*)d_per_image; P.pred_out = (long long*)d_pred;
+        P.C = C; P.h = h; P.w = w; P.H = H; P.W = W; P.lh = lh; P.lw = lw;
+        P.s = s; P.off = g.off; P.rs = g.rs;
+        const int bps = s / 4;
+        P.q = (g.off + s / 2) / 4;
+        P.tgy = 8 / bps; P.tgx = 16 / bps;
+        const int nt = mode == LC2IS_BILINEAR ? 2 : 4;
+        const size_t tile = (size_t)C * (P.tgy + nt - 1) * (P.tgx + nt - 1) * sizeof(float);
+        if (tile <= 200 * 1024) {
+            dim3 grid((w + 1 + P.tgx - 1) / P.tgx, (h + 1 + P.tgy - 1) / P.tgy, N);
+            auto launch = [&](auto kernel) -> int {
+                if (int e = set_smem(kernel, tile)) return e;
+                kernel<<<grid, 128, tile, st>>>(P);
+                return 0;
+            };
+            int e;
+            if (mode == LC2IS_BILINEAR)
+                e = s == 4 ? launch(k3_low_fast_kernel<0, 1>) : s == 8 ? launch(k3_low_fast_kernel<0, 2>)
+                                                                       : launch(k3_low_fast_kernel<0, 4>);
+            else
+                e = s == 4 ? launch(k3_low_fast_kernel<1, 1>) : s == 8 ? launch(k3_low_fast_kernel<1, 2>)
+                                                                       : launch(k3_low_fast_kernel<1, 4>);
+            if (e) return e;
+            LC2IS_CHECK_LAUNCH("k3_low_fast_kernel");
+            return 0;
         }
-        LC2IS_CHECK_LAUNCH("k3_low_fast_kernel");
-        return 0;
     }
     // generic: ATen scale for size= mode is (float)in / out
     const float sy = (float)h / (float)H, sx = (float)w / (float)W;
