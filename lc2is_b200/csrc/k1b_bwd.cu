@@ -25,13 +25,13 @@ constexpr int KB_THREADS = 192;
 // r[m] = sum_c G[m,c]*L[m,c]   ;   rt[set][c] += sum_m G[m,c]*L[m,c]
 // One thread per pixel (coalesced along pixels for every class); the per-class column sums are
 // reduced with warp shuffles into per-warp shared slots, combined once at the end.
-constexpr int PREP_CMAX = 1024;
-__global__ void __launch_bounds__(256)
+constexpr int PREP_T = 64;        // small CTAs: the 32^2 grid has only 16K pixels - spread them over all SMs
+__global__ void __launch_bounds__(PREP_T)
 k1b_prep_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ L, int B, int C, int C_pad, int hw,
                 int n_sets, float* __restrict__ r, float* __restrict__ rt) {
-    extern __shared__ float part[];                       // [8 warps][C]
+    extern __shared__ float part[];                       // [PREP_T/32 warps][C]
     const int b = blockIdx.y;
-    const int p = blockIdx.x * 256 + threadIdx.x;
+    const int p = blockIdx.x * PREP_T + threadIdx.x;
     const bool in = p < hw;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const __nv_bfloat16* g = G + (size_t)b * C_pad * hw + p;
@@ -53,10 +53,10 @@ k1b_prep_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ L
     if (in) r[(size_t)b * hw + p] = acc;
     __syncthreads();
     float* rts = rt + (size_t)(n_sets > 1 ? b : 0) * C;
-    for (int c = threadIdx.x; c < C; c += 256) {
+    for (int c = threadIdx.x; c < C; c += PREP_T) {
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += part[w * C + c];
+        for (int w = 0; w < PREP_T / 32; ++w) t += part[w * C + c];
         if (t != 0.f) atomicAdd(rts + c, t);
     }
 }
@@ -406,11 +406,11 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits_bf16, const flo
 
     // ---- projections r, rt -----------------------------------------------------------------------
     if (normalize) {
-        dim3 grid((hw + 255) / 256, B);
-        const size_t psm = (size_t)8 * C * sizeof(float);
+        dim3 grid((hw + PREP_T - 1) / PREP_T, B);
+        const size_t psm = (size_t)(PREP_T / 32) * C * sizeof(float);
         if (psm > 48 * 1024)
             LC2IS_CUDA(cudaFuncSetAttribute(k1b_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-        k1b_prep_kernel<<<grid, 256, psm, st>>>((const __nv_bfloat16*)d_grad_logits_bf16, d_logits, B, C, C_pad, hw,
+        k1b_prep_kernel<<<grid, PREP_T, psm, st>>>((const __nv_bfloat16*)d_grad_logits_bf16, d_logits, B, C, C_pad, hw,
                                                 n_sets, d_r, d_rt);
         LC2IS_CHECK_LAUNCH("k1b_prep_kernel");
     }

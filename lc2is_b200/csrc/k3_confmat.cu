@@ -18,7 +18,8 @@
 namespace lc2is {
 
 constexpr int K3_THREADS = 256;
-constexpr int K3_SMEM_HIST_MAX_C = 224;   // 224*224*4 = 200,704 B
+constexpr int K3_SMEM_HIST_MAX_C = 300;   // 16-bit counters, two per word: 300*300*2 = 180,000 B
+constexpr int K3_FLUSH_ITEMS = 60;        // flush before a 16-bit counter can overflow (60 * 1024 px < 65536)
 
 struct ArgmaxState {
     float best;
@@ -43,7 +44,7 @@ __device__ __forceinline__ void hist_add(int* hist, unsigned long long* confmat,
     if ((int)(threadIdx.x & 31) == leader) {
         int cnt = __popc(m);
         if (hist) {
-            atomicAdd(&hist[key], cnt);
+            atomicAdd(&hist[key >> 1], cnt << ((key & 1) * 16));     // two 16-bit counters per word
         } else {
             atomicAdd(&confmat[key], (unsigned long long)cnt);
             if (per_img) {
@@ -59,16 +60,24 @@ __device__ __forceinline__ void hist_add(int* hist, unsigned long long* confmat,
 __device__ __forceinline__ void hist_flush(int* hist, unsigned long long* confmat,
                                            unsigned long long* per_img, int C) {
     __syncthreads();
-    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
-        int v = hist[i];
-        if (v) {
-            hist[i] = 0;
-            atomicAdd(&confmat[i], (unsigned long long)v);
-            if (per_img) {
-                int t = i / C, p = i - t * C;
-                if (t == p) atomicAdd(&per_img[t], (unsigned long long)v);
-                atomicAdd(&per_img[C + t], (unsigned long long)v);
-                atomicAdd(&per_img[2 * C + p], (unsigned long long)v);
+    const int nw = (C * C + 1) >> 1;
+    for (int wi = threadIdx.x; wi < nw; wi += blockDim.x) {
+        const unsigned word = (unsigned)hist[wi];
+        if (word) {
+            hist[wi] = 0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const unsigned v = (word >> (16 * k)) & 0xffffu;
+                const int i = wi * 2 + k;
+                if (v) {
+                    atomicAdd(&confmat[i], (unsigned long long)v);
+                    if (per_img) {
+                        int t = i / C, p = i - t * C;
+                        if (t == p) atomicAdd(&per_img[t], (unsigned long long)v);
+                        atomicAdd(&per_img[C + t], (unsigned long long)v);
+                        atomicAdd(&per_img[2 * C + p], (unsigned long long)v);
+                    }
+                }
             }
         }
     }
@@ -113,7 +122,7 @@ k3_full_kernel(const T* __restrict__ logits, int N, int C, int H, int W,
     extern __shared__ int hist_smem[];
     int* hist = use_smem_hist ? hist_smem : nullptr;
     constexpr int PIX = VEC ? Vec<T>::PIX : 1;
-    constexpr int U = 8;
+    constexpr int U = VEC ? 16 : 8;     // independent 128-bit loads in flight per thread
     const long long HW = (long long)H * W;
     const int chunk = K3_THREADS * PIX;
     const int chunks_per_img = (int)((HW + chunk - 1) / chunk);
@@ -124,18 +133,21 @@ k3_full_kernel(const T* __restrict__ logits, int N, int C, int H, int W,
     const int ry = H / lh, rx = W / lw;
 
     if (hist) {
-        for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+        for (int i = threadIdx.x; i < (C * C + 1) / 2; i += blockDim.x) hist[i] = 0;
         __syncthreads();
     }
     int cur_img = -1;
+    int since_flush = 0;
     for (long long it = it0; it < it1; ++it) {
         const int n = (int)(it / chunks_per_img);
         const int k = (int)(it - (long long)n * chunks_per_img);
-        if (n != cur_img) {
+        if (n != cur_img || since_flush >= K3_FLUSH_ITEMS) {
             if (hist && cur_img >= 0)
                 hist_flush(hist, confmat, per_image ? per_image + (size_t)cur_img * 3 * C : nullptr, C);
             cur_img = n;
+            since_flush = 0;
         }
+        ++since_flush;
         const long long p0 = (long long)k * chunk + (long long)threadIdx.x * PIX;
         const bool in = p0 < HW;
         ArgmaxState st[PIX];
@@ -454,14 +466,16 @@ k3_low_gen_kernel(const float* __restrict__ low, int C, int h, int w, int H, int
     int* hist = use_smem_hist ? hist_smem : nullptr;
     const int n = blockIdx.y;
     if (hist) {
-        for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+        for (int i = threadIdx.x; i < (C * C + 1) / 2; i += blockDim.x) hist[i] = 0;
         __syncthreads();
     }
     constexpr int NT = MODE == 0 ? 2 : 4;
     const long long HW = (long long)H * W;
     const int ry = H / lh, rx = W / lw;
     unsigned long long* pimg = per_image ? per_image + (size_t)n * 3 * C : nullptr;
+    int since_flush = 0;
     for (long long p0 = (long long)blockIdx.x * K3_THREADS; p0 < HW; p0 += (long long)gridDim.x * K3_THREADS) {
+        if (hist && ++since_flush > 200) { hist_flush(hist, confmat, pimg, C); since_flush = 0; }   // 16-bit counters
         const long long p = p0 + threadIdx.x;
         bool valid = p < HW;
         int pr = 0, t = 0;
@@ -553,9 +567,9 @@ extern "C" int lc2is_argmax_confmat(const void* d_logits, int dtype, int N, int 
     if (int e = check_labels_ratio(H, W, lh, lw)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int use_hist = C <= K3_SMEM_HIST_MAX_C;
-    const size_t smem = use_hist ? (size_t)C * C * sizeof(int) : 0;
+    const size_t smem = use_hist ? ((size_t)C * C + 1) / 2 * sizeof(int) : 0;
     const long long HW = (long long)H * W;
-    const int ctas_per_sm = smem > 100 * 1024 ? 1 : 2;
+    const int ctas_per_sm = smem > 100 * 1024 ? 1 : (smem > 50 * 1024 ? 2 : 4);
     auto launch = [&](auto kernel, int pix, auto ptr) -> int {
         if (int e = set_smem(kernel, smem)) return e;
         long long chunk = (long long)K3_THREADS * pix;
@@ -598,7 +612,7 @@ extern "C" int lc2is_argmax_confmat_lowres(const float* d_low, int N, int C, int
     if (int e = check_labels_ratio(H, W, lh, lw)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int use_hist = C <= K3_SMEM_HIST_MAX_C;
-    const size_t smem = use_hist ? (size_t)C * C * sizeof(int) : 0;
+    const size_t smem = use_hist ? ((size_t)C * C + 1) / 2 * sizeof(int) : 0;
     int s = 0;
     if (fast_scale(h, w, H, W, &s) && s <= 16) {
         BlockGeom g = make_geom(H, W, s);
