@@ -165,13 +165,15 @@ int lc2is_argmax_confmat_lowres(const float* d_low, int N, int C, int h, int w, 
  * h_out_loss (mean CE), h_out_n_valid, h_out_confmat [C,C] (overwritten).
  * d_ws: device workspace of lc2is_head_step_workspace(...) bytes (caller-allocated).
  * do_backward: also run K1b (gradients stay on the device, in the workspace).
+ * copy_stream: optional second stream (NULL = none): the batch is then cut into 4 chunks and the H2D copy
+ *   of chunk i+1 overlaps the kernels of chunk i (the 1/N_valid scale is applied at the end, in K1b).
  */
 int64_t lc2is_head_step_workspace(int B, int hw, int D, int C, int H, int W);
 int lc2is_head_step_host(const void* h_v, const float* h_t, const int64_t* h_labels,
                          int B, int h, int w, int D, int C, int H, int W,
                          int64_t ignore_index, float logit_scale, int do_backward,
                          float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
-                         void* d_ws, lc2is_stream_t stream);
+                         void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream);
 
 #ifdef __cplusplus
 }

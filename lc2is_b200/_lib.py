@@ -55,7 +55,7 @@ SIGNATURES = {
                                             c_int, _p, _p, _p, _p]),
     "lc2is_head_step_workspace": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "lc2is_head_step_host": (c_int, [_p, _p, _p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
-                                     c_float, c_int, _p, _p, _p, _p, _p]),
+                                     c_float, c_int, _p, _p, _p, _p, _p, _p]),
 }
 for _name, (_res, _args) in SIGNATURES.items():
     _fn = getattr(_lib, _name)

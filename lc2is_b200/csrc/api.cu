@@ -109,21 +109,24 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
                                     int B, int h, int w, int D, int C, int H, int W,
                                     int64_t ignore_index, float logit_scale, int do_backward,
                                     float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
-                                    void* d_ws, lc2is_stream_t stream) {
+                                    void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream) {
     if (int e = ensure_device()) return e;
     if (!h_v || !h_t || !h_labels || !h_out_loss || !h_out_n_valid || !h_out_confmat || !d_ws)
         return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (B <= 0) return fail(LC2IS_ERR_SHAPE, "B must be positive%s");
     cudaStream_t st = (cudaStream_t)stream;
+    cudaStream_t cst = copy_stream ? (cudaStream_t)copy_stream : st;
+    const bool piped = copy_stream && copy_stream != stream;
     const int hw = h * w;
     const StepWs L = step_layout(B, hw, D, C, H, W);
     uint8_t* ws = (uint8_t*)d_ws;
     const size_t M = (size_t)B * hw;
-    void* d_v = ws + L.v_in;
+    uint8_t* d_v = ws + L.v_in;
     int64_t* d_labels = (int64_t*)(ws + L.labels);
     float* d_t = (float*)(ws + L.t_in);
     void* d_that = ws + L.t_hat;
     float* d_invt = (float*)(ws + L.inv_t);
-    void* d_vhat = ws + L.v_hat;
+    uint8_t* d_vhat = ws + L.v_hat;
     float* d_invv = (float*)(ws + L.inv_v);
     float* d_logits = (float*)(ws + L.logits);
     float* d_glow = (float*)(ws + L.grad_low);
@@ -134,33 +137,76 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
     float* d_loss = (float*)(ws + L.scalars + 20);
     int64_t* d_cm = (int64_t*)(ws + L.confmat);
 
-    // H2D of the batch (engine.py:75 / :145)
-    LC2IS_CUDA(cudaMemcpyAsync(d_labels, h_labels, (size_t)B * H * W * 8, cudaMemcpyHostToDevice, st));
-    LC2IS_CUDA(cudaMemcpyAsync(d_t, h_t, (size_t)C * D * 4, cudaMemcpyHostToDevice, st));
-    LC2IS_CUDA(cudaMemcpyAsync(d_v, h_v, M * D * 2, cudaMemcpyHostToDevice, st));
-    LC2IS_CUDA(cudaMemsetAsync(ws + L.scalars, 0, 256, st));
-    LC2IS_CUDA(cudaMemsetAsync(d_cm, 0, (size_t)C * C * 8, st));
-
-    if (int e = lc2is_count_valid(d_labels, (int64_t)B * H * W, ignore_index, d_nvalid, stream)) return e;
-    if (int e = lc2is_mean_scale(d_nvalid, 1.0f, d_gscale, stream)) return e;
-    if (int e = lc2is_proto_normalize(d_t, 1, C, D, 1, d_that, d_invt, stream)) return e;
-    if (int e = lc2is_cosine_logits_fwd(d_v, LC2IS_BF16, B, hw, D, d_that, 1, C, 1, logit_scale, d_vhat, d_invv,
-                                        d_logits, stream)) return e;
-    if (int e = lc2is_upsample_ce_fwd_bwd(d_logits, d_labels, B, C, h, w, H, W, ignore_index, d_gscale, d_loss_sum,
-                                          d_glow, do_backward ? d_gbf : nullptr, stream)) return e;
-    if (do_backward) {
-        LC2IS_CUDA(cudaMemsetAsync(ws + L.grad_t, 0, (size_t)C * D * 4, st));
-        if (int e = lc2is_cosine_logits_bwd(d_gbf, d_logits, d_vhat, d_invv, d_that, d_invt, B, hw, D, 1, C, 1,
-                                            logit_scale, nullptr, ws + L.grad_v, LC2IS_BF16,
-                                            (float*)(ws + L.grad_t), ws + L.bwd_ws, stream)) return e;
+    // The batch is cut into chunks: chunk i+1 is copied host->device on `copy_stream` while the
+    // kernels of chunk i run on `stream` (engine.py:75 / :145 copy the whole batch up front).
+    // Gradients are produced un-normalised (g = 1) per chunk; the 1/N_valid of the 'mean' reduction is
+    // only known after the last chunk and is applied by K1b through its device-side grad_scale.
+    const int nchunk = piped ? (B < 4 ? B : 4) : 1;
+    const int bc = (B + nchunk - 1) / nchunk;
+    cudaEvent_t ev_start = nullptr, ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
+    auto cleanup = [&]() {
+        if (ev_start) cudaEventDestroy(ev_start);
+        for (auto& e : ev_copy) if (e) cudaEventDestroy(e);
+    };
+#define STEP_CUDA(call)                                                  \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) { cleanup(); return lc2is::cuda_fail(e__, #call); } \
+    } while (0)
+#define STEP_RC(call)                                                    \
+    do {                                                                 \
+        int rc__ = (call);                                               \
+        if (rc__) { cleanup(); return rc__; }                            \
+    } while (0)
+    if (piped) {
+        STEP_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        for (int i = 0; i < nchunk; ++i) STEP_CUDA(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
+        STEP_CUDA(cudaEventRecord(ev_start, st));           // the workspace is free once earlier work on
+        STEP_CUDA(cudaStreamWaitEvent(cst, ev_start, 0));   // `stream` has drained
     }
-    if (int e = lc2is_argmax_confmat_lowres(d_logits, B, C, h, w, H, W, LC2IS_BILINEAR, d_labels, H, W, d_cm,
-                                            nullptr, nullptr, stream)) return e;
-    if (int e = lc2is_finalize_loss(d_loss_sum, d_nvalid, d_loss, stream)) return e;
+    STEP_CUDA(cudaMemsetAsync(ws + L.scalars, 0, 256, st));
+    STEP_CUDA(cudaMemsetAsync(d_cm, 0, (size_t)C * C * 8, st));
+    STEP_CUDA(cudaMemcpyAsync(d_t, h_t, (size_t)C * D * 4, cudaMemcpyHostToDevice, cst));
+    for (int i = 0; i < nchunk; ++i) {
+        const int b0 = i * bc, nb = (b0 + bc <= B ? bc : B - b0);
+        if (nb <= 0) break;
+        const size_t lab_off = (size_t)b0 * H * W, v_off = (size_t)b0 * hw * D * 2;
+        STEP_CUDA(cudaMemcpyAsync(d_labels + lab_off, h_labels + lab_off, (size_t)nb * H * W * 8,
+                                  cudaMemcpyHostToDevice, cst));
+        STEP_CUDA(cudaMemcpyAsync(d_v + v_off, (const uint8_t*)h_v + v_off, (size_t)nb * hw * D * 2,
+                                  cudaMemcpyHostToDevice, cst));
+        if (piped) {
+            STEP_CUDA(cudaEventRecord(ev_copy[i], cst));
+            STEP_CUDA(cudaStreamWaitEvent(st, ev_copy[i], 0));
+        }
+        STEP_RC(lc2is_count_valid(d_labels + lab_off, (int64_t)nb * H * W, ignore_index, d_nvalid, stream));
+        if (i == 0) STEP_RC(lc2is_proto_normalize(d_t, 1, C, D, 1, d_that, d_invt, stream));
+        float* lg = d_logits + (size_t)b0 * C * hw;
+        STEP_RC(lc2is_cosine_logits_fwd(d_v + v_off, LC2IS_BF16, nb, hw, D, d_that, 1, C, 1, logit_scale,
+                                        d_vhat + v_off, d_invv + (size_t)b0 * hw, lg, stream));
+        STEP_RC(lc2is_upsample_ce_fwd_bwd(lg, d_labels + lab_off, nb, C, h, w, H, W, ignore_index, nullptr,
+                                          d_loss_sum, do_backward ? d_glow + (size_t)b0 * C * hw : nullptr,
+                                          do_backward ? (uint8_t*)d_gbf + (size_t)b0 * class_pad(C) * hw * 2 : nullptr,
+                                          stream));
+        STEP_RC(lc2is_argmax_confmat_lowres(lg, nb, C, h, w, H, W, LC2IS_BILINEAR, d_labels + lab_off, H, W, d_cm,
+                                            nullptr, nullptr, stream));
+    }
+    STEP_RC(lc2is_mean_scale(d_nvalid, 1.0f, d_gscale, stream));
+    if (do_backward) {
+        STEP_CUDA(cudaMemsetAsync(ws + L.grad_t, 0, (size_t)C * D * 4, st));
+        STEP_RC(lc2is_cosine_logits_bwd(d_gbf, d_logits, d_vhat, d_invv, d_that, d_invt, B, hw, D, 1, C, 1,
+                                        logit_scale, d_gscale, ws + L.grad_v, LC2IS_BF16,
+                                        (float*)(ws + L.grad_t), ws + L.bwd_ws, stream));
+    }
+    STEP_RC(lc2is_finalize_loss(d_loss_sum, d_nvalid, d_loss, stream));
     // D2H of the step's results (engine.py:108 .item(); :162-163)
-    LC2IS_CUDA(cudaMemcpyAsync(h_out_loss, d_loss, 4, cudaMemcpyDeviceToHost, st));
-    LC2IS_CUDA(cudaMemcpyAsync(h_out_n_valid, d_nvalid, 8, cudaMemcpyDeviceToHost, st));
-    LC2IS_CUDA(cudaMemcpyAsync(h_out_confmat, d_cm, (size_t)C * C * 8, cudaMemcpyDeviceToHost, st));
-    LC2IS_CUDA(cudaStreamSynchronize(st));
+    STEP_CUDA(cudaMemcpyAsync(h_out_loss, d_loss, 4, cudaMemcpyDeviceToHost, st));
+    STEP_CUDA(cudaMemcpyAsync(h_out_n_valid, d_nvalid, 8, cudaMemcpyDeviceToHost, st));
+    STEP_CUDA(cudaMemcpyAsync(h_out_confmat, d_cm, (size_t)C * C * 8, cudaMemcpyDeviceToHost, st));
+    STEP_CUDA(cudaStreamSynchronize(st));
+    cleanup();
+#undef STEP_CUDA
+#undef STEP_RC
+    (void)M;
     return 0;
 }

@@ -23,42 +23,42 @@ constexpr int KB_THREADS = 192;
 
 // ---------------------------------------------------------------------------------------------
 // r[m] = sum_c G[m,c]*L[m,c]   ;   rt[set][c] += sum_m G[m,c]*L[m,c]
-// One thread per pixel (coalesced along pixels for every class); the per-class column sums are
-// reduced with warp shuffles into per-warp shared slots, combined once at the end.
-constexpr int PREP_T = 64;        // small CTAs: the 32^2 grid has only 16K pixels - spread them over all SMs
-__global__ void __launch_bounds__(PREP_T)
+// CTA = 64 pixels x 4 class quarters (256 threads): thread (quarter q, pixel) walks the classes of its
+// quarter (coalesced along pixels); class sums are reduced with warp shuffles (one warp = 32 pixels of one
+// quarter) and added to rt with one reduction per (warp, class); pixel sums meet in shared memory.
+constexpr int PREP_PX = 64, PREP_Q = 4;
+__global__ void __launch_bounds__(PREP_PX * PREP_Q)
 k1b_prep_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ L, int B, int C, int C_pad, int hw,
                 int n_sets, float* __restrict__ r, float* __restrict__ rt) {
-    extern __shared__ float part[];                       // [PREP_T/32 warps][C]
+    __shared__ float racc[PREP_Q][PREP_PX];
     const int b = blockIdx.y;
-    const int p = blockIdx.x * PREP_T + threadIdx.x;
+    const int px = threadIdx.x % PREP_PX, q = threadIdx.x / PREP_PX;
+    const int p = blockIdx.x * PREP_PX + px;
     const bool in = p < hw;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
+    const int cq = (C + PREP_Q - 1) / PREP_Q;
+    const int c_lo = q * cq, c_hi = min(C, c_lo + cq);
     const __nv_bfloat16* g = G + (size_t)b * C_pad * hw + p;
     const float* l = L + (size_t)b * C * hw + p;
-    float acc = 0.f;
-    float mine = 0.f;                                     // lane (c & 31) keeps class c's warp sum
-    for (int c0 = 0; c0 < C; c0 += 32) {
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const int c = c0 + k;
-            float v = 0.f;
-            if (c < C && in) v = __bfloat162float(g[(size_t)c * hw]) * __ldg(l + (size_t)c * hw);
-            acc += v;
-            const float w = warp_sum(v);
-            if (lane == k) mine = w;
-        }
-        if (c0 + lane < C) part[warp * C + c0 + lane] = mine;
-    }
-    if (in) r[(size_t)b * hw + p] = acc;
-    __syncthreads();
     float* rts = rt + (size_t)(n_sets > 1 ? b : 0) * C;
-    for (int c = threadIdx.x; c < C; c += PREP_T) {
-        float t = 0.f;
+    float acc = 0.f;
+    for (int c0 = c_lo; c0 < c_hi; c0 += 8) {
+        float v[8];
 #pragma unroll
-        for (int w = 0; w < PREP_T / 32; ++w) t += part[w * C + c];
-        if (t != 0.f) atomicAdd(rts + c, t);
+        for (int k = 0; k < 8; ++k) {
+            const int c = c0 + k;
+            v[k] = (c < c_hi && in) ? __bfloat162float(g[(size_t)c * hw]) * __ldg(l + (size_t)c * hw) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            acc += v[k];
+            const float w = warp_sum(v[k]);
+            if (lane == 0 && c0 + k < c_hi && w != 0.f) atomicAdd(rts + c0 + k, w);
+        }
     }
+    racc[q][px] = acc;
+    __syncthreads();
+    if (q == 0 && in) r[(size_t)b * hw + p] = (racc[0][px] + racc[1][px]) + (racc[2][px] + racc[3][px]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -406,12 +406,9 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits_bf16, const flo
 
     // ---- projections r, rt -----------------------------------------------------------------------
     if (normalize) {
-        dim3 grid((hw + PREP_T - 1) / PREP_T, B);
-        const size_t psm = (size_t)(PREP_T / 32) * C * sizeof(float);
-        if (psm > 48 * 1024)
-            LC2IS_CUDA(cudaFuncSetAttribute(k1b_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-        k1b_prep_kernel<<<grid, PREP_T, psm, st>>>((const __nv_bfloat16*)d_grad_logits_bf16, d_logits, B, C, C_pad, hw,
-                                                n_sets, d_r, d_rt);
+        dim3 grid((hw + PREP_PX - 1) / PREP_PX, B);
+        k1b_prep_kernel<<<grid, PREP_PX * PREP_Q, 0, st>>>((const __nv_bfloat16*)d_grad_logits_bf16, d_logits, B, C,
+                                                           C_pad, hw, n_sets, d_r, d_rt);
         LC2IS_CHECK_LAUNCH("k1b_prep_kernel");
     }
     // ---- dV ----------------------------------------------------------------------------------------

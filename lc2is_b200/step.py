@@ -102,7 +102,8 @@ class HostStep:
     H2D / D2H copies inside the call (bench.py's `e2e`)."""
 
     def __init__(self, B: int, h: int, w: int, H: int, W: int, C: int, D: int = 512, ignore_index: int = 0,
-                 logit_scale: float = 1.0, backward: bool = True, device: Optional[torch.device] = None) -> None:
+                 logit_scale: float = 1.0, backward: bool = True, device: Optional[torch.device] = None,
+                 pipelined: bool = True) -> None:
         dev = device or torch.device("cuda", torch.cuda.current_device())
         self.args = (B, h, w, D, C, H, W)
         self.ignore_index, self.logit_scale, self.backward = ignore_index, logit_scale, backward
@@ -111,6 +112,7 @@ class HostStep:
         self.out_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.out_n_valid = torch.zeros(1, dtype=torch.int64).pin_memory()
         self.out_confmat = torch.zeros(C, C, dtype=torch.int64).pin_memory()
+        self.copy_stream = torch.cuda.Stream(device=dev) if pipelined else None
         self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + B * H * W * 8
         self.d2h_bytes = 4 + 8 + C * C * 8
 
@@ -119,5 +121,6 @@ class HostStep:
         assert h_v.dtype == torch.bfloat16 and not h_v.is_cuda and not h_labels.is_cuda
         check(lib.lc2is_head_step_host(ptr(h_v), ptr(h_t), ptr(h_labels), B, h, w, D, C, H, W, self.ignore_index,
                                        self.logit_scale, int(self.backward), ptr(self.out_loss),
-                                       ptr(self.out_n_valid), ptr(self.out_confmat), ptr(self.ws), stream_ptr()),
+                                       ptr(self.out_n_valid), ptr(self.out_confmat), ptr(self.ws), stream_ptr(),
+                                       self.copy_stream.cuda_stream if self.copy_stream is not None else None),
               "lc2is_head_step_host")
