@@ -288,10 +288,14 @@ def run_b200(a):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     k2_bytes = 2 * B * C * h * w * 4 + B * H * W * 8 + 8
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath) and a.geometry == "A" and B == 16 and C == 150:
+        traffic = json.load(open(tpath)).get("k2_fast_kernel<4>")     # from one `ncu --set full` capture
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
     roofline = {"kernel": "k2_fast_kernel (lc2is_upsample_ce_fwd_bwd: memset + fused upsample/CE fwd+bwd)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": k2_bytes, "kernel_us": k2_ms * 1e3,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": k2_bytes, "kernel_us": k2_ms * 1e3,
                 "note": "K2 is instruction-bound (ex2 + fp32 issue), not HBM-bound: see DESIGN.md; "
                         f"{B * C * H * W / (k2_ms * 1e-3) / 1e12:.3f} T softmax-elements/s"}
 

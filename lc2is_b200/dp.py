@@ -62,6 +62,19 @@ def allreduce_sum_(t: Tensor) -> Tensor:
     return t
 
 
+class _Done:
+    def wait(self):
+        return None
+
+
+def allreduce_sum_async(t: Tensor):
+    """SUM all-reduce issued asynchronously (NCCL: on its own stream after the current one; `wait()` makes
+    the current stream wait, never the host).  Returns an object with .wait()."""
+    if is_dist():
+        return dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+    return _Done()
+
+
 def allreduce_confmat_(confmat: Tensor) -> Tensor:
     """int64 [C,C] SUM all-reduce (180 kB at C=150, 5.7 MB at C=847)."""
     assert confmat.dtype == torch.int64

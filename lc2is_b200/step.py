@@ -56,22 +56,28 @@ class HeadStep:
         self.k2_events = None          # optional (start, stop) CUDA events around the K2 call
 
     def __call__(self, v: torch.Tensor, t: torch.Tensor, labels: torch.Tensor) -> None:
-        """v [B,hw,D] (bf16/fp32), t [C,D] fp32, labels [B,H,W] int64 - all on the device."""
+        """v [B,hw,D] (bf16/fp32), t [C,D] fp32, labels [B,H,W] int64 - all on the device.
+
+        Data-parallel ordering: the three collectives are issued asynchronously so that the valid-count
+        all-reduce hides behind K0/K1 and the confusion-matrix all-reduce behind K1b; only the final
+        gradient-bucket all-reduce is exposed."""
         st = stream_ptr()
         B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
+        dist_on = self.distributed
         self.scalars.zero_()
         self.confmat.zero_()
         if self.backward:
             self.bucket.zero_()
         check(lib.lc2is_count_valid(ptr(labels), labels.numel(), self.ignore_index, ptr(self.n_valid), st), "count_valid")
-        if self.distributed:
-            dp.global_valid_count_(self.n_valid)
-        check(lib.lc2is_mean_scale(ptr(self.n_valid), 1.0, ptr(self.gscale), st), "mean_scale")
+        w_valid = dp.allreduce_sum_async(self.n_valid) if dist_on else None
         check(lib.lc2is_proto_normalize(ptr(t), 1, C, D, int(self.normalize), ptr(self.t_hat), ptr(self.inv_t), st),
               "proto_normalize")
         check(lib.lc2is_cosine_logits_fwd(ptr(v), BF16 if v.dtype == torch.bfloat16 else F32, B, hw, D,
                                           ptr(self.t_hat), 1, C, int(self.normalize), self.logit_scale,
                                           ptr(self.v_hat), ptr(self.inv_v), ptr(self.logits), st), "cosine_logits_fwd")
+        if w_valid is not None:
+            w_valid.wait()                                        # stream-level wait, no host sync
+        check(lib.lc2is_mean_scale(ptr(self.n_valid), 1.0, ptr(self.gscale), st), "mean_scale")
         if self.k2_events is not None:
             self.k2_events[0].record()
         check(lib.lc2is_upsample_ce_fwd_bwd(ptr(self.logits), ptr(labels), B, C, h, w, H, W, self.ignore_index,
@@ -80,18 +86,20 @@ class HeadStep:
               "upsample_ce_fwd_bwd")
         if self.k2_events is not None:
             self.k2_events[1].record()
+        check(lib.lc2is_argmax_confmat_lowres(ptr(self.logits), B, C, h, w, H, W, BILINEAR, ptr(labels), H, W,
+                                              ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
+        w_cm = dp.allreduce_sum_async(self.confmat) if dist_on else None
         if self.backward:
             check(lib.lc2is_grad_to_bf16(ptr(self.grad_low), B, C, hw, ptr(self.grad_bf16), st), "grad_to_bf16")
             check(lib.lc2is_cosine_logits_bwd(ptr(self.grad_bf16), ptr(self.logits), ptr(self.v_hat), ptr(self.inv_v),
                                               ptr(self.t_hat), ptr(self.inv_t), B, hw, D, 1, C, int(self.normalize),
                                               self.logit_scale, None, ptr(self.grad_v), BF16, ptr(self.grad_t),
                                               ptr(self.bwd_ws), st), "cosine_logits_bwd")
-        check(lib.lc2is_argmax_confmat_lowres(ptr(self.logits), B, C, h, w, H, W, BILINEAR, ptr(labels), H, W,
-                                              ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
-        if self.distributed:
+        if dist_on:
             self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
-            self.bucket.allreduce_()
-            dp.allreduce_confmat_(self.confmat)
+            w_b = dp.allreduce_sum_async(self.bucket.flat)
+            w_cm.wait()
+            w_b.wait()
             self.loss.copy_(self.bucket.views[1] / self.n_valid)
         else:
             check(lib.lc2is_finalize_loss(ptr(self.loss_sum), ptr(self.n_valid), ptr(self.loss), st), "finalize_loss")

@@ -46,6 +46,10 @@ def _worker(rank, world, port, q):
     bucket.views[0].copy_((x.grad * w_shared).sum(0))            # a "shared parameter" gradient
     bucket.views[1].copy_(loss_sum.detach().reshape(1))
     bucket.allreduce_()
+    xa = torch.full((3,), float(rank + 1))
+    wk = dp.allreduce_sum_async(xa)
+    wk.wait()
+    assert torch.equal(xa, torch.full((3,), 3.0))
     if rank == 0:
         q.put(dict(cm=cm, allper=allper, nv=nv, g=bucket.views[0].clone(), loss=bucket.views[1] / nv,
                    pred=pred, lab=lab, low=low, labels=labels))
