@@ -131,6 +131,27 @@ int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_labels,
                               double* d_loss_sum, float* d_grad_low, void* d_grad_low_bf16,
                               lc2is_stream_t stream);
 
+/* Split form of K2 for power-of-two scales 8 / 16 (what the whole-step entries run): the same
+ * reference lines (model/loss.py:19-20 + autograd), cut so that everything that depends on the
+ * labels only happens once, in one pass over the int64 map.
+ * lc2is_ce_labels_prepass: n_valid += #counted pixels; d_labels_packed [B,H,W] uint16 = label, 0xFFFF
+ *   where the pixel is not counted (ignore_index / out of [0,C)); d_grad_low [B,C,h,w] fp32
+ *   ACCUMULATES the un-scaled -onehot term (minus the bilinear tap weights of every counted pixel).
+ *   d_grad_low / d_labels_packed / d_n_valid may each be NULL to skip that output.  Scales 4 / 8 / 16.
+ * lc2is_upsample_ce_packed (scales 8 / 16): d_loss_sum += sum over counted pixels of
+ *   (log-sum-exp - logit_target); d_grad_low ACCUMULATES the un-scaled softmax term (NULL = forward
+ *   only).  After both calls d_loss_sum / n_valid is the mean CE and d_grad_low / n_valid its
+ *   gradient (lc2is_cosine_logits_bwd applies the scale when given the fp32 gradient).
+ * Unsupported geometries return LC2IS_ERR_UNSUPPORTED (use lc2is_upsample_ce_fwd_bwd). */
+int lc2is_ce_split_supported(int h, int w, int H, int W);
+int lc2is_ce_labels_prepass(const int64_t* d_labels,
+                            int B, int C, int h, int w, int H, int W, int64_t ignore_index,
+                            uint16_t* d_labels_packed, int64_t* d_n_valid,
+                            float* d_grad_low, lc2is_stream_t stream);
+int lc2is_upsample_ce_packed(const float* d_low, const uint16_t* d_labels_packed,
+                             int B, int C, int h, int w, int H, int W,
+                             double* d_loss_sum, float* d_grad_low, lc2is_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K3  argmax + confusion matrix.  Replaces, per image,
  *       F.interpolate(bicubic) + nn.Softmax2d + JaccardIndex (argmax + bincount)

@@ -50,6 +50,9 @@ SIGNATURES = {
     "lc2is_finalize_loss": (c_int, [_p, _p, _p, _p]),
     "lc2is_upsample_ce_fwd_bwd": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, _p, _p,
                                           _p, _p, _p]),
+    "lc2is_ce_split_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "lc2is_ce_labels_prepass": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, _p, _p, _p, _p]),
+    "lc2is_upsample_ce_packed": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p]),
     "lc2is_argmax_confmat": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, _p, c_int, c_int, _p, _p, _p, _p]),
     "lc2is_argmax_confmat_lowres": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _p, c_int,
                                             c_int, _p, _p, _p, _p]),

@@ -138,6 +138,30 @@ def upsample_ce(low: Tensor, labels: Tensor, ignore_index: int = -100, grad_scal
     return loss_sum, grad, gbf
 
 
+def ce_split_supported(h: int, w: int, H: int, W: int) -> bool:
+    return bool(lib.lc2is_ce_split_supported(h, w, H, W))
+
+
+def upsample_ce_split(low: Tensor, labels: Tensor, ignore_index: int = -100, want_grad: bool = True):
+    """Split K2 (scale 8 / 16): label prepass + packed-label strip kernel.
+    -> (loss_sum double[1], n_valid int64[1], grad_low fp32 UNSCALED | None, labels_packed uint16 [B,H,W])."""
+    low = _req(low, torch.float32, "low")
+    labels = _req(labels, torch.int64, "labels")
+    B, C, h, w = low.shape
+    _, H, W = labels.shape
+    dev = low.device
+    loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+    n_valid = torch.zeros(1, dtype=torch.int64, device=dev)
+    grad = torch.zeros_like(low) if want_grad else None
+    packed = torch.empty(B, H, W, dtype=torch.uint16, device=dev)
+    st = stream_ptr()
+    check(lib.lc2is_ce_labels_prepass(ptr(labels), B, C, h, w, H, W, int(ignore_index), ptr(packed),
+                                      ptr(n_valid), ptr(grad), st), "lc2is_ce_labels_prepass")
+    check(lib.lc2is_upsample_ce_packed(ptr(low), ptr(packed), B, C, h, w, H, W, ptr(loss_sum), ptr(grad), st),
+          "lc2is_upsample_ce_packed")
+    return loss_sum, n_valid, grad, packed
+
+
 # ---- K3 -----------------------------------------------------------------------------------
 def argmax_confmat(logits: Tensor, labels: Tensor, confmat: Optional[Tensor] = None, per_image: bool = False,
                    want_pred: bool = False, size: Optional[Tuple[int, int]] = None, mode: Optional[str] = None):

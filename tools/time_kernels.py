@@ -36,6 +36,8 @@ def main():
         res["count_valid"] = timeit(lambda i: ops.count_valid(L[i % nset], 0))
     if want("k2"):
         res["k2(memset+fused)"] = timeit(lambda i: ops.upsample_ce(outs[i % nset][0], L[i % nset], 0, gs))
+        if ops.ce_split_supported(h, h, H, H):
+            res["k2_split(memset+prepass+strip)"] = timeit(lambda i: ops.upsample_ce_split(outs[i % nset][0], L[i % nset], 0))
         res["k2_fwd_only"] = timeit(lambda i: ops.upsample_ce(outs[i % nset][0], L[i % nset], 0, gs, want_grad=False))
     _, g, gb = ops.upsample_ce(outs[0][0], L[0], 0, gs, want_bf16=True)
     if want("k1b"):
