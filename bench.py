@@ -287,16 +287,21 @@ def run_b200(a):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    k2_bytes = 2 * B * C * h * w * 4 + B * H * W * 8 + 8
+    split = step.split
+    # algorithmic bytes of the K2 launch: read low + accumulate grad_low (fp32) + the label map it reads
+    # (packed uint16 from the label prepass on the split path, int64 otherwise) + the loss scalar
+    k2_bytes = 2 * B * C * h * w * 4 + B * H * W * (2 if split else 8) + 8
+    k2_name = "k2_strip_kernel<16, true>" if split and H // h == 16 else (
+        "k2_strip_kernel<8, true>" if split else "k2_fast_kernel / k2_generic_kernel")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and a.geometry == "A" and B == 16 and C == 150:
-        traffic = json.load(open(tpath)).get("k2_fast_kernel<4>")     # from one `ncu --set full` capture
+        traffic = json.load(open(tpath)).get(k2_name)                 # from one `ncu --set full` capture
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
-    roofline = {"kernel": "k2_fast_kernel (lc2is_upsample_ce_fwd_bwd: memset + fused upsample/CE fwd+bwd)",
+    roofline = {"kernel": f"{k2_name} (lc2is_upsample_ce_packed: fused bilinear upsample + softmax-CE fwd+bwd)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": k2_bytes, "kernel_us": k2_ms * 1e3,
-                "note": "K2 is instruction-bound (ex2 + fp32 issue), not HBM-bound: see DESIGN.md; "
+                "note": "K2 is FP32-pipe bound (packed FFMA2 at 2 warp-inst/clk/SM), not HBM-bound: see DESIGN.md; "
                         f"{B * C * H * W / (k2_ms * 1e-3) / 1e12:.3f} T softmax-elements/s"}
 
     cpu_baseline = None

@@ -78,8 +78,9 @@ int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int hw, int D,
 
 /* ---------------------------------------------------------------------------------------
  * K1b cosine_logits_bwd.  Replaces autograd of the K1 lines (loss.backward(), engine.py:100).
- * d_grad_logits_bf16 [B, C_pad, hw] bf16: dL/dlogits (rows C..C_pad-1 zero) - produced by K2
- *            (or lc2is_grad_to_bf16).
+ * d_grad_logits: dL/dlogits, g_dtype LC2IS_BF16: [B, C_pad, hw] bf16 (rows C..C_pad-1 zero; K2's
+ *            bf16 output or lc2is_grad_to_bf16), or LC2IS_F32: [B, C, hw] fp32 (K2's fp32 gradient;
+ *            converted to the bf16 GEMM operand in the same pass that forms the projections).
  * d_logits   [B, C, hw] fp32 from K1 (used for the normalise-backward projection
  *            v_hat . dV_hat = sum_c G_c * logits_c).
  * d_grad_scale: optional DEVICE fp32 scalar multiplied into every gradient (the upstream
@@ -90,7 +91,7 @@ int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int hw, int D,
  * d_ws       workspace, lc2is_cosine_logits_bwd_workspace(...) bytes.
  */
 int64_t lc2is_cosine_logits_bwd_workspace(int B, int hw, int D, int n_sets, int C);
-int lc2is_cosine_logits_bwd(const void* d_grad_logits_bf16, const float* d_logits,
+int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, const float* d_logits,
                             const void* d_v_hat, const float* d_inv_norm_v,
                             const void* d_t_hat, const float* d_inv_norm_t,
                             int B, int hw, int D, int n_sets, int C,
@@ -134,8 +135,9 @@ int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_labels,
 /* Split form of K2 for power-of-two scales 8 / 16 (what the whole-step entries run): the same
  * reference lines (model/loss.py:19-20 + autograd), cut so that everything that depends on the
  * labels only happens once, in one pass over the int64 map.
- * lc2is_ce_labels_prepass: n_valid += #counted pixels; d_labels_packed [B,H,W] uint16 = label, 0xFFFF
- *   where the pixel is not counted (ignore_index / out of [0,C)); d_grad_low [B,C,h,w] fp32
+ * lc2is_ce_labels_prepass: n_valid += #counted pixels; d_labels_packed [B,H,W] uint16 = label, with
+ *   bit 15 set where label == ignore_index (not counted by the CE, still a row of the confusion
+ *   matrix) and 0xFFFF where the label is outside [0,C); d_grad_low [B,C,h,w] fp32
  *   ACCUMULATES the un-scaled -onehot term (minus the bilinear tap weights of every counted pixel).
  *   d_grad_low / d_labels_packed / d_n_valid may each be NULL to skip that output.  Scales 4 / 8 / 16.
  * lc2is_upsample_ce_packed (scales 8 / 16): d_loss_sum += sum over counted pixels of
@@ -176,6 +178,12 @@ int lc2is_argmax_confmat_lowres(const float* d_low, int N, int C, int h, int w, 
                                 int mode, const int64_t* d_labels, int lh, int lw,
                                 int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                 lc2is_stream_t stream);
+/* Same, bilinear, scale 8 / 16 only, with the packed labels [N,H,W] written by lc2is_ce_labels_prepass
+ * (what the whole-step entries run; LC2IS_ERR_UNSUPPORTED otherwise). */
+int lc2is_argmax_confmat_lowres_packed(const float* d_low, int N, int C, int h, int w, int H, int W,
+                                       const uint16_t* d_labels_packed,
+                                       int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                                       lc2is_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Whole step from HOST buffers (the end-to-end path bench.py times as `e2e`).  Replaces one

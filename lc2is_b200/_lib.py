@@ -42,7 +42,7 @@ SIGNATURES = {
     "lc2is_cosine_logits_fwd": (c_int, [_p, c_int, c_int, c_int, c_int, _p, c_int, c_int, c_int, c_float,
                                         _p, _p, _p, _p]),
     "lc2is_cosine_logits_bwd_workspace": (c_int64, [c_int, c_int, c_int, c_int, c_int]),
-    "lc2is_cosine_logits_bwd": (c_int, [_p, _p, _p, _p, _p, _p, c_int, c_int, c_int, c_int, c_int, c_int,
+    "lc2is_cosine_logits_bwd": (c_int, [_p, c_int, _p, _p, _p, _p, _p, c_int, c_int, c_int, c_int, c_int, c_int,
                                         c_float, _p, _p, c_int, _p, _p, _p]),
     "lc2is_grad_to_bf16": (c_int, [_p, c_int, c_int, c_int, _p, _p]),
     "lc2is_count_valid": (c_int, [_p, c_int64, c_int64, _p, _p]),
@@ -56,6 +56,7 @@ SIGNATURES = {
     "lc2is_argmax_confmat": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, _p, c_int, c_int, _p, _p, _p, _p]),
     "lc2is_argmax_confmat_lowres": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _p, c_int,
                                             c_int, _p, _p, _p, _p]),
+    "lc2is_argmax_confmat_lowres_packed": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p]),
     "lc2is_head_step_workspace": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "lc2is_head_step_host": (c_int, [_p, _p, _p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
                                      c_float, c_int, _p, _p, _p, _p, _p, _p]),

@@ -73,7 +73,7 @@ extern "C" int lc2is_finalize_loss(const double* d_loss_sum, const int64_t* d_n_
 // whole step from host buffers
 namespace {
 struct StepWs {
-    size_t v_in, labels, t_in, t_hat, inv_t, v_hat, inv_v, logits, grad_low, grad_bf16, grad_v, grad_t,
+    size_t v_in, labels, packed, t_in, t_hat, inv_t, v_hat, inv_v, logits, grad_low, grad_v, grad_t,
         bwd_ws, confmat, scalars, total;
 };
 inline size_t al(size_t x) { return (x + 255) / 256 * 256; }
@@ -83,6 +83,7 @@ StepWs step_layout(int B, int hw, int D, int C, int H, int W) {
     size_t o = 0;
     w.v_in = o;     o += al(M * D * 2);
     w.labels = o;   o += al((size_t)B * H * W * 8);
+    w.packed = o;   o += al((size_t)B * H * W * 2);
     w.t_in = o;     o += al((size_t)C * D * 4);
     w.t_hat = o;    o += al(Cp * D * 2);
     w.inv_t = o;    o += al((size_t)C * 4);
@@ -90,7 +91,6 @@ StepWs step_layout(int B, int hw, int D, int C, int H, int W) {
     w.inv_v = o;    o += al(M * 4);
     w.logits = o;   o += al(M * C * 4);
     w.grad_low = o; o += al(M * C * 4);
-    w.grad_bf16 = o; o += al(M * Cp * 2);
     w.grad_v = o;   o += al(M * D * 2);
     w.grad_t = o;   o += al((size_t)C * D * 4);
     w.bwd_ws = o;   o += al((size_t)lc2is_cosine_logits_bwd_workspace(B, hw, D, 1, C));
@@ -130,12 +130,15 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
     float* d_invv = (float*)(ws + L.inv_v);
     float* d_logits = (float*)(ws + L.logits);
     float* d_glow = (float*)(ws + L.grad_low);
-    void* d_gbf = ws + L.grad_bf16;
+    uint16_t* d_packed = (uint16_t*)(ws + L.packed);
     double* d_loss_sum = (double*)(ws + L.scalars);
     int64_t* d_nvalid = (int64_t*)(ws + L.scalars + 8);
     float* d_gscale = (float*)(ws + L.scalars + 16);
     float* d_loss = (float*)(ws + L.scalars + 20);
     int64_t* d_cm = (int64_t*)(ws + L.confmat);
+    // Power-of-two scales 8 / 16 run the split form of K2 (label prepass + packed-label kernels); other
+    // geometries the one-call K2 and the int64-label K3.
+    const bool split = lc2is_ce_split_supported(h, w, H, W) != 0;
 
     // The batch is cut into chunks: chunk i+1 is copied host->device on `copy_stream` while the
     // kernels of chunk i run on `stream` (engine.py:75 / :145 copy the whole batch up front).
@@ -166,6 +169,7 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
     }
     STEP_CUDA(cudaMemsetAsync(ws + L.scalars, 0, 256, st));
     STEP_CUDA(cudaMemsetAsync(d_cm, 0, (size_t)C * C * 8, st));
+    if (split && do_backward) STEP_CUDA(cudaMemsetAsync(d_glow, 0, M * C * 4, st));
     STEP_CUDA(cudaMemcpyAsync(d_t, h_t, (size_t)C * D * 4, cudaMemcpyHostToDevice, cst));
     for (int i = 0; i < nchunk; ++i) {
         const int b0 = i * bc, nb = (b0 + bc <= B ? bc : B - b0);
@@ -179,23 +183,32 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
             STEP_CUDA(cudaEventRecord(ev_copy[i], cst));
             STEP_CUDA(cudaStreamWaitEvent(st, ev_copy[i], 0));
         }
-        STEP_RC(lc2is_count_valid(d_labels + lab_off, (int64_t)nb * H * W, ignore_index, d_nvalid, stream));
-        if (i == 0) STEP_RC(lc2is_proto_normalize(d_t, 1, C, D, 1, d_that, d_invt, stream));
         float* lg = d_logits + (size_t)b0 * C * hw;
+        float* gl = do_backward ? d_glow + (size_t)b0 * C * hw : nullptr;
+        if (split)
+            STEP_RC(lc2is_ce_labels_prepass(d_labels + lab_off, nb, C, h, w, H, W, ignore_index, d_packed + lab_off,
+                                            d_nvalid, gl, stream));
+        else
+            STEP_RC(lc2is_count_valid(d_labels + lab_off, (int64_t)nb * H * W, ignore_index, d_nvalid, stream));
+        if (i == 0) STEP_RC(lc2is_proto_normalize(d_t, 1, C, D, 1, d_that, d_invt, stream));
         STEP_RC(lc2is_cosine_logits_fwd(d_v + v_off, LC2IS_BF16, nb, hw, D, d_that, 1, C, 1, logit_scale,
                                         d_vhat + v_off, d_invv + (size_t)b0 * hw, lg, stream));
-        STEP_RC(lc2is_upsample_ce_fwd_bwd(lg, d_labels + lab_off, nb, C, h, w, H, W, ignore_index, nullptr,
-                                          d_loss_sum, do_backward ? d_glow + (size_t)b0 * C * hw : nullptr,
-                                          do_backward ? (uint8_t*)d_gbf + (size_t)b0 * class_pad(C) * hw * 2 : nullptr,
-                                          stream));
-        STEP_RC(lc2is_argmax_confmat_lowres(lg, nb, C, h, w, H, W, LC2IS_BILINEAR, d_labels + lab_off, H, W, d_cm,
-                                            nullptr, nullptr, stream));
+        if (split) {
+            STEP_RC(lc2is_upsample_ce_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, stream));
+            STEP_RC(lc2is_argmax_confmat_lowres_packed(lg, nb, C, h, w, H, W, d_packed + lab_off, d_cm, nullptr,
+                                                       nullptr, stream));
+        } else {
+            STEP_RC(lc2is_upsample_ce_fwd_bwd(lg, d_labels + lab_off, nb, C, h, w, H, W, ignore_index, nullptr,
+                                              d_loss_sum, gl, nullptr, stream));
+            STEP_RC(lc2is_argmax_confmat_lowres(lg, nb, C, h, w, H, W, LC2IS_BILINEAR, d_labels + lab_off, H, W,
+                                                d_cm, nullptr, nullptr, stream));
+        }
     }
     STEP_RC(lc2is_mean_scale(d_nvalid, 1.0f, d_gscale, stream));
     if (do_backward) {
         STEP_CUDA(cudaMemsetAsync(ws + L.grad_t, 0, (size_t)C * D * 4, st));
-        STEP_RC(lc2is_cosine_logits_bwd(d_gbf, d_logits, d_vhat, d_invv, d_that, d_invt, B, hw, D, 1, C, 1,
-                                        logit_scale, d_gscale, ws + L.grad_v, LC2IS_BF16,
+        STEP_RC(lc2is_cosine_logits_bwd(d_glow, LC2IS_F32, d_logits, d_vhat, d_invv, d_that, d_invt, B, hw, D, 1, C,
+                                        1, logit_scale, d_gscale, ws + L.grad_v, LC2IS_BF16,
                                         (float*)(ws + L.grad_t), ws + L.bwd_ws, stream));
     }
     STEP_RC(lc2is_finalize_loss(d_loss_sum, d_nvalid, d_loss, stream));
@@ -207,6 +220,5 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
     cleanup();
 #undef STEP_CUDA
 #undef STEP_RC
-    (void)M;
     return 0;
 }

@@ -61,6 +61,57 @@ k1b_prep_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ L
     if (q == 0 && in) r[(size_t)b * hw + p] = (racc[0][px] + racc[1][px]) + (racc[2][px] + racc[3][px]);
 }
 
+// Same projections from the fp32 gradient [B,C,hw] (what K2 produces), fused with its conversion to the
+// bf16 [B,C_pad,hw] operand of the two GEMMs (pad rows zeroed): one pass over G and the logits.
+// CTA = 128 pixels x all classes: warp w walks classes w, w+8, ... with one float4 of G and of the logits per
+// lane; class sums leave with one reduction per (class, CTA), pixel sums meet in shared memory.
+constexpr int PREPF_PX = 128, PREPF_W = 8;
+__global__ void __launch_bounds__(PREPF_W * 32)
+k1b_prep_f32_kernel(const float* __restrict__ G, const float* __restrict__ L, int B, int C, int C_pad, int hw,
+                    int n_sets, int want_proj, __nv_bfloat16* __restrict__ Gb, float* __restrict__ r,
+                    float* __restrict__ rt) {
+    __shared__ float racc_s[PREPF_W][PREPF_PX];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x * PREPF_PX + lane * 4;
+    const bool in = p < hw;                                  // hw % 4 == 0
+    const float* g = G + (size_t)b * C * hw + p;
+    const float* l = L + (size_t)b * C * hw + p;
+    __nv_bfloat16* gb = Gb + (size_t)b * C_pad * hw + p;
+    float* rts = rt + (size_t)(n_sets > 1 ? b : 0) * C;
+    float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int c = warp; c < C_pad; c += PREPF_W) {
+        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), lv = gv;
+        if (c < C && in) {
+            gv = __ldcs(reinterpret_cast<const float4*>(g + (size_t)c * hw));
+            if (want_proj) lv = __ldg(reinterpret_cast<const float4*>(l + (size_t)c * hw));
+        }
+        if (in) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x, gv.y), hi = __floats2bfloat162_rn(gv.z, gv.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<unsigned*>(&lo); pk.y = *reinterpret_cast<unsigned*>(&hi);
+            *reinterpret_cast<uint2*>(gb + (size_t)c * hw) = pk;
+        }
+        if (want_proj && c < C) {
+            const float4 pr = make_float4(gv.x * lv.x, gv.y * lv.y, gv.z * lv.z, gv.w * lv.w);
+            racc.x += pr.x; racc.y += pr.y; racc.z += pr.z; racc.w += pr.w;
+            const float s = warp_sum((pr.x + pr.y) + (pr.z + pr.w));
+            if (lane == 0 && s != 0.f) atomicAdd(rts + c, s);
+        }
+    }
+    if (!want_proj) return;
+    *reinterpret_cast<float4*>(&racc_s[warp][lane * 4]) = racc;
+    __syncthreads();
+    if (threadIdx.x < PREPF_PX) {
+        const int pp = blockIdx.x * PREPF_PX + threadIdx.x;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < PREPF_W; ++w) t += racc_s[w][threadIdx.x];
+        if (pp < hw) r[(size_t)b * hw + pp] = t;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // dV GEMM.  Tile = 128 pixels x 256 channels (2 n-tiles of D=512 ...), K = C_pad in steps of 16.
 struct DvParams {
@@ -359,13 +410,14 @@ k1b_dt_finish_kernel(const float* __restrict__ dt_raw, const float* __restrict__
     }
 }
 
-struct BwdWs { size_t r, rt, dt_raw, total; };
+struct BwdWs { size_t r, rt, dt_raw, gbf, total; };
 static BwdWs bwd_layout(int B, int hw, int D, int n_sets, int C) {
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     BwdWs w; size_t o = 0;
     w.r = o; o += al((size_t)B * hw * 4);
     w.rt = o; o += al((size_t)n_sets * C * 4);
     w.dt_raw = o; o += al((size_t)n_sets * C * D * 4);
+    w.gbf = o; o += al((size_t)B * class_pad(C) * hw * 2);     // bf16 copy of an fp32 gradient
     w.total = o;
     return w;
 }
@@ -378,7 +430,7 @@ extern "C" int64_t lc2is_cosine_logits_bwd_workspace(int B, int hw, int D, int n
     return (int64_t)bwd_layout(B, hw, D, n_sets, C).total;
 }
 
-extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits_bf16, const float* d_logits,
+extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, const float* d_logits,
                                        const void* d_v_hat, const float* d_inv_norm_v,
                                        const void* d_t_hat, const float* d_inv_norm_t,
                                        int B, int hw, int D, int n_sets, int C,
@@ -388,8 +440,9 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits_bf16, const flo
     if (int e = ensure_device()) return e;
     if (B < 0 || hw <= 0 || C <= 0 || D <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
     if (B == 0) return 0;
-    if (!d_grad_logits_bf16 || !d_logits || !d_v_hat || !d_inv_norm_v || !d_t_hat || !d_ws)
+    if (!d_grad_logits || !d_logits || !d_v_hat || !d_inv_norm_v || !d_t_hat || !d_ws)
         return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (g_dtype != LC2IS_F32 && g_dtype != LC2IS_BF16) return fail(LC2IS_ERR_ARG, "g_dtype%s");
     if (normalize && !d_inv_norm_t) return fail(LC2IS_ERR_ARG, "inv_norm_t required when normalize%s");
     if (D % 64) return fail(LC2IS_ERR_SHAPE, "D must be a multiple of 64%s");
     if (hw % 8) return fail(LC2IS_ERR_SHAPE, "hw must be a multiple of 8 for the backward (TMA 16-byte strides); got %s%lld", "", hw);
@@ -402,10 +455,17 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits_bf16, const flo
     float* d_r = (float*)(ws + L.r);
     float* d_rt = (float*)(ws + L.rt);
     float* d_dtraw = (float*)(ws + L.dt_raw);
-    LC2IS_CUDA(cudaMemsetAsync(ws + L.rt, 0, L.total - L.rt, st));          // rt and dt_raw
+    LC2IS_CUDA(cudaMemsetAsync(ws + L.rt, 0, L.gbf - L.rt, st));            // rt and dt_raw
 
-    // ---- projections r, rt -----------------------------------------------------------------------
-    if (normalize) {
+    // ---- projections r, rt (and the bf16 operand copy of an fp32 gradient) -------------------------
+    const void* d_grad_logits_bf16 = d_grad_logits;
+    if (g_dtype == LC2IS_F32) {
+        d_grad_logits_bf16 = ws + L.gbf;
+        dim3 grid((hw + PREPF_PX - 1) / PREPF_PX, B);
+        k1b_prep_f32_kernel<<<grid, PREPF_W * 32, 0, st>>>((const float*)d_grad_logits, d_logits, B, C, C_pad, hw,
+                                                           n_sets, normalize, (__nv_bfloat16*)(ws + L.gbf), d_r, d_rt);
+        LC2IS_CHECK_LAUNCH("k1b_prep_f32_kernel");
+    } else if (normalize) {
         dim3 grid((hw + PREP_PX - 1) / PREP_PX, B);
         k1b_prep_kernel<<<grid, PREP_PX * PREP_Q, 0, st>>>((const __nv_bfloat16*)d_grad_logits_bf16, d_logits, B, C,
                                                            C_pad, hw, n_sets, d_r, d_rt);

@@ -862,7 +862,8 @@ k2_strip_kernel(const K2SParams P) {
 // Label prepass of the split path (power-of-two scale S): everything of the cross-entropy that depends on
 // the labels only, in one pass over the int64 label map:
 //   * n_valid += #{label != ignore_index and in [0,C)}                         (the 'mean' denominator)
-//   * packed[b,y,x] = (uint16) label, 0xFFFF where the pixel is not counted     (read by K2 / K3 afterwards)
+//   * packed[b,y,x] = (uint16) label; bit 15 set where the label is ignore_index (a class id that the
+//     cross-entropy does not count, but the confusion matrix does); 0xFFFF where it is no class id at all
 //   * grad_low[b,t,tap] -= w_tap(pixel)   for the four bilinear taps of every counted pixel (the -onehot
 //     term of dL/dlogits, unscaled; exact integer weights lambda*2S, run-length aggregated along the row)
 // One thread owns the S pixels of one row of one group (same group geometry as the strip kernel).
@@ -899,35 +900,44 @@ k2_labels_prepass_kernel(const long long* __restrict__ labels,
             atomicAdd(gp + oA, -fa); atomicAdd(gp + oB, -fb);
             atomicAdd(gp + oC, -fc); atomicAdd(gp + oD, -fd);
         };
+        // all loads of the segment first (the run-length code below has atomics the loads cannot cross)
+        longlong2 tv[S / 2];
+        const bool in0 = x0 >= 0, in1 = x0 + S / 2 < W;                  // left / right half inside the row
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {                                  // two half segments of S/2 pixels
-            const int xh = x0 + hh * (S / 2);
-            if (xh < 0 || xh >= W) continue;
-            unsigned pk[S / 4];
+        for (int k = 0; k < S / 2; ++k) {
+            const bool in = k < S / 4 ? in0 : in1;
+            tv[k] = in ? __ldg(reinterpret_cast<const longlong2*>(row + x0 + 2 * k)) : make_longlong2(-1, -1);
+        }
+        unsigned pk[S / 2];
 #pragma unroll
-            for (int k = 0; k < S / 4; ++k) {
-                const longlong2 t = __ldg(reinterpret_cast<const longlong2*>(row + xh + 2 * k));
-                unsigned word = 0;
+        for (int k = 0; k < S / 2; ++k) {
+            unsigned word = 0;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const long long tl = e ? t.y : t.x;
-                    const bool ok = tl != ignore && tl >= 0 && tl < C;
-                    const int lab = ok ? (int)tl : 0xffff;
-                    word |= (unsigned)lab << (16 * e);
-                    if (ok) {
-                        ++cnt;
-                        const int j = hh * (S / 2) + 2 * k + e;
-                        if (lab != cur) { flush(); cur = lab; sw0 = 0; sw1 = 0; }
-                        sw0 += 2 * S - (2 * j + 1);
-                        sw1 += 2 * j + 1;
-                    }
+            for (int e = 0; e < 2; ++e) {
+                const unsigned long long tl = (unsigned long long)(e ? tv[k].y : tv[k].x);
+                const bool inr = tl < (unsigned long long)C;                // a class id
+                const bool ok = inr && tl != (unsigned long long)ignore;     // counted by the cross-entropy
+                const int lab = (int)tl;
+                word |= (unsigned)(inr ? (ok ? lab : (lab | 0x8000)) : 0xffff) << (16 * e);
+                if (ok) {
+                    ++cnt;
+                    const int j = 2 * k + e;
+                    if (lab != cur) { flush(); cur = lab; sw0 = 0; sw1 = 0; }
+                    sw0 += 2 * S - (2 * j + 1);
+                    sw1 += 2 * j + 1;
                 }
-                pk[k] = word;
             }
-            if (prow) {
-                if constexpr (S == 16) *reinterpret_cast<uint4*>(prow + xh) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                else if constexpr (S == 8) *reinterpret_cast<uint2*>(prow + xh) = make_uint2(pk[0], pk[1]);
-                else *reinterpret_cast<unsigned*>(prow + xh) = pk[0];
+            pk[k] = word;
+        }
+        if (prow) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                if (!(hh ? in1 : in0)) continue;
+                unsigned short* d = prow + x0 + hh * (S / 2);
+                const unsigned* q = pk + hh * (S / 4);
+                if constexpr (S == 16) *reinterpret_cast<uint4*>(d) = make_uint4(q[0], q[1], q[2], q[3]);
+                else if constexpr (S == 8) *reinterpret_cast<uint2*>(d) = make_uint2(q[0], q[1]);
+                else *reinterpret_cast<unsigned*>(d) = q[0];
             }
         }
         flush();
@@ -1165,7 +1175,7 @@ extern "C" int lc2is_ce_labels_prepass(const int64_t* d_labels,
                                        float* d_grad_low, lc2is_stream_t stream) {
     if (int e = ensure_device()) return e;
     if (B < 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
-    if (C >= 0xffff) return fail(LC2IS_ERR_UNSUPPORTED, "packed labels hold class ids < 65535%s");
+    if (C >= 0x7fff) return fail(LC2IS_ERR_UNSUPPORTED, "packed labels hold class ids < 32767%s");
     if (B == 0) return 0;
     if (!d_labels) return fail(LC2IS_ERR_ARG, "null pointer%s");
     int s = 0;

@@ -14,6 +14,7 @@
 //                pixel block that shares one set of bilinear (2x2) / bicubic (4x4) taps.
 //   k3_low_gen - any output size (compute_gt_mIOU's per-image original sizes): 1 pixel/thread.
 #include "common.cuh"
+#include <type_traits>
 
 namespace lc2is {
 
@@ -453,6 +454,202 @@ k3_low_fast_kernel(const K3LowParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// k3_strip: bilinear, scale S = 8 / 16 (the x16 aux-head geometry of the whole-step path).
+// Same group geometry as the K2 strip kernel: a GROUP is the S x S pixel region between source cells
+// (ky,kx)..(ky+1,kx+1); one thread owns ONE ROW of a group (S pixels), so the S lanes of a group are
+// consecutive lanes and a warp owns 32/S groups whose four taps it stages as quads st[c][group][4].
+// Along the row the upsampled logit is linear:  v(j) = fma(j, delta, v0)  - evaluated for all S columns
+// as S/2 packed FFMA2 per class (exact on the dyadic exactness set).
+// The argmax is taken in two phases so that the inner loop is one FMNMX3 per pixel per class PAIR:
+//   phase 1: chunks of 8 classes; cm(j) = max over the chunk (FMNMX3), and at the end of the chunk
+//            "if (cm > best) { best = cm; chunk = k }" (strict: the FIRST chunk reaching the maximum)
+//   phase 2: per pixel, the 8 classes of its winning chunk are re-evaluated with the identical
+//            arithmetic and scanned with a strict '>' (the FIRST class reaching the maximum).
+// Non-finite taps send the warp down the exact per-pixel path (argmax(softmax(x)) = 0 for poisoned pixels).
+struct K3SParams {
+    const float* low;
+    const void* labels;           // int64 [N,lh,lw] (nearest-upsampled) or packed uint16 [N,H,W]
+    unsigned long long* confmat;
+    unsigned long long* per_image;
+    long long* pred_out;
+    int N, C, h, w, H, W, lh, lw;
+};
+
+__device__ __forceinline__ float k3_strip_value(const float4 q, float ly, float lx0, float rsx, int j) {
+    const float L = fmaf(ly, q.z - q.x, q.x), R = fmaf(ly, q.w - q.y, q.y);
+    const float rl = R - L;
+    return fmaf((float)j, rl * rsx, fmaf(rl, lx0, L));
+}
+
+template <int S, bool PACKED>
+__global__ void __launch_bounds__(128)
+k3_strip_kernel(const K3SParams P) {
+    constexpr int GPW = 32 / S;                             // groups per warp
+    constexpr int CS = GPW * 4;                             // floats per class in the warp's tile
+    constexpr int CH = 8;                                   // classes per chunk
+    constexpr float RS = 1.f / S, LX0 = 0.5f / S;
+    extern __shared__ float smem[];
+    const int C = P.C;
+    const int lane = threadIdx.x & 31;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int gpi = (P.h + 1) * (P.w + 1);                  // groups per image
+    const long long ngroups = (long long)P.N * gpi;
+    if (wg * GPW >= ngroups) return;                        // whole warp; no CTA barrier below
+    float* st = smem + (size_t)(threadIdx.x >> 5) * (C + CH) * CS;   // + padding: the last chunk may overrun C
+    const size_t plane = (size_t)P.h * P.w;
+
+    // ---- stage: lane -> fixed (group, tap), strided over classes -----------------------------------------
+    {
+        constexpr int CSTEP = 32 / CS;                      // 4 (S=16) / 2 (S=8)
+        const int r = lane % CS;
+        const long long gq = wg * GPW + (r >> 2);
+        const int tap = r & 3;
+        const bool ok = gq < ngroups;
+        const int n = ok ? (int)(gq / gpi) : 0;
+        const int rem = ok ? (int)(gq - (long long)n * gpi) : 0;
+        const int ky = rem / (P.w + 1) - 1, kx = rem % (P.w + 1) - 1;
+        // ATen's taps (UpSample.h:289-312): index0 = max(k, 0), index1 = min(index0 + 1, size - 1); at the
+        // top / left border (k = -1) lambda is 0 but the second tap is still row / column 1 (matters only
+        // for non-finite logits: 0 * inf = NaN)
+        const int ya = ky < 0 ? 0 : ky, xa = kx < 0 ? 0 : kx;
+        const int yy = (tap >> 1) ? min(ya + 1, P.h - 1) : ya, xx = (tap & 1) ? min(xa + 1, P.w - 1) : xa;
+        const float* src = P.low + (size_t)n * C * plane + (size_t)yy * P.w + xx;
+        float* dst = st + r;
+        for (int c = lane / CS; c < C; c += CSTEP) {
+            if (ok) cp_async4_k3(dst + c * CS, src + (size_t)c * plane);
+            else dst[c * CS] = 0.f;
+        }
+        for (int c = C + lane / CS; c < C + CH; c += CSTEP) dst[c * CS] = -3.0e38f;    // padding never wins
+    }
+    const int gl = lane / S, i = lane % S;
+    const long long gid = wg * GPW + gl;
+    const bool group_in = gid < ngroups;
+    const int n = group_in ? (int)(gid / gpi) : 0;
+    const int rem = group_in ? (int)(gid - (long long)n * gpi) : 0;
+    const int ky = rem / (P.w + 1) - 1, kx = rem % (P.w + 1) - 1;
+    const int y = S * ky + S / 2 + i, x0 = S * kx + S / 2;
+    const bool row_in = group_in && y >= 0 && y < P.H;
+    const float ly = ky < 0 ? 0.f : ((float)i + 0.5f) * RS;
+    const float lx0 = kx < 0 ? 0.f : LX0, rsx = kx < 0 ? 0.f : RS;      // lambda_x(j) = lx0 + j * rsx
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    const float4* st4 = reinterpret_cast<const float4*>(st) + gl;      // + c * GPW
+
+    // ---- non-finite taps? ------------------------------------------------------------------------------------
+    bool exotic = false;
+    for (int c = i; c < C; c += S) {
+        const float4 q = st4[c * GPW];
+        exotic |= !(fabsf(q.x) < INFINITY) | !(fabsf(q.y) < INFINITY) | !(fabsf(q.z) < INFINITY) | !(fabsf(q.w) < INFINITY);
+    }
+    exotic = __any_sync(0xffffffffu, exotic);
+
+    int bidx[S];
+    if (!exotic) {
+        // ---- phase 1: running maximum per pixel, chunk of the first maximum -------------------------------
+        float best[S];
+        int bch[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) { best[j] = -INFINITY; bch[j] = 0; }
+        float2 J2[S / 2];
+#pragma unroll
+        for (int k = 0; k < S / 2; ++k) J2[k] = make_float2((float)(2 * k), (float)(2 * k + 1));
+        const int nch = (C + CH - 1) / CH;
+        const float4* qp = st4;
+#pragma unroll 1
+        for (int k = 0; k < nch; ++k) {
+            float cm[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) cm[j] = -INFINITY;
+#pragma unroll
+            for (int cc = 0; cc < CH; cc += 2) {
+                const float4 qa = qp[0], qb = qp[GPW];
+                qp += 2 * GPW;
+                const float La = fmaf(ly, qa.z - qa.x, qa.x), Ra = fmaf(ly, qa.w - qa.y, qa.y);
+                const float Lb = fmaf(ly, qb.z - qb.x, qb.x), Rb = fmaf(ly, qb.w - qb.y, qb.y);
+                const float rla = Ra - La, rlb = Rb - Lb;
+                const float2 va0 = make_float2(fmaf(rla, lx0, La), fmaf(rla, lx0, La)), da = make_float2(rla * rsx, rla * rsx);
+                const float2 vb0 = make_float2(fmaf(rlb, lx0, Lb), fmaf(rlb, lx0, Lb)), db = make_float2(rlb * rsx, rlb * rsx);
+#pragma unroll
+                for (int jj = 0; jj < S / 2; ++jj) {
+                    const float2 va = ffma2f(J2[jj], da, va0), vb = ffma2f(J2[jj], db, vb0);
+                    cm[2 * jj] = fmaxf(fmaxf(va.x, vb.x), cm[2 * jj]);
+                    cm[2 * jj + 1] = fmaxf(fmaxf(va.y, vb.y), cm[2 * jj + 1]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (cm[j] > best[j]) { best[j] = cm[j]; bch[j] = k; }
+        }
+        // ---- phase 2: first class of the winning chunk that reaches the maximum ---------------------------
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const int c0 = bch[j] * CH;
+            float bv = -INFINITY;
+            int bi = c0;
+#pragma unroll
+            for (int cc = 0; cc < CH; ++cc) {
+                const float v = k3_strip_value(st4[(c0 + cc) * GPW], ly, lx0, rsx, j);
+                if (v > bv) { bv = v; bi = c0 + cc; }
+            }
+            bidx[j] = bi;
+        }
+    } else {
+        // exact per-pixel path with the NaN / +inf rule (rare)
+#pragma unroll 1
+        for (int j = 0; j < S; ++j) {
+            ArgmaxState a;
+            am_init(a);
+            const float tx = lx0 + (float)j * rsx;
+            for (int c = 0; c < C; ++c) {
+                const float4 q = st4[c * GPW];
+                const float r0 = fmaf(q.y, tx, q.x * (1.f - tx)), r1 = fmaf(q.w, tx, q.z * (1.f - tx));
+                am_update(a, fmaf(r1, ly, r0 * (1.f - ly)), c);
+            }
+#pragma unroll
+            for (int jj = 0; jj < S; ++jj)
+                if (jj == j) bidx[jj] = am_result(a);
+        }
+    }
+
+    // ---- labels, predictions, counts ---------------------------------------------------------------------------
+    unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
+    const int ry = P.H / P.lh, rx = P.W / P.lw;
+    unsigned lw16[PACKED ? S / 2 : 1];
+    if constexpr (PACKED) {
+        using V = typename std::conditional<S == 16, uint4, uint2>::type;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int x = x0 + hh * (S / 2);
+            const bool in = row_in && x >= 0 && x < P.W;
+            V t;
+            if (in) t = __ldg(reinterpret_cast<const V*>((const unsigned short*)P.labels + ((size_t)n * P.H + y) * P.W + x));
+            const unsigned* wv = reinterpret_cast<const unsigned*>(&t);
+#pragma unroll
+            for (int k = 0; k < S / 4; ++k) lw16[hh * (S / 4) + k] = in ? wv[k] : 0xffffffffu;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const int x = x0 + j;
+        bool valid = row_in && x >= 0 && x < P.W;
+        int t = 0;
+        const int pr = bidx[j];
+        if (valid) {
+            if (P.pred_out) P.pred_out[((size_t)n * P.H + y) * P.W + x] = pr;
+            if constexpr (PACKED) {
+                t = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0x7fffu);    // bit 15: ignore flag of the CE
+                valid = t < C;
+            } else {
+                const long long tl = __ldg((const long long*)P.labels + ((size_t)n * P.lh + y / ry) * P.lw + x / rx);
+                valid = tl >= 0 && tl < C;
+                t = (int)tl;
+            }
+        }
+        hist_add(nullptr, P.confmat, pimg, C, valid, t, pr);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k3_low_gen: arbitrary output size, one pixel per thread, taps from global (L1/L2 cached).
 // scale_y/scale_x = the ATen source scale (in/out as float, or 1/scale_factor).
 template <int MODE>
@@ -552,9 +749,55 @@ static int check_labels_ratio(int H, int W, int lh, int lw) {
     return 0;
 }
 
+static int launch_k3_strip(const float* d_low, int N, int C, int h, int w, int H, int W, int s, const void* labels,
+                           bool packed, int lh, int lw, int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                           cudaStream_t st) {
+    const size_t smem_warp = (size_t)(C + 8) * (32 / s) * 16;
+    int wpc = 4;
+    while (wpc > 1 && smem_warp * wpc > 56 * 1024) wpc /= 2;
+    const size_t smem = smem_warp * wpc;
+    if (smem > 200 * 1024) return LC2IS_ERR_UNSUPPORTED;
+    K3SParams P;
+    P.low = d_low; P.labels = labels; P.confmat = (unsigned long long*)d_confmat;
+    P.per_image = (unsigned long long*)d_per_image; P.pred_out = (long long*)d_pred;
+    P.N = N; P.C = C; P.h = h; P.w = w; P.H = H; P.W = W; P.lh = lh; P.lw = lw;
+    const long long ngroups = (long long)N * (h + 1) * (w + 1);
+    const long long warps = (ngroups + (32 / s) - 1) / (32 / s);
+    const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
+    auto launch = [&](auto kernel) -> int {
+        if (int e = set_smem(kernel, smem)) return e;
+        kernel<<<grid, wpc * 32, smem, st>>>(P);
+        return 0;
+    };
+    int e;
+    if (s == 16) e = packed ? launch(k3_strip_kernel<16, true>) : launch(k3_strip_kernel<16, false>);
+    else e = packed ? launch(k3_strip_kernel<8, true>) : launch(k3_strip_kernel<8, false>);
+    if (e) return e;
+    LC2IS_CHECK_LAUNCH("k3_strip_kernel");
+    return 0;
+}
+
 }  // namespace lc2is
 
 using namespace lc2is;
+
+extern "C" int lc2is_argmax_confmat_lowres_packed(const float* d_low, int N, int C, int h, int w, int H, int W,
+                                                  const uint16_t* d_labels_packed,
+                                                  int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                                                  lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (N < 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (N == 0) return 0;
+    if (!d_low || !d_labels_packed || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if ((uintptr_t)d_labels_packed % 16) return fail(LC2IS_ERR_ARG, "packed labels must be 16-byte aligned%s");
+    int s = 0;
+    if (!fast_scale(h, w, H, W, &s) || (s != 8 && s != 16))
+        return fail(LC2IS_ERR_UNSUPPORTED, "packed-label argmax needs scale 8 or 16%s");
+    int e = launch_k3_strip(d_low, N, C, h, w, H, W, s, d_labels_packed, true, H, W, d_confmat, d_per_image, d_pred,
+                            (cudaStream_t)stream);
+    if (e == LC2IS_ERR_UNSUPPORTED) return fail(e, "too many classes for the strip kernel%s");
+    return e;
+}
 
 extern "C" int lc2is_argmax_confmat(const void* d_logits, int dtype, int N, int C, int H, int W,
                                     const int64_t* d_labels, int lh, int lw,
@@ -614,6 +857,10 @@ extern "C" int lc2is_argmax_confmat_lowres(const float* d_low, int N, int C, int
     const int use_hist = C <= K3_SMEM_HIST_MAX_C;
     const size_t smem = use_hist ? ((size_t)C * C + 1) / 2 * sizeof(int) : 0;
     int s = 0;
+    if (mode == LC2IS_BILINEAR && fast_scale(h, w, H, W, &s) && (s == 8 || s == 16)) {
+        int e = launch_k3_strip(d_low, N, C, h, w, H, W, s, d_labels, false, lh, lw, d_confmat, d_per_image, d_pred, st);
+        if (e != LC2IS_ERR_UNSUPPORTED) return e;
+    }
     if (fast_scale(h, w, H, W, &s) && s <= 16) {
         BlockGeom g = make_geom(H, W, s);
         K3LowParams P;

@@ -74,22 +74,24 @@ def grad_to_bf16(grad: Tensor) -> Tensor:
     return out
 
 
-def cosine_logits_bwd(grad_bf16: Tensor, logits: Tensor, v_hat: Tensor, inv_v: Tensor, t_hat: Tensor,
+def cosine_logits_bwd(grad: Tensor, logits: Tensor, v_hat: Tensor, inv_v: Tensor, t_hat: Tensor,
                       inv_t: Tensor, C: int, normalize: bool = True, logit_scale: float = 1.0,
                       grad_scale: Optional[Tensor] = None, grad_v_dtype=torch.float32,
                       grad_t: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
-    """-> (grad_v [B,hw,D], grad_t fp32 [n_sets,C,D]); grad_t is accumulated into if given."""
+    """grad: dL/dlogits, bf16 [B,C_pad,hw] or fp32 [B,C,h,w] (converted inside the projection pass).
+    -> (grad_v [B,hw,D], grad_t fp32 [n_sets,C,D]); grad_t is accumulated into if given."""
     B = logits.shape[0]
     hw = logits[0, 0].numel()
     D = v_hat.shape[1]
     n_sets = t_hat.shape[0]
     dev = logits.device
+    grad = grad.contiguous()
     grad_v = torch.empty(B, hw, D, dtype=grad_v_dtype, device=dev)
     if grad_t is None:
         grad_t = torch.zeros(n_sets, C, D, dtype=torch.float32, device=dev)
     nbytes = int(lib.lc2is_cosine_logits_bwd_workspace(B, hw, D, n_sets, C))
     ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
-    check(lib.lc2is_cosine_logits_bwd(ptr(grad_bf16), ptr(logits), ptr(v_hat), ptr(inv_v), ptr(t_hat), ptr(inv_t),
+    check(lib.lc2is_cosine_logits_bwd(ptr(grad), _dt(grad), ptr(logits), ptr(v_hat), ptr(inv_v), ptr(t_hat), ptr(inv_t),
                                       B, hw, D, n_sets, C, int(normalize), float(logit_scale), ptr(grad_scale),
                                       ptr(grad_v), _dt(grad_v), ptr(grad_t), ptr(ws), stream_ptr()),
           "lc2is_cosine_logits_bwd")
@@ -190,4 +192,20 @@ def argmax_confmat(logits: Tensor, labels: Tensor, confmat: Optional[Tensor] = N
         check(lib.lc2is_argmax_confmat_lowres(ptr(logits), N, C, h, w, H, W, _MODE[mode], ptr(labels), lh, lw,
                                               ptr(confmat), ptr(pi), ptr(pred), stream_ptr()),
               "lc2is_argmax_confmat_lowres")
+    return confmat, pi, pred
+
+
+def argmax_confmat_packed(low: Tensor, labels_packed: Tensor, size: Tuple[int, int], confmat: Optional[Tensor] = None,
+                          per_image: bool = False, want_pred: bool = False):
+    """Fused bilinear resize + argmax + confusion matrix from the packed labels of the CE label prepass."""
+    low = _req(low, torch.float32, "low")
+    N, C, h, w = low.shape
+    H, W = int(size[0]), int(size[1])
+    dev = low.device
+    if confmat is None:
+        confmat = torch.zeros(C, C, dtype=torch.int64, device=dev)
+    pi = torch.zeros(N, 3, C, dtype=torch.int64, device=dev) if per_image else None
+    pred = torch.empty(N, H, W, dtype=torch.int64, device=dev) if want_pred else None
+    check(lib.lc2is_argmax_confmat_lowres_packed(ptr(low), N, C, h, w, H, W, ptr(labels_packed), ptr(confmat), ptr(pi),
+                                                 ptr(pred), stream_ptr()), "lc2is_argmax_confmat_lowres_packed")
     return confmat, pi, pred

@@ -39,7 +39,8 @@ class HeadStep:
         self.inv_v = e(M)
         self.logits = e(B, C, h, w)
         self.grad_low = e(B, C, h, w)
-        self.grad_bf16 = e(B, Cp, self.hw, dt=torch.bfloat16)
+        self.split = bool(lib.lc2is_ce_split_supported(h, w, H, W))     # label prepass + packed-label K2 / K3
+        self.labels_packed = e(B, H, W, dt=torch.uint16) if self.split else None
         self.grad_v = e(B, self.hw, D, dt=torch.bfloat16)
         # flat all-reduce bucket: [grad_t (C*D) | loss_sum as fp32 (1)]
         self.bucket = dp.GradBucket([(1, C, D), (1,)], dev)
@@ -68,33 +69,49 @@ class HeadStep:
         self.confmat.zero_()
         if self.backward:
             self.bucket.zero_()
-        check(lib.lc2is_count_valid(ptr(labels), labels.numel(), self.ignore_index, ptr(self.n_valid), st), "count_valid")
+        glow = ptr(self.grad_low) if self.backward else None
+        if self.split:
+            # un-scaled gradients accumulate into grad_low (prepass: -onehot, K2: +softmax); 1/N_valid is applied
+            # by K1b, so the valid-count all-reduce hides behind K1 / K2 / K3
+            if self.backward:
+                self.grad_low.zero_()
+            check(lib.lc2is_ce_labels_prepass(ptr(labels), B, C, h, w, H, W, self.ignore_index,
+                                              ptr(self.labels_packed), ptr(self.n_valid), glow, st), "ce_labels_prepass")
+        else:
+            check(lib.lc2is_count_valid(ptr(labels), labels.numel(), self.ignore_index, ptr(self.n_valid), st),
+                  "count_valid")
         w_valid = dp.allreduce_sum_async(self.n_valid) if dist_on else None
         check(lib.lc2is_proto_normalize(ptr(t), 1, C, D, int(self.normalize), ptr(self.t_hat), ptr(self.inv_t), st),
               "proto_normalize")
         check(lib.lc2is_cosine_logits_fwd(ptr(v), BF16 if v.dtype == torch.bfloat16 else F32, B, hw, D,
                                           ptr(self.t_hat), 1, C, int(self.normalize), self.logit_scale,
                                           ptr(self.v_hat), ptr(self.inv_v), ptr(self.logits), st), "cosine_logits_fwd")
+        if self.k2_events is not None:
+            self.k2_events[0].record()
+        if self.split:
+            check(lib.lc2is_upsample_ce_packed(ptr(self.logits), ptr(self.labels_packed), B, C, h, w, H, W,
+                                               ptr(self.loss_sum), glow, st), "upsample_ce_packed")
+        else:
+            check(lib.lc2is_upsample_ce_fwd_bwd(ptr(self.logits), ptr(labels), B, C, h, w, H, W, self.ignore_index,
+                                                None, ptr(self.loss_sum), glow, None, st), "upsample_ce_fwd_bwd")
+        if self.k2_events is not None:
+            self.k2_events[1].record()
+        if self.split:
+            check(lib.lc2is_argmax_confmat_lowres_packed(ptr(self.logits), B, C, h, w, H, W, ptr(self.labels_packed),
+                                                         ptr(self.confmat), None, None, st), "argmax_confmat_packed")
+        else:
+            check(lib.lc2is_argmax_confmat_lowres(ptr(self.logits), B, C, h, w, H, W, BILINEAR, ptr(labels), H, W,
+                                                  ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
+        w_cm = dp.allreduce_sum_async(self.confmat) if dist_on else None
         if w_valid is not None:
             w_valid.wait()                                        # stream-level wait, no host sync
         check(lib.lc2is_mean_scale(ptr(self.n_valid), 1.0, ptr(self.gscale), st), "mean_scale")
-        if self.k2_events is not None:
-            self.k2_events[0].record()
-        check(lib.lc2is_upsample_ce_fwd_bwd(ptr(self.logits), ptr(labels), B, C, h, w, H, W, self.ignore_index,
-                                            ptr(self.gscale), ptr(self.loss_sum),
-                                            ptr(self.grad_low) if self.backward else None, None, st),
-              "upsample_ce_fwd_bwd")
-        if self.k2_events is not None:
-            self.k2_events[1].record()
-        check(lib.lc2is_argmax_confmat_lowres(ptr(self.logits), B, C, h, w, H, W, BILINEAR, ptr(labels), H, W,
-                                              ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
-        w_cm = dp.allreduce_sum_async(self.confmat) if dist_on else None
         if self.backward:
-            check(lib.lc2is_grad_to_bf16(ptr(self.grad_low), B, C, hw, ptr(self.grad_bf16), st), "grad_to_bf16")
-            check(lib.lc2is_cosine_logits_bwd(ptr(self.grad_bf16), ptr(self.logits), ptr(self.v_hat), ptr(self.inv_v),
-                                              ptr(self.t_hat), ptr(self.inv_t), B, hw, D, 1, C, int(self.normalize),
-                                              self.logit_scale, None, ptr(self.grad_v), BF16, ptr(self.grad_t),
-                                              ptr(self.bwd_ws), st), "cosine_logits_bwd")
+            check(lib.lc2is_cosine_logits_bwd(ptr(self.grad_low), F32, ptr(self.logits), ptr(self.v_hat),
+                                              ptr(self.inv_v), ptr(self.t_hat), ptr(self.inv_t), B, hw, D, 1, C,
+                                              int(self.normalize), self.logit_scale, ptr(self.gscale),
+                                              ptr(self.grad_v), BF16, ptr(self.grad_t), ptr(self.bwd_ws), st),
+                  "cosine_logits_bwd")
         if dist_on:
             self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
             w_b = dp.allreduce_sum_async(self.bucket.flat)

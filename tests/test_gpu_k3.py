@@ -151,3 +151,43 @@ def test_full_size_property_checksum():
     assert int(cm_f.sum()) == N * H * H
     assert torch.equal(cm_f.sum(1), torch.bincount(labels.flatten(), minlength=C))
     assert torch.equal(cm_f.sum(0), torch.bincount(pred.flatten(), minlength=C))
+
+
+@pytest.mark.parametrize("s,h,C,ign", [(16, 6, 151, 0), (8, 12, 150, 0), (16, 3, 19, 5), (16, 5, 847, 0)])
+def test_strip_kernel_packed_labels_bit_exact(s, h, C, ign):
+    """k3_strip_kernel through the packed labels of the CE label prepass (what HeadStep runs): the matrix keeps
+    the ignore_index row (bit 15 of the packed label only switches the pixel off for the cross-entropy) and
+    skips labels outside [0,C); dyadic logits -> bit-exact against the oracle."""
+    N = 3
+    low = synthetic.make_dyadic_logits(N, C, h, h)
+    H = s * h
+    labels = synthetic.make_labels(N, H, H, C, block=8, ignore_frac=0.1, ignore_index=ign)
+    labels[0, :2] = C + 3
+    labels[1, 5, :7] = -1
+    up = F.interpolate(low, mode="bilinear", scale_factor=s)
+    pred_ref = O.argmax_reference(up)
+    _, _, _, packed = ops.upsample_ce_split(low.to(DEV), labels.to(DEV), ign, want_grad=False)
+    cm, pi, pred = ops.argmax_confmat_packed(low.to(DEV), packed, (H, H), per_image=True, want_pred=True)
+    assert torch.equal(pred.cpu(), pred_ref)
+    assert torch.equal(cm.cpu(), O.confusion_matrix(pred_ref, labels, C))
+    assert torch.equal(pi.cpu(), _per_image_ref(pred_ref, labels, C))
+    # and the int64-label entry (same kernel) agrees
+    cm2, _, pred2 = ops.argmax_confmat(low.to(DEV), labels.to(DEV), want_pred=True, size=(H, H), mode="bilinear")
+    assert torch.equal(cm2, cm) and torch.equal(pred2, pred)
+
+
+def test_strip_kernel_non_finite_taps_and_ties():
+    """+inf / NaN taps poison exactly the pixels that interpolate them (class 0, like argmax(softmax)); equal
+    logits resolve to the first class, also across the 8-class chunks of the two-phase argmax."""
+    N, C, h, s = 1, 21, 4, 16
+    H = s * h
+    low = torch.zeros(N, C, h, h)
+    low[0, 3] = 0.5; low[0, 12] = 0.5; low[0, 20] = 0.5        # ties across chunks 0, 1, 2 -> class 3
+    low[0, 7, 1, 1] = float("inf")
+    low[0, 9, 2, 3] = float("nan")
+    labels = torch.randint(0, C, (N, H, H), generator=torch.Generator().manual_seed(3))
+    up = F.interpolate(low, mode="bilinear", scale_factor=s)
+    pred_ref = O.argmax_reference(up)
+    cm, _, pred = ops.argmax_confmat(low.to(DEV), labels.to(DEV), want_pred=True, size=(H, H), mode="bilinear")
+    assert torch.equal(pred.cpu(), pred_ref)
+    assert torch.equal(cm.cpu(), O.confusion_matrix(pred_ref, labels, C))

@@ -45,6 +45,9 @@ def main():
         res["k1b(prep+dv+dt+finish)"] = timeit(lambda i: ops.cosine_logits_bwd(gb, outs[i % nset][0], outs[i % nset][1], outs[i % nset][2], t_hat, inv_t, C, grad_v_dtype=torch.bfloat16))
     if want("k3"):
         res["k3_lowres_bilinear"] = timeit(lambda i: ops.argmax_confmat(outs[i % nset][0], L[i % nset], size=(H, H), mode="bilinear"))
+        if ops.ce_split_supported(h, h, H, H):
+            pk = ops.upsample_ce_split(outs[0][0], L[0], 0, want_grad=False)[3]
+            res["k3_strip_packed"] = timeit(lambda i: ops.argmax_confmat_packed(outs[i % nset][0], pk, (H, H)))
         res["k3_lowres_bicubic"] = timeit(lambda i: ops.argmax_confmat(outs[i % nset][0], L[i % nset], size=(H, H), mode="bicubic"))
     if want("k3full"):
         n3 = 4
