@@ -150,6 +150,12 @@ int lc2is_ce_labels_prepass(const int64_t* d_labels,
                             int B, int C, int h, int w, int H, int W, int64_t ignore_index,
                             uint16_t* d_labels_packed, int64_t* d_n_valid,
                             float* d_grad_low, lc2is_stream_t stream);
+/* Same as lc2is_ce_labels_prepass for labels that are already packed (lc2is_pack_labels_host). */
+int lc2is_ce_labels_prepass_packed(const uint16_t* d_labels_packed, int B, int C, int h, int w, int H, int W,
+                                   int64_t* d_n_valid, float* d_grad_low, lc2is_stream_t stream);
+/* HOST function: narrow an int64 label map (host memory) to the packed uint16 form on the library's
+ * worker threads (LC2IS_PACK_THREADS, default hardware threads - 2, at most 16).  Blocks until done. */
+int lc2is_pack_labels_host(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index, uint16_t* h_out);
 int lc2is_upsample_ce_packed(const float* d_low, const uint16_t* d_labels_packed,
                              int B, int C, int h, int w, int H, int W,
                              double* d_loss_sum, float* d_grad_low, lc2is_stream_t stream);
@@ -194,15 +200,33 @@ int lc2is_argmax_confmat_lowres_packed(const float* d_low, int N, int C, int h, 
  * h_out_loss (mean CE), h_out_n_valid, h_out_confmat [C,C] (overwritten).
  * d_ws: device workspace of lc2is_head_step_workspace(...) bytes (caller-allocated).
  * do_backward: also run K1b (gradients stay on the device, in the workspace).
- * copy_stream: optional second stream (NULL = none): the batch is then cut into 4 chunks and the H2D copy
+ * copy_stream: optional second stream (NULL = none): the batch is then cut into chunks and the H2D copy
  *   of chunk i+1 overlaps the kernels of chunk i (the 1/N_valid scale is applied at the end, in K1b).
+ * h_scratch: optional PINNED host buffer of B*H*W uint16 (NULL = none).  With it (and a power-of-two scale
+ *   8 / 16) the int64 labels are narrowed to the packed 2-byte form on the library's host worker threads,
+ *   chunk by chunk ahead of the copies, so a quarter of the label bytes cross PCIe.
  */
 int64_t lc2is_head_step_workspace(int B, int hw, int D, int C, int H, int W);
 int lc2is_head_step_host(const void* h_v, const float* h_t, const int64_t* h_labels,
                          int B, int h, int w, int D, int C, int H, int W,
                          int64_t ignore_index, float logit_scale, int do_backward,
                          float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
-                         void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream);
+                         void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
+                         uint16_t* h_scratch);
+
+/* The same step without the final synchronisation: everything (host-side label packing, H2D, kernels, D2H
+ * of the results) is enqueued and *done_event receives a handle; lc2is_head_step_host_wait blocks until that
+ * step's results are in the h_out_* buffers and releases the handle.  The copy of step i+1 then overlaps the
+ * kernels of step i (a prefetching data loader: engine.py:75 copies the next batch while the previous one
+ * computes).  Each step in flight needs its own workspace, scratch and output buffers; all host buffers
+ * must stay valid until the wait returns.  copy_stream must be a second stream. */
+int lc2is_head_step_host_submit(const void* h_v, const float* h_t, const int64_t* h_labels,
+                                int B, int h, int w, int D, int C, int H, int W,
+                                int64_t ignore_index, float logit_scale, int do_backward,
+                                float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
+                                void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
+                                uint16_t* h_scratch, void** done_event);
+int lc2is_head_step_host_wait(void* done_event);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,12 @@
 // C-ABI glue: error text, device probing, scalar helpers and the whole-step-from-host entry.
 #include "common.cuh"
+#include <immintrin.h>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
 
 namespace lc2is {
 
@@ -49,7 +56,7 @@ __global__ void finalize_loss_kernel(const double* loss_sum, const long long* n_
 using namespace lc2is;
 
 extern "C" const char* lc2is_last_error(void) { return g_err; }
-extern "C" int lc2is_abi_version(void) { return 1; }
+extern "C" int lc2is_abi_version(void) { return 2; }
 extern "C" int64_t lc2is_launch_count(void) { return g_launches.load(); }
 
 extern "C" int lc2is_mean_scale(const int64_t* d_n_valid, float mult, float* d_scale, lc2is_stream_t stream) {
@@ -66,6 +73,127 @@ extern "C" int lc2is_finalize_loss(const double* d_loss_sum, const int64_t* d_n_
     if (!d_loss_sum || !d_n_valid || !d_loss) return fail(LC2IS_ERR_ARG, "null pointer%s");
     finalize_loss_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_loss_sum, (const long long*)d_n_valid, d_loss);
     LC2IS_CHECK_LAUNCH("finalize_loss_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side label packing (the reference hands int64 label maps over in host memory: data/collator.py:91;
+// 8 bytes per pixel would make the PCIe copy of the labels the longest stage of the step).  Same encoding as
+// k2_labels_prepass_kernel: class id; bit 15 = label == ignore_index; 0xFFFF = outside [0,C).
+namespace {
+void pack_labels_scalar(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t v = (uint64_t)src[i];
+        const bool inr = v < (uint64_t)C;
+        uint16_t o = inr ? (uint16_t)v : (uint16_t)0xFFFF;
+        if (inr && src[i] == ign) o |= 0x8000;
+        dst[i] = o;
+    }
+}
+__attribute__((target("avx2")))
+void pack_labels_avx2(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+    const __m256i vC = _mm256_set1_epi64x((long long)C - 1), vign = _mm256_set1_epi64x(ign);
+    const __m256i zero = _mm256_setzero_si256(), ffff = _mm256_set1_epi64x(0xFFFF), flag = _mm256_set1_epi64x(0x8000);
+    const __m256i idx = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6);
+    const bool aligned = ((uintptr_t)dst % 16) == 0;
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        __m128i q[4];
+        for (int k = 0; k < 4; ++k) {
+            const __m256i v = _mm256_loadu_si256((const __m256i*)(src + i + 4 * k));
+            const __m256i bad = _mm256_or_si256(_mm256_cmpgt_epi64(zero, v), _mm256_cmpgt_epi64(v, vC));
+            __m256i r = _mm256_or_si256(v, _mm256_and_si256(_mm256_cmpeq_epi64(v, vign), flag));
+            r = _mm256_blendv_epi8(r, ffff, bad);
+            q[k] = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(r, idx));   // low 32 bits of the 4 lanes
+        }
+        // non-temporal stores: the buffer is read next by the GPU's copy engine, not by this core
+        if (aligned) {
+            _mm_stream_si128((__m128i*)(dst + i), _mm_packus_epi32(q[0], q[1]));
+            _mm_stream_si128((__m128i*)(dst + i + 8), _mm_packus_epi32(q[2], q[3]));
+        } else {
+            _mm_storeu_si128((__m128i*)(dst + i), _mm_packus_epi32(q[0], q[1]));
+            _mm_storeu_si128((__m128i*)(dst + i + 8), _mm_packus_epi32(q[2], q[3]));
+        }
+    }
+    _mm_sfence();
+    pack_labels_scalar(src + i, dst + i, n - i, C, ign);
+}
+void pack_labels_range(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+    static const bool have_avx2 = __builtin_cpu_supports("avx2");
+    if (have_avx2) pack_labels_avx2(src, dst, n, C, ign);
+    else pack_labels_scalar(src, dst, n, C, ign);
+}
+
+// A small persistent worker pool (created on first use, joined at process exit).
+class PackPool {
+public:
+    struct Task { const int64_t* src; uint16_t* dst; size_t n; int C; int64_t ign; std::atomic<int>* pending; };
+    explicit PackPool(int nthreads) {
+        for (int i = 0; i < nthreads; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~PackPool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    int size() const { return (int)workers_.size(); }
+    void submit(const Task& t) {
+        { std::lock_guard<std::mutex> g(m_); q_.push_back(t); }
+        cv_.notify_one();
+    }
+private:
+    void run() {
+        for (;;) {
+            Task t;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+                if (q_.empty()) return;
+                t = q_.front(); q_.pop_front();
+            }
+            pack_labels_range(t.src, t.dst, t.n, t.C, t.ign);
+            t.pending->fetch_sub(1, std::memory_order_release);
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Task> q_;
+    bool stop_ = false;
+};
+PackPool& pack_pool() {
+    static PackPool pool([] {
+        int n = (int)std::thread::hardware_concurrency() - 2;   // leave the caller's thread and one spare
+        const char* e = getenv("LC2IS_PACK_THREADS");
+        if (e) n = atoi(e);
+        return n < 1 ? 1 : (n > 16 ? 16 : n);
+    }());
+    return pool;
+}
+// split [0,n) into pieces for the pool; *pending counts the pieces still running
+void pack_submit(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign, std::atomic<int>* pending) {
+    PackPool& p = pack_pool();
+    const int pieces = p.size();
+    const size_t per = ((n + pieces - 1) / pieces + 63) / 64 * 64;
+    int cnt = 0;
+    for (size_t o = 0; o < n; o += per) ++cnt;
+    pending->store(cnt, std::memory_order_relaxed);
+    for (size_t o = 0; o < n; o += per)
+        p.submit({src + o, dst + o, per < n - o ? per : n - o, C, ign, pending});
+}
+inline void pack_wait(std::atomic<int>* pending) {
+    while (pending->load(std::memory_order_acquire) > 0) _mm_pause();
+}
+}  // namespace
+
+extern "C" int lc2is_pack_labels_host(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index,
+                                      uint16_t* h_out) {
+    if (n < 0 || C <= 0 || C >= 0x7fff) return fail(LC2IS_ERR_SHAPE, "bad n / C%s");
+    if (n == 0) return 0;
+    if (!h_labels || !h_out) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    std::atomic<int> pending{0};
+    pack_submit(h_labels, h_out, (size_t)n, C, ignore_index, &pending);
+    pack_wait(&pending);
     return 0;
 }
 
@@ -105,11 +233,12 @@ extern "C" int64_t lc2is_head_step_workspace(int B, int hw, int D, int C, int H,
     return (int64_t)step_layout(B, hw, D, C, H, W).total;
 }
 
-extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int64_t* h_labels,
-                                    int B, int h, int w, int D, int C, int H, int W,
-                                    int64_t ignore_index, float logit_scale, int do_backward,
-                                    float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
-                                    void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream) {
+static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h_labels,
+                             int B, int h, int w, int D, int C, int H, int W,
+                             int64_t ignore_index, float logit_scale, int do_backward,
+                             float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
+                             void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
+                             uint16_t* h_scratch, int n_chunks, bool async) {
     if (int e = ensure_device()) return e;
     if (!h_v || !h_t || !h_labels || !h_out_loss || !h_out_n_valid || !h_out_confmat || !d_ws)
         return fail(LC2IS_ERR_ARG, "null pointer%s");
@@ -144,10 +273,36 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
     // kernels of chunk i run on `stream` (engine.py:75 / :145 copy the whole batch up front).
     // Gradients are produced un-normalised (g = 1) per chunk; the 1/N_valid of the 'mean' reduction is
     // only known after the last chunk and is applied by K1b through its device-side grad_scale.
-    const int nchunk = piped ? (B < 4 ? B : 4) : 1;
+    // With a pinned scratch buffer the int64 labels are narrowed to the packed uint16 form on the host
+    // (worker pool), chunk by chunk ahead of the copies: 2 bytes per pixel cross PCIe instead of 8.
+    const bool hpack = split && h_scratch != nullptr && C < 0x7fff;
+    constexpr int MAXCH = 8;
+    // chunks: a blocking call overlaps copy and compute inside the step (2 chunks with packed labels, 4 with
+    // int64 labels: the copy is the longest stage there); a submitted step overlaps with its neighbours and
+    // runs whole-batch kernels (1 chunk)
+    int want_chunks = n_chunks > 0 ? n_chunks : (async ? 1 : (hpack ? 2 : 4));
+    if (getenv("LC2IS_STEP_CHUNKS")) want_chunks = atoi(getenv("LC2IS_STEP_CHUNKS"));
+    if (want_chunks > MAXCH) want_chunks = MAXCH;
+    const bool trace = getenv("LC2IS_STEP_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_chunk[MAXCH + 1] = {};
+    std::vector<std::pair<const char*, cudaEvent_t>> tev;
+    auto mark = [&](const char* name, cudaStream_t sx) { if (trace) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, sx); tev.push_back({name, e}); } };
+    const int nchunk = piped ? (B < want_chunks ? B : want_chunks) : 1;
     const int bc = (B + nchunk - 1) / nchunk;
-    cudaEvent_t ev_start = nullptr, ev_copy[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::atomic<int> pack_pending[MAXCH];
+    if (hpack)
+        for (int i = 0; i < nchunk; ++i) {
+            const int b0 = i * bc, nb = (b0 + bc <= B ? bc : B - b0);
+            pack_pending[i].store(0);
+            if (nb > 0)
+                pack_submit(h_labels + (size_t)b0 * H * W, h_scratch + (size_t)b0 * H * W, (size_t)nb * H * W, C,
+                            ignore_index, &pack_pending[i]);
+        }
+    cudaEvent_t ev_start = nullptr, ev_copy[MAXCH] = {};
     auto cleanup = [&]() {
+        if (hpack) for (int i = 0; i < nchunk; ++i) pack_wait(&pack_pending[i]);   // workers still read h_labels
         if (ev_start) cudaEventDestroy(ev_start);
         for (auto& e : ev_copy) if (e) cudaEventDestroy(e);
     };
@@ -164,9 +319,12 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
     if (piped) {
         STEP_CUDA(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
         for (int i = 0; i < nchunk; ++i) STEP_CUDA(cudaEventCreateWithFlags(&ev_copy[i], cudaEventDisableTiming));
-        STEP_CUDA(cudaEventRecord(ev_start, st));           // the workspace is free once earlier work on
-        STEP_CUDA(cudaStreamWaitEvent(cst, ev_start, 0));   // `stream` has drained
+        if (!async) {
+            STEP_CUDA(cudaEventRecord(ev_start, st));           // the workspace is free once earlier work on
+            STEP_CUDA(cudaStreamWaitEvent(cst, ev_start, 0));   // `stream` has drained
+        }   // (a submitted step owns its workspace: the caller waited for the slot's previous step)
     }
+    mark("start", st);
     STEP_CUDA(cudaMemsetAsync(ws + L.scalars, 0, 256, st));
     STEP_CUDA(cudaMemsetAsync(d_cm, 0, (size_t)C * C * 8, st));
     if (split && do_backward) STEP_CUDA(cudaMemsetAsync(d_glow, 0, M * C * 4, st));
@@ -175,24 +333,36 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
         const int b0 = i * bc, nb = (b0 + bc <= B ? bc : B - b0);
         if (nb <= 0) break;
         const size_t lab_off = (size_t)b0 * H * W, v_off = (size_t)b0 * hw * D * 2;
-        STEP_CUDA(cudaMemcpyAsync(d_labels + lab_off, h_labels + lab_off, (size_t)nb * H * W * 8,
-                                  cudaMemcpyHostToDevice, cst));
         STEP_CUDA(cudaMemcpyAsync(d_v + v_off, (const uint8_t*)h_v + v_off, (size_t)nb * hw * D * 2,
                                   cudaMemcpyHostToDevice, cst));
+        if (hpack) {
+            pack_wait(&pack_pending[i]);
+            STEP_CUDA(cudaMemcpyAsync(d_packed + lab_off, h_scratch + lab_off, (size_t)nb * H * W * 2,
+                                      cudaMemcpyHostToDevice, cst));
+        } else {
+            STEP_CUDA(cudaMemcpyAsync(d_labels + lab_off, h_labels + lab_off, (size_t)nb * H * W * 8,
+                                      cudaMemcpyHostToDevice, cst));
+        }
+        mark("h2d", cst);
         if (piped) {
             STEP_CUDA(cudaEventRecord(ev_copy[i], cst));
             STEP_CUDA(cudaStreamWaitEvent(st, ev_copy[i], 0));
         }
+        t_chunk[i] = now() - t_begin;
         float* lg = d_logits + (size_t)b0 * C * hw;
         float* gl = do_backward ? d_glow + (size_t)b0 * C * hw : nullptr;
-        if (split)
+        if (hpack)
+            STEP_RC(lc2is_ce_labels_prepass_packed(d_packed + lab_off, nb, C, h, w, H, W, d_nvalid, gl, stream));
+        else if (split)
             STEP_RC(lc2is_ce_labels_prepass(d_labels + lab_off, nb, C, h, w, H, W, ignore_index, d_packed + lab_off,
                                             d_nvalid, gl, stream));
         else
             STEP_RC(lc2is_count_valid(d_labels + lab_off, (int64_t)nb * H * W, ignore_index, d_nvalid, stream));
+        mark("prepass", st);
         if (i == 0) STEP_RC(lc2is_proto_normalize(d_t, 1, C, D, 1, d_that, d_invt, stream));
         STEP_RC(lc2is_cosine_logits_fwd(d_v + v_off, LC2IS_BF16, nb, hw, D, d_that, 1, C, 1, logit_scale,
                                         d_vhat + v_off, d_invv + (size_t)b0 * hw, lg, stream));
+        mark("k1", st);
         if (split) {
             STEP_RC(lc2is_upsample_ce_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, stream));
             STEP_RC(lc2is_argmax_confmat_lowres_packed(lg, nb, C, h, w, H, W, d_packed + lab_off, d_cm, nullptr,
@@ -204,6 +374,7 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
                                                 d_cm, nullptr, nullptr, stream));
         }
     }
+    mark("k2k3", st);
     STEP_RC(lc2is_mean_scale(d_nvalid, 1.0f, d_gscale, stream));
     if (do_backward) {
         STEP_CUDA(cudaMemsetAsync(ws + L.grad_t, 0, (size_t)C * D * 4, st));
@@ -211,14 +382,61 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
                                         1, logit_scale, d_gscale, ws + L.grad_v, LC2IS_BF16,
                                         (float*)(ws + L.grad_t), ws + L.bwd_ws, stream));
     }
+    mark("bwd", st);
     STEP_RC(lc2is_finalize_loss(d_loss_sum, d_nvalid, d_loss, stream));
     // D2H of the step's results (engine.py:108 .item(); :162-163)
     STEP_CUDA(cudaMemcpyAsync(h_out_loss, d_loss, 4, cudaMemcpyDeviceToHost, st));
     STEP_CUDA(cudaMemcpyAsync(h_out_n_valid, d_nvalid, 8, cudaMemcpyDeviceToHost, st));
     STEP_CUDA(cudaMemcpyAsync(h_out_confmat, d_cm, (size_t)C * C * 8, cudaMemcpyDeviceToHost, st));
-    STEP_CUDA(cudaStreamSynchronize(st));
+    const double t_enq = now() - t_begin;
+    if (!async) STEP_CUDA(cudaStreamSynchronize(st));
+    if (trace && !async) {
+        fprintf(stderr, "step trace: chunks %d copies-enqueued-at(us):", nchunk);
+        for (int i = 0; i < nchunk; ++i) fprintf(stderr, " %.0f", t_chunk[i]);
+        fprintf(stderr, " all-enqueued %.0f synced %.0f | gpu(us):", t_enq, now() - t_begin);
+        for (size_t k = 1; k < tev.size(); ++k) { float ms = 0; cudaEventElapsedTime(&ms, tev[0].second, tev[k].second); fprintf(stderr, " %s %.0f", tev[k].first, ms * 1e3); }
+        fprintf(stderr, "\n");
+        for (auto& e : tev) cudaEventDestroy(e.second);
+    }
     cleanup();
 #undef STEP_CUDA
 #undef STEP_RC
+    return 0;
+}
+
+extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int64_t* h_labels,
+                                    int B, int h, int w, int D, int C, int H, int W,
+                                    int64_t ignore_index, float logit_scale, int do_backward,
+                                    float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
+                                    void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
+                                    uint16_t* h_scratch) {
+    return head_step_enqueue(h_v, h_t, h_labels, B, h, w, D, C, H, W, ignore_index, logit_scale, do_backward,
+                             h_out_loss, h_out_n_valid, h_out_confmat, d_ws, stream, copy_stream, h_scratch, 0, false);
+}
+
+extern "C" int lc2is_head_step_host_submit(const void* h_v, const float* h_t, const int64_t* h_labels,
+                                           int B, int h, int w, int D, int C, int H, int W,
+                                           int64_t ignore_index, float logit_scale, int do_backward,
+                                           float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
+                                           void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
+                                           uint16_t* h_scratch, void** done_event) {
+    if (!done_event) return fail(LC2IS_ERR_ARG, "done_event is NULL%s");
+    if (!copy_stream || copy_stream == stream) return fail(LC2IS_ERR_ARG, "submit needs a separate copy stream%s");
+    int e = head_step_enqueue(h_v, h_t, h_labels, B, h, w, D, C, H, W, ignore_index, logit_scale, do_backward,
+                              h_out_loss, h_out_n_valid, h_out_confmat, d_ws, stream, copy_stream, h_scratch, 0, true);
+    if (e) return e;
+    cudaEvent_t ev;
+    LC2IS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    LC2IS_CUDA(cudaEventRecord(ev, (cudaStream_t)stream));
+    *done_event = (void*)ev;
+    return 0;
+}
+
+extern "C" int lc2is_head_step_host_wait(void* done_event) {
+    if (!done_event) return fail(LC2IS_ERR_ARG, "done_event is NULL%s");
+    cudaEvent_t ev = (cudaEvent_t)done_event;
+    cudaError_t e = cudaEventSynchronize(ev);
+    cudaEventDestroy(ev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
     return 0;
 }

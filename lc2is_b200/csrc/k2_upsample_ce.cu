@@ -867,9 +867,11 @@ k2_strip_kernel(const K2SParams P) {
 //   * grad_low[b,t,tap] -= w_tap(pixel)   for the four bilinear taps of every counted pixel (the -onehot
 //     term of dL/dlogits, unscaled; exact integer weights lambda*2S, run-length aggregated along the row)
 // One thread owns the S pixels of one row of one group (same group geometry as the strip kernel).
-template <int S>
+// LT = long long: the reference's int64 label map (packs it); LT = unsigned short: labels already packed on
+// the host (lc2is_pack_labels_host, same encoding): only the count and the -onehot term remain.
+template <int S, typename LT>
 __global__ void __launch_bounds__(256)
-k2_labels_prepass_kernel(const long long* __restrict__ labels,
+k2_labels_prepass_kernel(const LT* __restrict__ labels,
                          int B, int C, int h, int w, int H, int W, long long ignore,
                          unsigned short* __restrict__ packed, unsigned long long* __restrict__ n_valid,
                          float* __restrict__ grad_low) {
@@ -888,7 +890,7 @@ k2_labels_prepass_kernel(const long long* __restrict__ labels,
         const int Ya = clampi2(ky, 0, h - 1), Yb = clampi2(ky + 1, 0, h - 1);
         const int Xa = clampi2(kx, 0, w - 1), Xb = clampi2(kx + 1, 0, w - 1);
         const size_t oA = (size_t)Ya * w + Xa, oB = (size_t)Ya * w + Xb, oC = (size_t)Yb * w + Xa, oD = (size_t)Yb * w + Xb;
-        const long long* row = labels + ((size_t)n * H + y) * W;
+        const LT* row = labels + ((size_t)n * H + y) * W;
         unsigned short* prow = packed ? packed + ((size_t)n * H + y) * W : nullptr;
         const size_t ibase = (size_t)n * C * plane;
         int cur = -1, sw0 = 0, sw1 = 0;
@@ -900,9 +902,38 @@ k2_labels_prepass_kernel(const long long* __restrict__ labels,
             atomicAdd(gp + oA, -fa); atomicAdd(gp + oB, -fb);
             atomicAdd(gp + oC, -fc); atomicAdd(gp + oD, -fd);
         };
+        const bool in0 = x0 >= 0, in1 = x0 + S / 2 < W;                  // left / right half inside the row
+        if constexpr (sizeof(LT) == 2) {
+            // packed input: S/2 labels (S bytes) per load
+            using V = typename std::conditional<S == 16, uint4, typename std::conditional<S == 8, uint2, unsigned>::type>::type;
+            V hv[2];
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                if (hh ? in1 : in0) hv[hh] = __ldg(reinterpret_cast<const V*>(row + x0 + hh * (S / 2)));
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                if (!(hh ? in1 : in0)) continue;
+                const unsigned* wv = reinterpret_cast<const unsigned*>(&hv[hh]);
+#pragma unroll
+                for (int k = 0; k < S / 4; ++k)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int lab = (int)((wv[k] >> (16 * e)) & 0xffffu);
+                        if (lab < C) {                                       // counted: a class id without the flag
+                            ++cnt;
+                            const int j = hh * (S / 2) + 2 * k + e;
+                            if (lab != cur) { flush(); cur = lab; sw0 = 0; sw1 = 0; }
+                            sw0 += 2 * S - (2 * j + 1);
+                            sw1 += 2 * j + 1;
+                        }
+                    }
+            }
+            flush();
+            continue;
+        }
         // all loads of the segment first (the run-length code below has atomics the loads cannot cross)
         longlong2 tv[S / 2];
-        const bool in0 = x0 >= 0, in1 = x0 + S / 2 < W;                  // left / right half inside the row
 #pragma unroll
         for (int k = 0; k < S / 2; ++k) {
             const bool in = k < S / 4 ? in0 : in1;
@@ -1192,10 +1223,37 @@ extern "C" int lc2is_ce_labels_prepass(const int64_t* d_labels,
             (const long long*)d_labels, B, C, h, w, H, W, (long long)ignore_index,
             (unsigned short*)d_labels_packed, (unsigned long long*)d_n_valid, d_grad_low);
     };
-    if (s == 4) launch(k2_labels_prepass_kernel<4>);
-    else if (s == 8) launch(k2_labels_prepass_kernel<8>);
-    else launch(k2_labels_prepass_kernel<16>);
+    if (s == 4) launch(k2_labels_prepass_kernel<4, long long>);
+    else if (s == 8) launch(k2_labels_prepass_kernel<8, long long>);
+    else launch(k2_labels_prepass_kernel<16, long long>);
     LC2IS_CHECK_LAUNCH("k2_labels_prepass_kernel");
+    return 0;
+}
+
+extern "C" int lc2is_ce_labels_prepass_packed(const uint16_t* d_labels_packed, int B, int C, int h, int w, int H,
+                                              int W, int64_t* d_n_valid, float* d_grad_low,
+                                              lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (B < 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (B == 0) return 0;
+    if (!d_labels_packed) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    int s = 0;
+    if (!fast_scale(h, w, H, W, &s) || s > 16)
+        return fail(LC2IS_ERR_UNSUPPORTED, "label prepass needs a power-of-two scale 4 / 8 / 16%s");
+    if ((uintptr_t)d_labels_packed % 16) return fail(LC2IS_ERR_ARG, "labels must be 16-byte aligned%s");
+    const long long total = (long long)B * H * (w + 1);
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    auto launch = [&](auto kernel) {
+        kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+            (const unsigned short*)d_labels_packed, B, C, h, w, H, W, 0LL, (unsigned short*)nullptr,
+            (unsigned long long*)d_n_valid, d_grad_low);
+    };
+    if (s == 4) launch(k2_labels_prepass_kernel<4, unsigned short>);
+    else if (s == 8) launch(k2_labels_prepass_kernel<8, unsigned short>);
+    else launch(k2_labels_prepass_kernel<16, unsigned short>);
+    LC2IS_CHECK_LAUNCH("k2_labels_prepass_kernel(packed)");
     return 0;
 }
 

@@ -124,28 +124,78 @@ class HeadStep:
 
 class HostStep:
     """The same pass through ``lc2is_head_step_host``: HOST (pinned) buffers in, host results out,
-    H2D / D2H copies inside the call (bench.py's `e2e`)."""
+    H2D / D2H copies inside the call (bench.py's `e2e`).
+
+    ``hs(v, t, labels)`` blocks until the results are in ``out_loss / out_n_valid / out_confmat``.
+    ``hs.submit(v, t, labels)`` / ``hs.wait()`` keep up to ``depth`` steps in flight (each with its own
+    workspace, scratch and output buffers), so the copy of the next batch overlaps the kernels of the
+    previous one, like a prefetching data loader; ``wait()`` returns the oldest step's (loss, n_valid, confmat)."""
+
+    class _Slot:
+        def __init__(self, nbytes, B, H, W, C, dev, host_pack):
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.out_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+            self.out_n_valid = torch.zeros(1, dtype=torch.int64).pin_memory()
+            self.out_confmat = torch.zeros(C, C, dtype=torch.int64).pin_memory()
+            self.h_scratch = torch.empty(B, H, W, dtype=torch.uint16).pin_memory() if host_pack else None
+            self.event = None
+            self.keep = None
 
     def __init__(self, B: int, h: int, w: int, H: int, W: int, C: int, D: int = 512, ignore_index: int = 0,
                  logit_scale: float = 1.0, backward: bool = True, device: Optional[torch.device] = None,
-                 pipelined: bool = True) -> None:
+                 pipelined: bool = True, host_pack: bool = True, depth: int = 2) -> None:
         dev = device or torch.device("cuda", torch.cuda.current_device())
         self.args = (B, h, w, D, C, H, W)
         self.ignore_index, self.logit_scale, self.backward = ignore_index, logit_scale, backward
         nbytes = int(lib.lc2is_head_step_workspace(B, h * w, D, C, H, W))
-        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        self.out_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
-        self.out_n_valid = torch.zeros(1, dtype=torch.int64).pin_memory()
-        self.out_confmat = torch.zeros(C, C, dtype=torch.int64).pin_memory()
+        # pinned scratch for the host-side int64 -> packed uint16 narrowing of the labels (split geometries)
+        self.host_pack = bool(host_pack and lib.lc2is_ce_split_supported(h, w, H, W) and C < 0x7fff)
+        self.slots = [HostStep._Slot(nbytes, B, H, W, C, dev, self.host_pack) for _ in range(max(1, depth))]
         self.copy_stream = torch.cuda.Stream(device=dev) if pipelined else None
-        self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + B * H * W * 8
+        self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + B * H * W * (2 if self.host_pack else 8)
         self.d2h_bytes = 4 + 8 + C * C * 8
+        self._next, self._inflight = 0, []
+        self._set_outputs(self.slots[0])
+
+    def _set_outputs(self, s) -> None:
+        self.out_loss, self.out_n_valid, self.out_confmat = s.out_loss, s.out_n_valid, s.out_confmat
+
+    def _check_inputs(self, h_v, h_labels) -> None:
+        assert h_v.dtype == torch.bfloat16 and not h_v.is_cuda and not h_labels.is_cuda
 
     def __call__(self, h_v: torch.Tensor, h_t: torch.Tensor, h_labels: torch.Tensor) -> None:
         B, h, w, D, C, H, W = self.args
-        assert h_v.dtype == torch.bfloat16 and not h_v.is_cuda and not h_labels.is_cuda
+        self._check_inputs(h_v, h_labels)
+        assert not self._inflight, "wait() for the submitted steps first"
+        s = self.slots[0]
         check(lib.lc2is_head_step_host(ptr(h_v), ptr(h_t), ptr(h_labels), B, h, w, D, C, H, W, self.ignore_index,
-                                       self.logit_scale, int(self.backward), ptr(self.out_loss),
-                                       ptr(self.out_n_valid), ptr(self.out_confmat), ptr(self.ws), stream_ptr(),
-                                       self.copy_stream.cuda_stream if self.copy_stream is not None else None),
+                                       self.logit_scale, int(self.backward), ptr(s.out_loss),
+                                       ptr(s.out_n_valid), ptr(s.out_confmat), ptr(s.ws), stream_ptr(),
+                                       self.copy_stream.cuda_stream if self.copy_stream is not None else None,
+                                       ptr(s.h_scratch)),
               "lc2is_head_step_host")
+        self._set_outputs(s)
+
+    def submit(self, h_v: torch.Tensor, h_t: torch.Tensor, h_labels: torch.Tensor) -> None:
+        import ctypes
+        B, h, w, D, C, H, W = self.args
+        self._check_inputs(h_v, h_labels)
+        assert self.copy_stream is not None, "submit() needs pipelined=True (a copy stream)"
+        assert len(self._inflight) < len(self.slots), "all slots are in flight: wait() first"
+        s = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        ev = ctypes.c_void_p()
+        check(lib.lc2is_head_step_host_submit(ptr(h_v), ptr(h_t), ptr(h_labels), B, h, w, D, C, H, W, self.ignore_index,
+                                              self.logit_scale, int(self.backward), ptr(s.out_loss),
+                                              ptr(s.out_n_valid), ptr(s.out_confmat), ptr(s.ws), stream_ptr(),
+                                              self.copy_stream.cuda_stream, ptr(s.h_scratch), ctypes.byref(ev)),
+              "lc2is_head_step_host_submit")
+        s.event, s.keep = ev, (h_v, h_t, h_labels)          # host buffers must outlive the step
+        self._inflight.append(s)
+
+    def wait(self):
+        s = self._inflight.pop(0)
+        check(lib.lc2is_head_step_host_wait(s.event), "lc2is_head_step_host_wait")
+        s.event, s.keep = None, None
+        self._set_outputs(s)
+        return s.out_loss, s.out_n_valid, s.out_confmat

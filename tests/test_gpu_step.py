@@ -54,3 +54,35 @@ def test_head_step_device_matches_oracle_and_host_step():
     assert torch.equal(hs.out_confmat, step.confmat.cpu())
     assert abs(float(hs.out_loss) - float(step.loss)) <= 2e-6 * float(step.loss)
     assert abs(float(metrics.miou_from_confmat(step.confmat, 0)) - float(O.jaccard_macro(step.confmat.cpu(), 0))) < 1e-7
+
+
+def test_submit_wait_pipeline_matches_blocking_call():
+    """Two steps in flight (lc2is_head_step_host_submit / _wait) over alternating batches give, step by step,
+    exactly the results of the blocking call; host-side label packing on and off agree bit for bit."""
+    B, h, H, C = 4, 8, 128, 151
+    batches = []
+    for k in range(3):
+        v = synthetic.make_patch_embeddings(B, h * h, 512, seed=100 + k).pin_memory()
+        lab = synthetic.make_labels(B, H, H, C, seed=100 + k, block=8, ignore_frac=0.1)
+        lab[0, 0, :4] = torch.tensor([-100, C, 255, 2 ** 40])          # not class ids: skipped everywhere
+        batches.append((v, lab.pin_memory()))
+    t = synthetic.make_prototypes(C, 512).pin_memory()
+    ref = []
+    blocking = HostStep(B, h, h, H, H, C, ignore_index=0, host_pack=False)
+    for v, lab in batches:
+        blocking(v, t, lab)
+        ref.append((float(blocking.out_loss), int(blocking.out_n_valid), blocking.out_confmat.clone()))
+    hs = HostStep(B, h, h, H, H, C, ignore_index=0, depth=2)
+    assert hs.host_pack
+    got = []
+    seq = [0, 1, 2, 0, 1, 2, 1]
+    hs.submit(batches[seq[0]][0], t, batches[seq[0]][1])
+    for k in seq[1:]:
+        hs.submit(batches[k][0], t, batches[k][1])
+        l, nv, cm = hs.wait()
+        got.append((float(l), int(nv), cm.clone()))
+    l, nv, cm = hs.wait()
+    got.append((float(l), int(nv), cm.clone()))
+    for k, g in zip(seq, got):
+        assert g[1] == ref[k][1] and torch.equal(g[2], ref[k][2])
+        assert abs(g[0] - ref[k][0]) <= 2e-6 * abs(ref[k][0])

@@ -83,3 +83,22 @@ def test_synthetic_inputs_are_seeded():
     assert synthetic.make_prototypes(847).shape == (847, 512)
     d = synthetic.make_dyadic_logits(1, 5, 4, 4)
     assert torch.equal(d * 256, (d * 256).round())
+
+
+def test_host_label_packing_matches_device_encoding():
+    """lc2is_pack_labels_host (HOST code, worker pool + AVX2): int64 -> uint16 class id, bit 15 = ignore_index,
+    0xFFFF = not a class id; ragged lengths exercise the scalar tail."""
+    import torch
+    from lc2is_b200 import _lib
+    g = torch.Generator().manual_seed(9)
+    for n, C, ign in ((1, 5, 0), (17, 151, 0), (100003, 150, -100), (4 * 512 * 512, 847, 3)):
+        lab = torch.randint(-3, C + 4, (n,), generator=g)
+        lab[:: max(1, n // 7)] = ign
+        if n > 3:
+            lab[1], lab[2], lab[3] = 2 ** 40, -2 ** 40, 65535
+        out = torch.full((n + 8,), 7, dtype=torch.uint16)
+        _lib.check(_lib.lib.lc2is_pack_labels_host(lab.data_ptr(), n, C, ign, out.data_ptr()), "pack")
+        inr = (lab >= 0) & (lab < C)
+        ref = torch.where(inr, torch.where(lab == ign, lab | 0x8000, lab), torch.full_like(lab, 0xFFFF))
+        assert torch.equal(out[:n].to(torch.int64), ref)
+        assert bool((out[n:] == 7).all())                     # nothing written past the end
