@@ -531,6 +531,30 @@ k3_strip_kernel(const K3SParams P) {
     const bool row_in = group_in && y >= 0 && y < P.H;
     const float ly = ky < 0 ? 0.f : ((float)i + 0.5f) * RS;
     const float lx0 = kx < 0 ? 0.f : LX0, rsx = kx < 0 ? 0.f : RS;      // lambda_x(j) = lx0 + j * rsx
+    // the row's labels (issued before the taps are waited for)
+    unsigned lw16[PACKED ? S / 2 : 1];
+    long long lab64[PACKED ? 1 : S];
+    if constexpr (PACKED) {
+        using V = typename std::conditional<S == 16, uint4, uint2>::type;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int x = x0 + hh * (S / 2);
+            const bool in = row_in && x >= 0 && x < P.W;
+            V t = {};
+            if (in) t = __ldg(reinterpret_cast<const V*>((const unsigned short*)P.labels + ((size_t)n * P.H + y) * P.W + x));
+            const unsigned* wv = reinterpret_cast<const unsigned*>(&t);
+#pragma unroll
+            for (int k = 0; k < S / 4; ++k) lw16[hh * (S / 4) + k] = in ? wv[k] : 0xffffffffu;
+        }
+    } else {
+        const int ryl = P.H / P.lh, rxl = P.W / P.lw;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const int x = x0 + j;
+            lab64[j] = (row_in && x >= 0 && x < P.W)
+                           ? __ldg((const long long*)P.labels + ((size_t)n * P.lh + y / ryl) * P.lw + x / rxl) : -1;
+        }
+    }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     const float4* st4 = reinterpret_cast<const float4*>(st) + gl;      // + c * GPW
@@ -612,40 +636,37 @@ k3_strip_kernel(const K3SParams P) {
     }
 
     // ---- labels, predictions, counts ---------------------------------------------------------------------------
+    // run-length along the thread's row: one 64-bit reduction per run of equal (target, prediction) pairs
     unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
-    const int ry = P.H / P.lh, rx = P.W / P.lw;
-    unsigned lw16[PACKED ? S / 2 : 1];
-    if constexpr (PACKED) {
-        using V = typename std::conditional<S == 16, uint4, uint2>::type;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int x = x0 + hh * (S / 2);
-            const bool in = row_in && x >= 0 && x < P.W;
-            V t;
-            if (in) t = __ldg(reinterpret_cast<const V*>((const unsigned short*)P.labels + ((size_t)n * P.H + y) * P.W + x));
-            const unsigned* wv = reinterpret_cast<const unsigned*>(&t);
-#pragma unroll
-            for (int k = 0; k < S / 4; ++k) lw16[hh * (S / 4) + k] = in ? wv[k] : 0xffffffffu;
+    int cur = -1, cnt = 0;
+    auto flush = [&]() {
+        if (cur < 0) return;
+        atomicAdd(&P.confmat[cur], (unsigned long long)cnt);
+        if (pimg) {
+            const int t = cur / C, p = cur - t * C;
+            if (t == p) atomicAdd(&pimg[t], (unsigned long long)cnt);
+            atomicAdd(&pimg[C + t], (unsigned long long)cnt);
+            atomicAdd(&pimg[2 * C + p], (unsigned long long)cnt);
         }
-    }
+    };
+    if (row_in) {
 #pragma unroll
-    for (int j = 0; j < S; ++j) {
-        const int x = x0 + j;
-        bool valid = row_in && x >= 0 && x < P.W;
-        int t = 0;
-        const int pr = bidx[j];
-        if (valid) {
+        for (int j = 0; j < S; ++j) {
+            const int x = x0 + j;
+            if (x < 0 || x >= P.W) continue;
+            const int pr = bidx[j];
             if (P.pred_out) P.pred_out[((size_t)n * P.H + y) * P.W + x] = pr;
-            if constexpr (PACKED) {
-                t = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0x7fffu);    // bit 15: ignore flag of the CE
-                valid = t < C;
-            } else {
-                const long long tl = __ldg((const long long*)P.labels + ((size_t)n * P.lh + y / ry) * P.lw + x / rx);
-                valid = tl >= 0 && tl < C;
-                t = (int)tl;
+            int t;
+            if constexpr (PACKED) t = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0x7fffu);   // bit 15: ignore flag of the CE
+            else {
+                const long long tl = lab64[j];
+                t = (tl >= 0 && tl < C) ? (int)tl : C;
             }
+            const int key = t < C ? t * C + pr : -1;
+            if (key != cur) { flush(); cur = key; cnt = 0; }
+            ++cnt;
         }
-        hist_add(nullptr, P.confmat, pimg, C, valid, t, pr);
+        flush();
     }
 }
 

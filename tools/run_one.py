@@ -15,6 +15,9 @@ for _ in range(3):
     if which == "k1": ops.cosine_logits_fwd(V, t_hat, C, (h, h))
     if which == "k2": ops.upsample_ce(logits, L, 0, gs)
     if which == "k2split": ops.upsample_ce_split(logits, L, 0)
+    if which == "k3split":
+        pk = ops.upsample_ce_split(logits, L, 0, want_grad=False)[3]
+        ops.argmax_confmat_packed(logits, pk, (H, H))
     if which == "k3low": ops.argmax_confmat(logits, L, size=(H, H), mode="bilinear")
     if which == "k3bic": ops.argmax_confmat(logits, L, size=(H, H), mode="bicubic")
     if which == "k3full":
