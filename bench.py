@@ -204,6 +204,7 @@ def run_b200(a):
     # ---- device-resident timing -----------------------------------------------------------------------
     for i in range(warmup):
         step(dev_sets[i % nset][0], t_dev, dev_sets[i % nset][1])
+    step.finish()
     torch.cuda.synchronize()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     barrier()
@@ -216,6 +217,7 @@ def run_b200(a):
         step.k2_events = k2_pairs[i]
         v_i, l_i = dev_sets[(warmup + i) % nset]
         step(v_i, t_dev, l_i)
+    step.finish()
     ev1.record()
     torch.cuda.synchronize()
     sampler.stop_flag = True

@@ -154,8 +154,10 @@ int lc2is_ce_labels_prepass(const int64_t* d_labels,
 int lc2is_ce_labels_prepass_packed(const uint16_t* d_labels_packed, int B, int C, int h, int w, int H, int W,
                                    int64_t* d_n_valid, float* d_grad_low, lc2is_stream_t stream);
 /* HOST function: narrow an int64 label map (host memory) to the packed uint16 form on the library's
- * worker threads (LC2IS_PACK_THREADS, default hardware threads - 2, at most 16).  Blocks until done. */
+ * worker threads (see lc2is_pack_threads).  Blocks until done. */
 int lc2is_pack_labels_host(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index, uint16_t* h_out);
+/* number of worker threads the packing pool uses (hardware threads / LOCAL_WORLD_SIZE - 2, 1..12) */
+int lc2is_pack_threads(void);
 int lc2is_upsample_ce_packed(const float* d_low, const uint16_t* d_labels_packed,
                              int B, int C, int h, int w, int H, int W,
                              double* d_loss_sum, float* d_grad_low, lc2is_stream_t stream);

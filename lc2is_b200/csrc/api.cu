@@ -161,13 +161,19 @@ private:
     std::deque<Task> q_;
     bool stop_ = false;
 };
+int pack_threads_default() {
+    // hardware threads shared by the ranks of this node (torchrun sets LOCAL_WORLD_SIZE), minus the
+    // caller's thread and one spare; LC2IS_PACK_THREADS overrides
+    int n = (int)std::thread::hardware_concurrency();
+    const char* lws = getenv("LOCAL_WORLD_SIZE");
+    const int ranks = lws ? atoi(lws) : 1;
+    n = n / (ranks > 1 ? ranks : 1) - 2;
+    const char* e = getenv("LC2IS_PACK_THREADS");
+    if (e) n = atoi(e);
+    return n < 1 ? 1 : (n > 12 ? 12 : n);
+}
 PackPool& pack_pool() {
-    static PackPool pool([] {
-        int n = (int)std::thread::hardware_concurrency() - 2;   // leave the caller's thread and one spare
-        const char* e = getenv("LC2IS_PACK_THREADS");
-        if (e) n = atoi(e);
-        return n < 1 ? 1 : (n > 16 ? 16 : n);
-    }());
+    static PackPool pool(pack_threads_default());
     return pool;
 }
 // split [0,n) into pieces for the pool; *pending counts the pieces still running
@@ -185,6 +191,8 @@ inline void pack_wait(std::atomic<int>* pending) {
     while (pending->load(std::memory_order_acquire) > 0) _mm_pause();
 }
 }  // namespace
+
+extern "C" int lc2is_pack_threads(void) { return pack_threads_default(); }
 
 extern "C" int lc2is_pack_labels_host(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index,
                                       uint16_t* h_out) {

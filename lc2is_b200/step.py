@@ -55,6 +55,7 @@ class HeadStep:
         nbytes = int(lib.lc2is_cosine_logits_bwd_workspace(B, self.hw, D, 1, C))
         self.bwd_ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
         self.k2_events = None          # optional (start, stop) CUDA events around the K2 call
+        self._pending = None           # outstanding all-reduces of the previous step (data-parallel)
 
     def __call__(self, v: torch.Tensor, t: torch.Tensor, labels: torch.Tensor) -> None:
         """v [B,hw,D] (bf16/fp32), t [C,D] fp32, labels [B,H,W] int64 - all on the device.
@@ -65,6 +66,7 @@ class HeadStep:
         st = stream_ptr()
         B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
         dist_on = self.distributed
+        self.finish()
         self.scalars.zero_()
         self.confmat.zero_()
         if self.backward:
@@ -115,11 +117,19 @@ class HeadStep:
         if dist_on:
             self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
             w_b = dp.allreduce_sum_async(self.bucket.flat)
-            w_cm.wait()
-            w_b.wait()
-            self.loss.copy_(self.bucket.views[1] / self.n_valid)
+            # the two result all-reduces are waited for lazily (finish(), or the start of the next step): in a
+            # trainer they overlap the upstream backward that consumes grad_v; nothing below depends on them
+            self._pending = (w_cm, w_b)
         else:
             check(lib.lc2is_finalize_loss(ptr(self.loss_sum), ptr(self.n_valid), ptr(self.loss), st), "finalize_loss")
+
+    def finish(self) -> None:
+        """Make the current stream wait for the step's outstanding all-reduces (no host sync) and form the loss."""
+        if self._pending is not None:
+            for wk in self._pending:
+                wk.wait()
+            self._pending = None
+            self.loss.copy_(self.bucket.views[1] / self.n_valid)
 
 
 class HostStep:
@@ -149,7 +159,9 @@ class HostStep:
         self.ignore_index, self.logit_scale, self.backward = ignore_index, logit_scale, backward
         nbytes = int(lib.lc2is_head_step_workspace(B, h * w, D, C, H, W))
         # pinned scratch for the host-side int64 -> packed uint16 narrowing of the labels (split geometries)
-        self.host_pack = bool(host_pack and lib.lc2is_ce_split_supported(h, w, H, W) and C < 0x7fff)
+        # (needs a few host threads per rank: with fewer than 4 the 8-byte labels cross PCIe as they are)
+        self.host_pack = bool(host_pack and lib.lc2is_ce_split_supported(h, w, H, W) and C < 0x7fff
+                              and lib.lc2is_pack_threads() >= 4)
         self.slots = [HostStep._Slot(nbytes, B, H, W, C, dev, self.host_pack) for _ in range(max(1, depth))]
         self.copy_stream = torch.cuda.Stream(device=dev) if pipelined else None
         self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + B * H * W * (2 if self.host_pack else 8)
