@@ -43,6 +43,7 @@ def parse():
     p.add_argument("--no-backward", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--kernel-times", action="store_true", help="extra pass: per-section CUDA-event times (not the timed run)")
     return p.parse_args()
 
 
@@ -242,6 +243,16 @@ def run_b200(a):
     sampler.join(timeout=1)
     clocks = sampler.result()
 
+    section_us = None
+    if a.kernel_times:
+        step.timers = {}
+        for i in range(20):
+            step(dev_sets[i % nset][0], t_dev, dev_sets[i % nset][1])
+        step.finish()
+        torch.cuda.synchronize()
+        section_us = {k: round(statistics.mean(s.elapsed_time(e) for s, e in v) * 1e3, 1) for k, v in step.timers.items()}
+        step.timers = None
+
     # ---- end to end: host (pinned) buffers through the C-ABI host entry, H2D/D2H inside the timed region
     e2e = None
     if not a.no_e2e:
@@ -350,7 +361,7 @@ def run_b200(a):
                    "backward": backward,
                    "l2": f"inputs rotate over {nset} distinct sets ({nset * set_bytes / 2**20:.0f} MiB) > 126 MiB L2; no flush"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "cpu_baseline": cpu_baseline,
+        "cpu_baseline": cpu_baseline, "section_us": section_us,
         "check": {"loss": loss_val, "mIoU": miou, "n_valid": int(step.n_valid)},
     }
     print(json.dumps(line), flush=True)

@@ -97,10 +97,14 @@ def gather_per_image(per_image: Tensor, counts: Sequence[int]) -> Tensor:
 class GradBucket:
     """One flat fp32 buffer holding views of every head gradient, all-reduced with a single call."""
 
-    def __init__(self, shapes: Iterable[Sequence[int]], device) -> None:
+    def __init__(self, shapes: Iterable[Sequence[int]], device, flat: Optional[Tensor] = None) -> None:
         self.shapes = [tuple(s) for s in shapes]
         self.sizes = [int(torch.Size(s).numel()) for s in self.shapes]
-        self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=device)
+        # `flat`: optional caller-owned fp32 storage of exactly the bucket's size (e.g. a slice of a larger
+        # buffer that is zeroed in one go)
+        if flat is not None:
+            assert flat.dtype == torch.float32 and flat.numel() == sum(self.sizes) and flat.is_contiguous()
+        self.flat = flat if flat is not None else torch.zeros(sum(self.sizes), dtype=torch.float32, device=device)
         self.views: List[Tensor] = []
         o = 0
         for s, n in zip(self.shapes, self.sizes):

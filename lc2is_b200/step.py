@@ -38,16 +38,26 @@ class HeadStep:
         self.v_hat = e(M, D, dt=torch.bfloat16)
         self.inv_v = e(M)
         self.logits = e(B, C, h, w)
-        self.grad_low = e(B, C, h, w)
         self.split = bool(lib.lc2is_ce_split_supported(h, w, H, W))     # label prepass + packed-label K2 / K3
         self.labels_packed = e(B, H, W, dt=torch.uint16) if self.split else None
         self.grad_v = e(B, self.hw, D, dt=torch.bfloat16)
-        # flat all-reduce bucket: [grad_t (C*D) | loss_sum as fp32 (1)]
-        self.bucket = dp.GradBucket([(1, C, D), (1,)], dev)
+        # Everything a step accumulates into lives in ONE flat buffer that is zeroed with a single fill:
+        #   [ grad bucket: grad_t (C*D) | loss_sum as fp32 (1) | pad ] [ grad_low (B*C*h*w) ] [ confmat C*C int64 ]
+        #   [ scalars: double loss_sum | int64 n_valid | float gscale | float loss ]
+        nb = C * D + 1
+        nb_pad = (nb + 3) // 4 * 4
+        ngl = B * C * self.hw
+        ngl_pad = (ngl + 3) // 4 * 4
+        self._acc = torch.zeros(4 * (nb_pad + ngl_pad) + 8 * C * C + 32, dtype=torch.uint8, device=dev)
+        f32 = self._acc[: 4 * (nb_pad + ngl_pad)].view(torch.float32)
+        self.bucket = dp.GradBucket([(1, C, D), (1,)], dev, flat=f32[:nb])
         self.grad_t = self.bucket.views[0]
-        self.confmat = torch.zeros(C, C, dtype=torch.int64, device=dev)
+        self.grad_low = f32[nb_pad:nb_pad + ngl].view(B, C, h, w)
+        o = 4 * (nb_pad + ngl_pad)
+        self.confmat = self._acc[o:o + 8 * C * C].view(torch.int64).view(C, C)
+        o += 8 * C * C
         # scalars: [0:8] double loss_sum | [8:16] int64 n_valid | [16:20] float gscale | [20:24] float loss
-        self.scalars = torch.zeros(32, dtype=torch.uint8, device=dev)
+        self.scalars = self._acc[o:o + 32]
         self.loss_sum = self.scalars[0:8].view(torch.float64)
         self.n_valid = self.scalars[8:16].view(torch.int64)
         self.gscale = self.scalars[16:20].view(torch.float32)
@@ -56,6 +66,18 @@ class HeadStep:
         self.bwd_ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
         self.k2_events = None          # optional (start, stop) CUDA events around the K2 call
         self._pending = None           # outstanding all-reduces of the previous step (data-parallel)
+        self._open = None
+        self.timers = None             # optional {name: [(start, stop) CUDA events]} per C-ABI call (bench --kernel-times)
+
+    def _mark(self, name: str) -> None:
+        """Close the running timed section and open `name` (None = just close).  No-op unless self.timers is a dict."""
+        if self.timers is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        if self._open is not None:
+            self.timers.setdefault(self._open[0], []).append((self._open[1], ev))
+        self._open = (name, ev) if name is not None else None
 
     def __call__(self, v: torch.Tensor, t: torch.Tensor, labels: torch.Tensor) -> None:
         """v [B,hw,D] (bf16/fp32), t [C,D] fp32, labels [B,H,W] int64 - all on the device.
@@ -67,27 +89,26 @@ class HeadStep:
         B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
         dist_on = self.distributed
         self.finish()
-        self.scalars.zero_()
-        self.confmat.zero_()
-        if self.backward:
-            self.bucket.zero_()
+        self._mark("zero-fill")
+        self._acc.zero_()                                        # bucket, grad_low, confmat, scalars: one fill
         glow = ptr(self.grad_low) if self.backward else None
+        self._mark("label prepass / count")
         if self.split:
             # un-scaled gradients accumulate into grad_low (prepass: -onehot, K2: +softmax); 1/N_valid is applied
             # by K1b, so the valid-count all-reduce hides behind K1 / K2 / K3
-            if self.backward:
-                self.grad_low.zero_()
             check(lib.lc2is_ce_labels_prepass(ptr(labels), B, C, h, w, H, W, self.ignore_index,
                                               ptr(self.labels_packed), ptr(self.n_valid), glow, st), "ce_labels_prepass")
         else:
             check(lib.lc2is_count_valid(ptr(labels), labels.numel(), self.ignore_index, ptr(self.n_valid), st),
                   "count_valid")
         w_valid = dp.allreduce_sum_async(self.n_valid) if dist_on else None
+        self._mark("K0+K1 logits")
         check(lib.lc2is_proto_normalize(ptr(t), 1, C, D, int(self.normalize), ptr(self.t_hat), ptr(self.inv_t), st),
               "proto_normalize")
         check(lib.lc2is_cosine_logits_fwd(ptr(v), BF16 if v.dtype == torch.bfloat16 else F32, B, hw, D,
                                           ptr(self.t_hat), 1, C, int(self.normalize), self.logit_scale,
                                           ptr(self.v_hat), ptr(self.inv_v), ptr(self.logits), st), "cosine_logits_fwd")
+        self._mark("K2 upsample+CE")
         if self.k2_events is not None:
             self.k2_events[0].record()
         if self.split:
@@ -98,12 +119,14 @@ class HeadStep:
                                                 None, ptr(self.loss_sum), glow, None, st), "upsample_ce_fwd_bwd")
         if self.k2_events is not None:
             self.k2_events[1].record()
+        self._mark("K3 argmax+confmat")
         if self.split:
             check(lib.lc2is_argmax_confmat_lowres_packed(ptr(self.logits), B, C, h, w, H, W, ptr(self.labels_packed),
                                                          ptr(self.confmat), None, None, st), "argmax_confmat_packed")
         else:
             check(lib.lc2is_argmax_confmat_lowres(ptr(self.logits), B, C, h, w, H, W, BILINEAR, ptr(labels), H, W,
                                                   ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
+        self._mark("K1b backward")
         w_cm = dp.allreduce_sum_async(self.confmat) if dist_on else None
         if w_valid is not None:
             w_valid.wait()                                        # stream-level wait, no host sync
@@ -114,6 +137,7 @@ class HeadStep:
                                               int(self.normalize), self.logit_scale, ptr(self.gscale),
                                               ptr(self.grad_v), BF16, ptr(self.grad_t), ptr(self.bwd_ws), st),
                   "cosine_logits_bwd")
+        self._mark("finalize")
         if dist_on:
             self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
             w_b = dp.allreduce_sum_async(self.bucket.flat)
@@ -122,6 +146,7 @@ class HeadStep:
             self._pending = (w_cm, w_b)
         else:
             check(lib.lc2is_finalize_loss(ptr(self.loss_sum), ptr(self.n_valid), ptr(self.loss), st), "finalize_loss")
+        self._mark(None)
 
     def finish(self) -> None:
         """Make the current stream wait for the step's outstanding all-reduces (no host sync) and form the loss."""
