@@ -344,6 +344,13 @@ def run_b200(a):
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": k2_bytes, "kernel_us": k2_ms * 1e3,
                 "note": "K2 is FP32-pipe bound (packed FFMA2 at 2 warp-inst/clk/SM), not HBM-bound: see DESIGN.md; "
                         f"{B * C * H * W / (k2_ms * 1e-3) / 1e12:.3f} T softmax-elements/s"}
+    # the bound that does bind K2: 4 packed fp32x2 instructions per pixel pair and class (pass A: add + mul,
+    # pass B: two fma) at the measured packed issue rate of 2.0 warp-inst/clk/SM (tools/micro/k2loops.cu)
+    sm_hz = (clocks.get("sm_mhz") or 1965) * 1e6
+    alg_inst = B * C * H * W / 2 * 4 / 32
+    alg_us = alg_inst / (2.0 * 148 * sm_hz) * 1e6
+    roofline["fp32_pipe"] = {"algorithmic_packed_warp_inst": alg_inst, "peak_warp_inst_per_clk_per_sm": 2.0,
+                             "algorithmic_us": alg_us, "frac": alg_us / (k2_ms * 1e3)}
 
     cpu_baseline = None
     if not a.no_cpu_baseline and world == 1:

@@ -63,9 +63,10 @@ k1b_prep_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ L
 
 // Same projections from the fp32 gradient [B,C,hw] (what K2 produces), fused with its conversion to the
 // bf16 [B,C_pad,hw] operand of the two GEMMs (pad rows zeroed): one pass over G and the logits.
-// CTA = 128 pixels x all classes: warp w walks classes w, w+8, ... with one float4 of G and of the logits per
-// lane; class sums leave with one reduction per (class, CTA), pixel sums meet in shared memory.
-constexpr int PREPF_PX = 128, PREPF_W = 8;
+// CTA = 128 pixels x one class slice (blockIdx.z of PREPF_CS slices): warp w walks classes w, w+8, ... of the slice with
+// one float4 of G and of the logits per lane; class sums leave with one reduction per (class, CTA), pixel sums meet in
+// shared memory and leave with one reduction per (pixel, slice) (r is zeroed by the caller).
+constexpr int PREPF_PX = 128, PREPF_W = 8, PREPF_CS = 4;
 __global__ void __launch_bounds__(PREPF_W * 32)
 k1b_prep_f32_kernel(const float* __restrict__ G, const float* __restrict__ L, int B, int C, int C_pad, int hw,
                     int n_sets, int want_proj, __nv_bfloat16* __restrict__ Gb, float* __restrict__ r,
@@ -75,13 +76,15 @@ k1b_prep_f32_kernel(const float* __restrict__ G, const float* __restrict__ L, in
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.x * PREPF_PX + lane * 4;
     const bool in = p < hw;                                  // hw % 4 == 0
+    const int cper = ((C_pad + PREPF_CS - 1) / PREPF_CS + PREPF_W - 1) / PREPF_W * PREPF_W;
+    const int c_lo = blockIdx.z * cper, c_hi = min(C_pad, c_lo + cper);
     const float* g = G + (size_t)b * C * hw + p;
     const float* l = L + (size_t)b * C * hw + p;
     __nv_bfloat16* gb = Gb + (size_t)b * C_pad * hw + p;
     float* rts = rt + (size_t)(n_sets > 1 ? b : 0) * C;
     float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int c = warp; c < C_pad; c += PREPF_W) {
+#pragma unroll 5
+    for (int c = c_lo + warp; c < c_hi; c += PREPF_W) {
         float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), lv = gv;
         if (c < C && in) {
             gv = __ldcs(reinterpret_cast<const float4*>(g + (size_t)c * hw));
@@ -108,7 +111,7 @@ k1b_prep_f32_kernel(const float* __restrict__ G, const float* __restrict__ L, in
         float t = 0.f;
 #pragma unroll
         for (int w = 0; w < PREPF_W; ++w) t += racc_s[w][threadIdx.x];
-        if (pp < hw) r[(size_t)b * hw + pp] = t;
+        if (pp < hw) atomicAdd(r + (size_t)b * hw + pp, t);
     }
 }
 
@@ -455,13 +458,13 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, c
     float* d_r = (float*)(ws + L.r);
     float* d_rt = (float*)(ws + L.rt);
     float* d_dtraw = (float*)(ws + L.dt_raw);
-    LC2IS_CUDA(cudaMemsetAsync(ws + L.rt, 0, L.gbf - L.rt, st));            // rt and dt_raw
+    LC2IS_CUDA(cudaMemsetAsync(ws + L.r, 0, L.gbf - L.r, st));              // r, rt and dt_raw
 
     // ---- projections r, rt (and the bf16 operand copy of an fp32 gradient) -------------------------
     const void* d_grad_logits_bf16 = d_grad_logits;
     if (g_dtype == LC2IS_F32) {
         d_grad_logits_bf16 = ws + L.gbf;
-        dim3 grid((hw + PREPF_PX - 1) / PREPF_PX, B);
+        dim3 grid((hw + PREPF_PX - 1) / PREPF_PX, B, PREPF_CS);
         k1b_prep_f32_kernel<<<grid, PREPF_W * 32, 0, st>>>((const float*)d_grad_logits, d_logits, B, C, C_pad, hw,
                                                            n_sets, normalize, (__nv_bfloat16*)(ws + L.gbf), d_r, d_rt);
         LC2IS_CHECK_LAUNCH("k1b_prep_f32_kernel");

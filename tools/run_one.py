@@ -15,6 +15,11 @@ for _ in range(3):
     if which == "k1": ops.cosine_logits_fwd(V, t_hat, C, (h, h))
     if which == "k2": ops.upsample_ce(logits, L, 0, gs)
     if which == "k2split": ops.upsample_ce_split(logits, L, 0)
+    if which == "step":
+        from lc2is_b200.step import HeadStep
+        if "hs" not in globals():
+            hs = HeadStep(B, h, h, H, H, C, ignore_index=0)
+        hs(V, t, L)
     if which == "k3split":
         pk = ops.upsample_ce_split(logits, L, 0, want_grad=False)[3]
         ops.argmax_confmat_packed(logits, pk, (H, H))
