@@ -20,6 +20,14 @@ from ._lib import BF16, BILINEAR, F32, check, lib, ptr, stream_ptr
 
 
 class HeadStep:
+    """Pre-allocated device-resident step.  Per call: loss / n_valid / grad_v / grad_t of the batch; the confusion
+    matrix ACCUMULATES over calls (``reset_metrics()`` clears it, ``global_confmat()`` returns it summed over the
+    ranks - integer sums commute, so an evaluation pass needs ONE int64 all-reduce at its end).
+
+    Data-parallel order of a call (weak scaling, one process per GPU):
+        zero-fill -> label prepass -> [n_valid all-reduce, async] -> K0 -> K1 -> K2 -> [wait n_valid] -> K1b ->
+        [gradient-bucket all-reduce, async] -> K3 -> [wait bucket] -> loss
+    so the valid-count all-reduce hides behind K0/K1/K2 and the gradient all-reduce behind K3."""
 
     def __init__(self, B: int, h: int, w: int, H: int, W: int, C: int, D: int = 512, ignore_index: int = 0,
                  logit_scale: float = 1.0, normalize: bool = True, backward: bool = True,
@@ -42,32 +50,31 @@ class HeadStep:
         self.labels_packed = e(B, H, W, dt=torch.uint16) if self.split else None
         self.grad_v = e(B, self.hw, D, dt=torch.bfloat16)
         # Everything a step accumulates into lives in ONE flat buffer that is zeroed with a single fill:
-        #   [ grad bucket: grad_t (C*D) | loss_sum as fp32 (1) | pad ] [ grad_low (B*C*h*w) ] [ confmat C*C int64 ]
+        #   [ grad bucket: grad_t (C*D) | loss_sum as fp32 (1) | pad ] [ grad_low (B*C*h*w) ]
         #   [ scalars: double loss_sum | int64 n_valid | float gscale | float loss ]
         nb = C * D + 1
         nb_pad = (nb + 3) // 4 * 4
         ngl = B * C * self.hw
         ngl_pad = (ngl + 3) // 4 * 4
-        self._acc = torch.zeros(4 * (nb_pad + ngl_pad) + 8 * C * C + 32, dtype=torch.uint8, device=dev)
+        self._acc = torch.zeros(4 * (nb_pad + ngl_pad) + 32, dtype=torch.uint8, device=dev)
         f32 = self._acc[: 4 * (nb_pad + ngl_pad)].view(torch.float32)
         self.bucket = dp.GradBucket([(1, C, D), (1,)], dev, flat=f32[:nb])
         self.grad_t = self.bucket.views[0]
         self.grad_low = f32[nb_pad:nb_pad + ngl].view(B, C, h, w)
         o = 4 * (nb_pad + ngl_pad)
-        self.confmat = self._acc[o:o + 8 * C * C].view(torch.int64).view(C, C)
-        o += 8 * C * C
         # scalars: [0:8] double loss_sum | [8:16] int64 n_valid | [16:20] float gscale | [20:24] float loss
         self.scalars = self._acc[o:o + 32]
         self.loss_sum = self.scalars[0:8].view(torch.float64)
         self.n_valid = self.scalars[8:16].view(torch.int64)
         self.gscale = self.scalars[16:20].view(torch.float32)
         self.loss = self.scalars[20:24].view(torch.float32)
+        self.confmat = torch.zeros(C, C, dtype=torch.int64, device=dev)        # this rank's counts, accumulated
+        self._confmat_global = torch.zeros(C, C, dtype=torch.int64, device=dev) if self.distributed else None
         nbytes = int(lib.lc2is_cosine_logits_bwd_workspace(B, self.hw, D, 1, C))
         self.bwd_ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
         self.k2_events = None          # optional (start, stop) CUDA events around the K2 call
-        self._pending = None           # outstanding all-reduces of the previous step (data-parallel)
         self._open = None
-        self.timers = None             # optional {name: [(start, stop) CUDA events]} per C-ABI call (bench --kernel-times)
+        self.timers = None             # optional {name: [(start, stop) CUDA events]} per section (bench --kernel-times)
 
     def _mark(self, name: str) -> None:
         """Close the running timed section and open `name` (None = just close).  No-op unless self.timers is a dict."""
@@ -79,23 +86,35 @@ class HeadStep:
             self.timers.setdefault(self._open[0], []).append((self._open[1], ev))
         self._open = (name, ev) if name is not None else None
 
-    def __call__(self, v: torch.Tensor, t: torch.Tensor, labels: torch.Tensor) -> None:
-        """v [B,hw,D] (bf16/fp32), t [C,D] fp32, labels [B,H,W] int64 - all on the device.
+    def reset_metrics(self) -> None:
+        self.confmat.zero_()
 
-        Data-parallel ordering: the three collectives are issued asynchronously so that the valid-count
-        all-reduce hides behind K0/K1 and the confusion-matrix all-reduce behind K1b; only the final
-        gradient-bucket all-reduce is exposed."""
+    def global_confmat(self) -> torch.Tensor:
+        """The accumulated confusion matrix summed over all ranks (ONE int64 all-reduce; bit-identical to the
+        single-GPU matrix).  Without a process group: the local matrix."""
+        if not self.distributed:
+            return self.confmat
+        self._confmat_global.copy_(self.confmat)
+        dp.allreduce_confmat_(self._confmat_global)
+        return self._confmat_global
+
+    def finish(self) -> None:
+        """Kept for callers of the earlier interface: a call leaves nothing outstanding any more."""
+        return None
+
+    def __call__(self, v: torch.Tensor, t: torch.Tensor, labels: torch.Tensor) -> None:
+        """v [B,hw,D] (bf16/fp32), t [C,D] fp32, labels [B,H,W] int64 - all on the device.  Enqueues everything on
+        the current stream; no host synchronisation."""
         st = stream_ptr()
         B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
         dist_on = self.distributed
-        self.finish()
         self._mark("zero-fill")
-        self._acc.zero_()                                        # bucket, grad_low, confmat, scalars: one fill
+        self._acc.zero_()                                        # bucket, grad_low, scalars: one fill
         glow = ptr(self.grad_low) if self.backward else None
         self._mark("label prepass / count")
         if self.split:
             # un-scaled gradients accumulate into grad_low (prepass: -onehot, K2: +softmax); 1/N_valid is applied
-            # by K1b, so the valid-count all-reduce hides behind K1 / K2 / K3
+            # by K1b, so the valid-count all-reduce hides behind K0 / K1 / K2
             check(lib.lc2is_ce_labels_prepass(ptr(labels), B, C, h, w, H, W, self.ignore_index,
                                               ptr(self.labels_packed), ptr(self.n_valid), glow, st), "ce_labels_prepass")
         else:
@@ -119,15 +138,7 @@ class HeadStep:
                                                 None, ptr(self.loss_sum), glow, None, st), "upsample_ce_fwd_bwd")
         if self.k2_events is not None:
             self.k2_events[1].record()
-        self._mark("K3 argmax+confmat")
-        if self.split:
-            check(lib.lc2is_argmax_confmat_lowres_packed(ptr(self.logits), B, C, h, w, H, W, ptr(self.labels_packed),
-                                                         ptr(self.confmat), None, None, st), "argmax_confmat_packed")
-        else:
-            check(lib.lc2is_argmax_confmat_lowres(ptr(self.logits), B, C, h, w, H, W, BILINEAR, ptr(labels), H, W,
-                                                  ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
         self._mark("K1b backward")
-        w_cm = dp.allreduce_sum_async(self.confmat) if dist_on else None
         if w_valid is not None:
             w_valid.wait()                                        # stream-level wait, no host sync
         check(lib.lc2is_mean_scale(ptr(self.n_valid), 1.0, ptr(self.gscale), st), "mean_scale")
@@ -137,24 +148,24 @@ class HeadStep:
                                               int(self.normalize), self.logit_scale, ptr(self.gscale),
                                               ptr(self.grad_v), BF16, ptr(self.grad_t), ptr(self.bwd_ws), st),
                   "cosine_logits_bwd")
-        self._mark("finalize")
+        w_b = None
         if dist_on:
             self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
-            w_b = dp.allreduce_sum_async(self.bucket.flat)
-            # the two result all-reduces are waited for lazily (finish(), or the start of the next step): in a
-            # trainer they overlap the upstream backward that consumes grad_v; nothing below depends on them
-            self._pending = (w_cm, w_b)
+            w_b = dp.allreduce_sum_async(self.bucket.flat)       # ... and hides behind K3
+        self._mark("K3 argmax+confmat")
+        if self.split:
+            check(lib.lc2is_argmax_confmat_lowres_packed(ptr(self.logits), B, C, h, w, H, W, ptr(self.labels_packed),
+                                                         ptr(self.confmat), None, None, st), "argmax_confmat_packed")
+        else:
+            check(lib.lc2is_argmax_confmat_lowres(ptr(self.logits), B, C, h, w, H, W, BILINEAR, ptr(labels), H, W,
+                                                  ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
+        self._mark("finalize")
+        if dist_on:
+            w_b.wait()
+            self.loss.copy_(self.bucket.views[1] / self.n_valid)
         else:
             check(lib.lc2is_finalize_loss(ptr(self.loss_sum), ptr(self.n_valid), ptr(self.loss), st), "finalize_loss")
         self._mark(None)
-
-    def finish(self) -> None:
-        """Make the current stream wait for the step's outstanding all-reduces (no host sync) and form the loss."""
-        if self._pending is not None:
-            for wk in self._pending:
-                wk.wait()
-            self._pending = None
-            self.loss.copy_(self.bucket.views[1] / self.n_valid)
 
 
 class HostStep:

@@ -25,16 +25,16 @@ def _worker(rank, world, port, out):
     labels[Bg // 2:, :200] = 0                               # unequal valid counts per rank
     b = Bg // world
     step = HeadStep(b, h, h, H, H, C, ignore_index=0, device=dev, distributed=True)
-    for _ in range(2):                                       # twice: the lazily waited all-reduces of step 1
+    for _ in range(2):                                       # the confusion matrix accumulates over calls
         step(v[rank * b:(rank + 1) * b].to(dev), t.to(dev), labels[rank * b:(rank + 1) * b].to(dev))
-    step.finish()
+    cm_global = step.global_confmat().clone()                # ONE int64 all-reduce for both steps
     torch.cuda.synchronize()
     if rank == 0:
         ref = HeadStep(Bg, h, h, H, H, C, ignore_index=0, device=dev, distributed=False)
         ref(v.to(dev), t.to(dev), labels.to(dev))
         torch.cuda.synchronize()
         res = {
-            "cm_equal": bool(torch.equal(step.confmat, ref.confmat)),
+            "cm_equal": bool(torch.equal(cm_global, 2 * ref.confmat)),
             "nv": (int(step.n_valid), int(ref.n_valid)),
             "loss": (float(step.loss), float(ref.loss)),
             "gt_err": float((step.grad_t - ref.grad_t).abs().max() / ref.grad_t.abs().max()),
