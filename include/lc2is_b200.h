@@ -193,6 +193,17 @@ int lc2is_argmax_confmat_lowres_packed(const float* d_low, int N, int C, int h, 
                                        int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                        lc2is_stream_t stream);
 
+/* K2 (split form) and K3 in ONE warp-specialised kernel for the x16 geometry (what the whole-step entries run when
+ * lc2is_ce_argmax_fused_supported): the taps are staged once per 16 groups, four warps of a CTA run the
+ * cross-entropy strips (FP32-pipe bound), four the argmax rows (ALU / issue bound).  Same results as
+ * lc2is_upsample_ce_packed followed by lc2is_argmax_confmat_lowres_packed (bilinear). */
+int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W);
+int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* d_labels_packed,
+                                 int B, int C, int h, int w, int H, int W,
+                                 double* d_loss_sum, float* d_grad_low,
+                                 int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                                 lc2is_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Whole step from HOST buffers (the end-to-end path bench.py times as `e2e`).  Replaces one
  * iteration of Engine.train_loop / eval_loop over the head (engine.py:75-101,145-163):

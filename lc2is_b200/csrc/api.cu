@@ -371,7 +371,10 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         STEP_RC(lc2is_cosine_logits_fwd(d_v + v_off, LC2IS_BF16, nb, hw, D, d_that, 1, C, 1, logit_scale,
                                         d_vhat + v_off, d_invv + (size_t)b0 * hw, lg, stream));
         mark("k1", st);
-        if (split) {
+        if (split && lc2is_ce_argmax_fused_supported(C, h, w, H, W)) {
+            STEP_RC(lc2is_ce_argmax_fused_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, d_cm,
+                                                 nullptr, nullptr, stream));
+        } else if (split) {
             STEP_RC(lc2is_upsample_ce_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, stream));
             STEP_RC(lc2is_argmax_confmat_lowres_packed(lg, nb, C, h, w, H, W, d_packed + lab_off, d_cm, nullptr,
                                                        nullptr, stream));

@@ -20,21 +20,11 @@
 //
 // Generic path (any size): one pixel per thread, taps from global, global atomics.
 #include "common.cuh"
+#include "k2_strip.cuh"
 #include <type_traits>
+#include <stdlib.h>
 
 namespace lc2is {
-
-constexpr float LOG2E = 1.4426950408889634f;
-constexpr float LN2 = 0.6931471805599453f;
-constexpr float S_MIN = 1e-30f;       // below this the shared shift lost precision -> slow path
-
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
 
 // ---------------------------------------------------------------------------------------------
 // count valid labels (the 'mean' denominator)
@@ -83,59 +73,6 @@ struct K2Params {
     int tgy, tgx;                 // groups per CTA
     float rs;
 };
-
-constexpr float K2_FAST_RANGE = 40.f;   // max logit range inside a group for the shared-shift fast path
-
-__device__ __forceinline__ int clampi2(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 - two fp32 ops per issue slot) ------
-__device__ __forceinline__ unsigned long long pk2(float2 a) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
-    return r;
-}
-__device__ __forceinline__ float2 up2(unsigned long long r) {
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
-    return d;
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
-    return up2(d);
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)));
-    return up2(d);
-}
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
-    return up2(d);
-}
-__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
-
-// Sum (a,b,c,d) over the LPG consecutive lanes of a group.  After the call lane u of the group
-// holds in `a` the total of value number (u * 4 / LPG) [LPG >= 4], i.e. the first quarter of the
-// lanes hold sum(a), the second sum(b), ... ; for LPG == 1 nothing happens.
-template <int LPG>
-__device__ __forceinline__ void group_reduce4(float& a, float& b, float& c, float& d, int u) {
-    if constexpr (LPG >= 4) {
-        const bool up = u & (LPG / 2);
-        float s0 = up ? a : c, s1 = up ? b : d;          // what this lane gives away
-        float k0 = up ? c : a, k1 = up ? d : b;          // what it keeps
-        k0 += __shfl_xor_sync(0xffffffffu, s0, LPG / 2);
-        k1 += __shfl_xor_sync(0xffffffffu, s1, LPG / 2);
-        const bool up2 = u & (LPG / 4);
-        float g = up2 ? k0 : k1;
-        float k = up2 ? k1 : k0;
-        k += __shfl_xor_sync(0xffffffffu, g, LPG / 4);
-#pragma unroll
-        for (int o = LPG / 8; o > 0; o >>= 1) k += __shfl_xor_sync(0xffffffffu, k, o);
-        a = k;
-    }
-}
 
 // exp-polynomial of one class inside a 4x4 block: exp(l(i,j) - M) = E * p^i * q^j * t^(i*j)
 struct Poly { float E, p, q, t; };
@@ -473,95 +410,14 @@ k2_fast_kernel(const K2Params P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Strip path (scale S = 8 or 16): the dominant kernel at the aux-head geometry (32^2 -> 512^2).
-//
-// A GROUP (gy,gx) is the S x S pixel region that interpolates between source cells (ky,kx) = (gy-1,gx-1)
-// .. (ky+1,kx+1) (index-clamped; (h+1) x (w+1) groups per image, border groups are half empty).  One
-// thread owns a STRIP of the group: 2 rows x S columns, the two rows packed as fp32x2.  Along a row the
-// upsampled logit is linear in the column, so per (class, row)
-//       exp2(k*l(j) - k*M) = E * rho^j ,   E = exp2(k*(L + lx0*(R-L)) - k*M),  rho = exp2(k*(R-L)/S)
-// (L / R = the row's left / right source values): 4 ex2 per class per 2*S pixels, then
-//   pass A  S(j) += e ; e *= rho                      one FADD2 + one FMUL2 per pixel PAIR and class
-//   pass B  with U(j) = g / S(j):  h = sum_j U(j) rho^j and d = dh/drho by one Horner sweep
-//           (d = d*rho + h ; h = h*rho + U(j): two FFMA2 per pixel pair), which give the row's
-//           sum_j softmax*U = E*h and sum_j j*softmax*U = E*rho*d, i.e. the four tap gradients.
-// Warps are independent (no CTA barrier): a warp owns a 2 x (GPW/2) tile of groups, stages their taps
-// as per-group quads st[c][group][4] with cp.async, and in pass B the S/2 lanes of a group add their tap
-// gradients with a shuffle butterfly and store them IN PLACE over the group's staged taps.  Finally the
-// warp sums the quads of its tile per source cell in a fixed order: one L2 reduction per (class, cell),
-// 9 instead of 16 per 2x2-group tile.  The class loops are software pipelined by hand (the taps of class
-// c+1 are loaded and exponentiated before the chain of class c; the in-place store would otherwise pin
-// every shared-memory load behind it).
-// M = max tap of the group (a valid softmax shift); groups whose taps span more than K2_FAST_RANGE or are
-// not finite take the exact per-pixel path (k2_strip_slow, warp-uniform).
-struct K2SParams {
-    const float* low;
-    const long long* labels;      // int64 labels (one-call path) ...
-    const unsigned short* labels16;   // ... or packed labels from the prepass (split path), 0xFFFF = not counted
-    float* grad_low;
-    double* loss_sum;
-    const float* grad_scale;
-    long long ignore_index;
-    int B, C, h, w, H, W;
-    int nty, ntx;                 // warp tiles per image
-};
-
-template <int S, bool SPLIT>
-__device__ __noinline__ float k2_strip_slow(const float* st, int cs, int gl, unsigned vm, int n, int y0, int x0,
-                                            int u, const K2SParams& P, float gs, float* gA, float* gB,
-                                            float* gC, float* gD) {
-    const int C = P.C;
-    const size_t plane = (size_t)P.h * P.w;
-    float loss = 0.f;
-    for (int r = 0; r < 2; ++r)
-        for (int j = 0; j < S; ++j) {
-            if (!((vm >> (r * 16 + j)) & 1u)) continue;
-            // SPLIT: the prepass owns the -onehot term; the caller has already subtracted the target logits
-            const int t = SPLIT ? -1 : (int)__ldg(P.labels + ((size_t)n * P.H + (y0 + r)) * P.W + (x0 + j));
-            const float ly = ((float)(2 * u + r) + 0.5f) * (1.f / S), lx = ((float)j + 0.5f) * (1.f / S);
-            float m = -INFINITY;
-            for (int c = 0; c < C; ++c) {
-                const float4 q = *reinterpret_cast<const float4*>(st + (size_t)c * cs + gl * 4);
-                const float L = fmaf(ly, q.z - q.x, q.x), R = fmaf(ly, q.w - q.y, q.y);
-                m = fmaxf(m, fmaf(lx, R - L, L));
-            }
-            float sum = 0.f, lt = 0.f;
-            for (int c = 0; c < C; ++c) {
-                const float4 q = *reinterpret_cast<const float4*>(st + (size_t)c * cs + gl * 4);
-                const float L = fmaf(ly, q.z - q.x, q.x), R = fmaf(ly, q.w - q.y, q.y);
-                const float l = fmaf(lx, R - L, L);
-                sum += ex2f((l - m) * LOG2E);
-                if (c == t) lt = l;
-            }
-            loss += logf(sum) + m - lt;
-            if (gA) {
-                const float uu = gs / sum;
-                const float wa = (1.f - ly) * (1.f - lx), wb = (1.f - ly) * lx, wc = ly * (1.f - lx), wd = ly * lx;
-                for (int c = 0; c < C; ++c) {
-                    const float4 q = *reinterpret_cast<const float4*>(st + (size_t)c * cs + gl * 4);
-                    const float L = fmaf(ly, q.z - q.x, q.x), R = fmaf(ly, q.w - q.y, q.y);
-                    const float gg = ex2f((fmaf(lx, R - L, L) - m) * LOG2E) * uu - (c == t ? gs : 0.f);
-                    atomicAdd(gA + (size_t)c * plane, gg * wa); atomicAdd(gB + (size_t)c * plane, gg * wb);
-                    atomicAdd(gC + (size_t)c * plane, gg * wc); atomicAdd(gD + (size_t)c * plane, gg * wd);
-                }
-            }
-        }
-    return loss;
-}
-
+// Strip path kernel (scale 8 / 16); the device code lives in k2_strip.cuh
 // SPLIT = false: the one-call path (int64 labels; loss, -g*onehot and g*softmax all here).
-// SPLIT = true : the label-only work (valid count, packing, -onehot term, target logits) was done by
-//                k2_labels_prepass_kernel; this kernel adds sum(log-sum-exp) and the softmax term only.
+// SPLIT = true : the label-only work (valid count, packing, -onehot term) was done by k2_labels_prepass_kernel;
+//                this kernel adds sum(log-sum-exp - target logit) and the softmax term only.
 template <int S, bool SPLIT>
 __global__ void __launch_bounds__(128)
 k2_strip_kernel(const K2SParams P) {
-    constexpr int TPG = S / 2;                              // threads (lanes) per group
-    constexpr int GPW = 32 / TPG;                           // groups per warp: 4 (S=16) / 8 (S=8)
-    constexpr int WGX = GPW / 2;                            // warp tile = 2 x WGX groups
-    constexpr int CS = GPW * 4;                             // floats per class in the warp's tile
-    constexpr int NCX = WGX + 1, NCELL = 3 * NCX;           // source cells touched by the warp tile
-    constexpr float RS = 1.f / S;
-    constexpr float LX0 = 0.5f / S;                         // lambda_x of the group's first column
+    constexpr int TPG = S / 2, GPW = 32 / TPG, WGX = GPW / 2, CS = GPW * 4;
     extern __shared__ float smem[];
     const int C = P.C;
     const int lane = threadIdx.x & 31;
@@ -572,17 +428,9 @@ k2_strip_kernel(const K2SParams P) {
     const int trem = (int)(wt - (long long)n * tiles_per_img);
     const int tyi = trem / P.ntx, txi = trem - tyi * P.ntx;
     const int GY0 = tyi * 2, GX0 = txi * WGX;
-    float* st = smem + (size_t)(threadIdx.x >> 5) * (C + 2) * CS;   // + 2 padding class slots (look-ahead)  // st[c][group][4 taps]  (later: 4 tap gradients)
+    float* st = smem + (size_t)(threadIdx.x >> 5) * (C + 2) * CS;   // st[c][group][4 taps] + 2 padding class slots
     const size_t plane = (size_t)P.h * P.w;
     const float* lowb = P.low + (size_t)n * C * plane;
-
-    // ---- this thread's strip ------------------------------------------------------------------------------
-    const int gl = lane / TPG, u = lane % TPG;
-    const int ky = GY0 + gl / WGX - 1, kx = GX0 + gl % WGX - 1;   // top-left tap of the group (-1 .. h-1)
-    const bool group_in = ky < P.h && kx < P.w;
-    const int y0 = S * ky + S / 2 + 2 * u, x0 = S * kx + S / 2;
-    const float gs = P.grad_scale ? __ldg(P.grad_scale) : 1.f;
-
     // ---- stage the warp's taps: lane -> fixed (group, tap), strided over classes -------------------------------
     {
         constexpr int CSTEP = 32 / CS > 0 ? 32 / CS : 1;    // 2 (S=16) / 1 (S=8)
@@ -598,264 +446,7 @@ k2_strip_kernel(const K2SParams P) {
             else dst[c * CS] = 0.f;
         }
     }
-
-    // valid-label mask of the 2 x S pixels (bit r*16 + j); labels are re-read where their value is needed
-    unsigned vm = 0;
-    unsigned lw[SPLIT ? S : 1];                             // SPLIT: the strip's packed labels (2 per word)
-    if constexpr (SPLIT) {
-#pragma unroll
-        for (int k = 0; k < S; ++k) lw[k] = 0xffffffffu;
-    }
-    if (group_in) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int y = y0 + r;
-            if (y < 0 || y >= P.H) continue;
-            if constexpr (SPLIT) {
-                // packed labels: S/2 pixels (S bytes) per load
-                using V = typename std::conditional<S == 16, uint4, uint2>::type;
-                const unsigned short* row = P.labels16 + ((size_t)n * P.H + y) * P.W;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    const int x = x0 + hh * (S / 2);
-                    if (x < 0 || x >= P.W) continue;
-                    const V t = __ldg(reinterpret_cast<const V*>(row + x));
-                    const unsigned* wv = reinterpret_cast<const unsigned*>(&t);
-#pragma unroll
-                    for (int k = 0; k < S / 4; ++k) lw[r * (S / 2) + hh * (S / 4) + k] = wv[k];
-                }
-            } else {
-                const long long* row = P.labels + ((size_t)n * P.H + y) * P.W;
-#pragma unroll
-                for (int jj = 0; jj < S / 2; ++jj) {
-                    const int x = x0 + 2 * jj;
-                    if (x < 0 || x >= P.W) continue;
-                    const longlong2 t = __ldg(reinterpret_cast<const longlong2*>(row + x));
-                    if (t.x != P.ignore_index && t.x >= 0 && t.x < C) vm |= 1u << (r * 16 + 2 * jj);
-                    if (t.y != P.ignore_index && t.y >= 0 && t.y < C) vm |= 1u << (r * 16 + 2 * jj + 1);
-                }
-            }
-        }
-    }
-    if constexpr (SPLIT) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int k = 0; k < S / 2; ++k) {
-                const unsigned wd = lw[r * (S / 2) + k];
-                if ((wd & 0xffffu) < (unsigned)C) vm |= 1u << (r * 16 + 2 * k);
-                if ((wd >> 16) < (unsigned)C) vm |= 1u << (r * 16 + 2 * k + 1);
-            }
-    }
-    cp_async_wait_all();
-    __syncwarp();
-
-    const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
-    const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);
-    float* gb = P.grad_low ? P.grad_low + (size_t)n * C * plane : nullptr;
-    float* gA = gb ? gb + (size_t)Ya * P.w + Xa : nullptr; float* gB = gb ? gb + (size_t)Ya * P.w + Xb : nullptr;
-    float* gC = gb ? gb + (size_t)Yb * P.w + Xa : nullptr; float* gD = gb ? gb + (size_t)Yb * P.w + Xb : nullptr;
-    const float4* st4 = reinterpret_cast<const float4*>(st) + gl;      // + c * GPW
-
-    // ---- softmax shift: M = max over classes of the group's taps --------------------------------------------
-    float mx = -INFINITY, mn = INFINITY;
-    for (int c = u; c < C; c += TPG) {
-        const float4 q = st4[c * GPW];
-        mx = fmaxf(mx, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
-        mn = fminf(mn, fminf(fminf(q.x, q.y), fminf(q.z, q.w)));
-    }
-#pragma unroll
-    for (int o = TPG / 2; o > 0; o >>= 1) {
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-    const float M = mx;
-    const unsigned bal = __ballot_sync(0xffffffffu, vm != 0);
-    const bool warp_any = bal != 0;
-    const bool grp_any = ((bal >> (lane & ~(TPG - 1))) & ((1u << TPG) - 1u)) != 0;
-    const bool slow = __any_sync(0xffffffffu, vm != 0 && !((mx - mn) < K2_FAST_RANGE));
-    const float Mk = M * LOG2E;
-    const float2 ly2 = make_float2(((float)(2 * u) + 0.5f) * RS, ((float)(2 * u) + 1.5f) * RS);
-
-    // per class: (E, rho) of the thread's two rows from the group's taps q = (a, b, c, d)
-    auto row_exp = [&](const float4 q, float2& e2, float2& r2) {
-        const float2 dv = ffma2(make_float2(q.x, q.y), bc2(-1.f), make_float2(q.z, q.w));   // (c-a, d-b)
-        const float2 L2 = ffma2(ly2, bc2(dv.x), bc2(q.x));
-        const float2 R2 = ffma2(ly2, bc2(dv.y), bc2(q.y));
-        const float2 rl2 = ffma2(L2, bc2(-1.f), R2);
-        const float2 aE = ffma2(rl2, bc2(LX0 * LOG2E), ffma2(L2, bc2(LOG2E), bc2(-Mk)));
-        const float2 aR = fmul2(rl2, bc2(RS * LOG2E));
-        e2 = make_float2(ex2f(aE.x), ex2f(aE.y));
-        r2 = make_float2(ex2f(aR.x), ex2f(aR.y));
-    };
-
-    float loss = 0.f;
-    bool wrote = false;                                     // the warp's quads hold tap gradients
-    if constexpr (SPLIT) {
-        // -sum of the target logits of the strip (the -onehot gradient came from the label prepass)
-        if (vm) {
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const float lyr = r ? ly2.y : ly2.x;
-#pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    if (!((vm >> (r * 16 + j)) & 1u)) continue;
-                    const unsigned t = (lw[r * (S / 2) + (j >> 1)] >> (16 * (j & 1))) & 0xffffu;
-                    const float4 q = st4[t * GPW];
-                    const float L = fmaf(lyr, q.z - q.x, q.x), R = fmaf(lyr, q.w - q.y, q.y);
-                    loss -= fmaf(((float)j + 0.5f) * RS, R - L, L);
-                }
-            }
-        }
-    }
-    if (warp_any && !slow) {
-        // ---- pass A ---------------------------------------------------------------------------------------------
-        float2 U2[S];                                       // S(j) of rows (0,1); then U(j) = g / S(j)
-#pragma unroll
-        for (int j = 0; j < S; ++j) U2[j] = make_float2(0.f, 0.f);
-        {
-            // software pipeline: taps two classes ahead, exponentials one class ahead (the tile has two
-            // padding class slots, so the look-ahead needs no bounds check)
-            const float4* qp = st4 + GPW;
-            float2 eN, rN;
-            row_exp(st4[0], eN, rN);
-            float4 qn = *qp;
-#pragma unroll 2
-            for (int c = 0; c < C; ++c) {
-                float2 e2 = eN;
-                const float2 r2 = rN;
-                row_exp(qn, eN, rN);
-                qp += GPW;
-                qn = *qp;
-#pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    U2[j] = fadd2(U2[j], e2);
-                    if (j < S - 1) e2 = fmul2(e2, r2);
-                }
-            }
-        }
-        // ---- loss: log-sum-exp part, and U = g / S --------------------------------------------------------------
-        // (lg2.approx / rcp.approx: 2^-22 relative; S is in [exp(-K2_FAST_RANGE), C], never denormal)
-        {
-            float lg = 0.f;
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const bool va = (vm >> j) & 1u, vb = (vm >> (16 + j)) & 1u;
-                const float sa = va ? U2[j].x : 1.f, sb = vb ? U2[j].y : 1.f;
-                lg += lg2f(sa) + lg2f(sb);
-                U2[j] = make_float2(va ? gs * rcpf(sa) : 0.f, vb ? gs * rcpf(sb) : 0.f);
-            }
-            loss += fmaf((float)__popc(vm), M, lg * LN2);
-        }
-        // ---- target logits and the -g*onehot term (exact integer tap weights, run-length per row) ---------------
-        if (!SPLIT && vm) {
-            const float wscale = -gs / (float)(4 * S * S);
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                if (!((vm >> (r * 16)) & 0xffffu)) continue;
-                const long long* row = P.labels + ((size_t)n * P.H + (y0 + r)) * P.W + x0;
-                const float lyr = r ? ly2.y : ly2.x;
-                const int lyi = 2 * (2 * u + r) + 1;        // lambda_y * 2S
-                int cur = -1, sw0 = 0, sw1 = 0;
-                auto flush = [&]() {
-                    if (cur >= 0 && gb) {
-                        atomicAdd(gA + (size_t)cur * plane, wscale * (float)((2 * S - lyi) * sw0));
-                        atomicAdd(gB + (size_t)cur * plane, wscale * (float)((2 * S - lyi) * sw1));
-                        atomicAdd(gC + (size_t)cur * plane, wscale * (float)(lyi * sw0));
-                        atomicAdd(gD + (size_t)cur * plane, wscale * (float)(lyi * sw1));
-                    }
-                };
-#pragma unroll
-                for (int jj = 0; jj < S / 2; ++jj) {
-                    if (!((vm >> (r * 16 + 2 * jj)) & 3u)) continue;
-                    const longlong2 t2 = __ldg(reinterpret_cast<const longlong2*>(row + 2 * jj));
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int j = 2 * jj + e;
-                        if (!((vm >> (r * 16 + j)) & 1u)) continue;
-                        const int t = (int)(e ? t2.y : t2.x);
-                        const float4 q = st4[t * GPW];
-                        const float L = fmaf(lyr, q.z - q.x, q.x), R = fmaf(lyr, q.w - q.y, q.y);
-                        loss -= fmaf(((float)j + 0.5f) * RS, R - L, L);
-                        if (t != cur) { flush(); cur = t; sw0 = 0; sw1 = 0; }
-                        sw0 += 2 * S - (2 * j + 1);
-                        sw1 += 2 * j + 1;
-                    }
-                }
-                flush();
-            }
-        }
-        // ---- pass B: tap gradients of every class, stored in place ---------------------------------------------
-        if (gb) {
-            __syncwarp();                                   // every lane has read its target taps
-            const int role = (u * 4) / TPG;
-            const bool writer = (u % (TPG / 4)) == 0;
-            float* stw = st + gl * 4 + role;
-            const float2 omy = make_float2(1.f - ly2.x, 1.f - ly2.y);
-            const float4* qp = st4 + GPW;
-            float2 eN, rN;
-            row_exp(st4[0], eN, rN);
-            float4 qn = *qp;
-#pragma unroll 2
-            for (int c = 0; c < C; ++c) {
-                const float2 e2 = eN, r2 = rN;
-                row_exp(qn, eN, rN);                         // class c+1: read before this class's in-place store
-                qp += GPW;
-                qn = *qp;                                    // class c+2
-                float2 h2 = U2[S - 1], d2 = h2;
-                h2 = ffma2(h2, r2, U2[S - 2]);
-#pragma unroll
-                for (int j = S - 3; j >= 0; --j) {
-                    d2 = ffma2(d2, r2, h2);
-                    h2 = ffma2(h2, r2, U2[j]);
-                }
-                const float2 rd2 = fmul2(r2, d2);                              // sum_j j U rho^j
-                const float2 G2 = fmul2(e2, h2);                               // sum_j g
-                const float2 X2 = ffma2(fmul2(e2, rd2), bc2(RS), fmul2(G2, bc2(LX0)));   // sum_j lambda_x g
-                const float2 N2 = ffma2(X2, bc2(-1.f), G2);                    // sum_j (1 - lambda_x) g
-                const float2 a2 = fmul2(omy, N2), b2 = fmul2(omy, X2), c2 = fmul2(ly2, N2), d2y = fmul2(ly2, X2);
-                float A = a2.x + a2.y, Bv = b2.x + b2.y, Cv = c2.x + c2.y, Dv = d2y.x + d2y.y;
-                group_reduce4<TPG>(A, Bv, Cv, Dv, u);
-                if (writer) stw[c * CS] = grp_any ? A : 0.f;  // no valid pixel -> exactly zero (taps may be NaN)
-            }
-            wrote = true;
-        }
-    } else if (warp_any) {
-        loss += k2_strip_slow<S, SPLIT>(st, CS, gl, vm, n, y0, x0, u, P, gs, gA, gB, gC, gD);
-    }
-    if (gb && wrote) {
-        __syncwarp();
-        // ---- combine: one L2 reduction per (class, source cell of the warp tile) -------------------------------
-        // lane -> fixed cell (lane % NCELL), classes strided by 32 / NCELL
-        constexpr int CPI = 32 / NCELL;                     // classes per iteration: 3 (S=16) / 2 (S=8)
-        const int cell = lane % NCELL, c0 = lane / NCELL;
-        const int cy = cell / NCX, cx = cell - cy * NCX;
-        const int uy = GY0 - 1 + cy, ux = GX0 - 1 + cx;     // unclamped source cell
-        if (c0 < CPI && uy <= P.h && ux <= P.w) {
-            int o[4];
-            int no = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int gy_ = cy - (k >> 1), gx_ = cx - (k & 1);
-                if (gy_ >= 0 && gy_ < 2 && gx_ >= 0 && gx_ < WGX) o[no++] = (gy_ * WGX + gx_) * 4 + k;
-            }
-#pragma unroll
-            for (int k = 1; k < 4; ++k)
-                if (k >= no) o[k] = o[0];
-            float* dst = gb + (size_t)clampi2(uy, 0, P.h - 1) * P.w + clampi2(ux, 0, P.w - 1) + (size_t)c0 * plane;
-            const float* sc = st + c0 * CS;
-            for (int c = c0; c < C; c += CPI) {
-                float v = sc[o[0]];
-                if (no > 1) v += sc[o[1]];
-                if (no > 2) v += sc[o[2]] + sc[o[3]];
-                atomicAdd(dst, v);
-                sc += CPI * CS;
-                dst += (size_t)CPI * plane;
-            }
-        }
-    }
-    loss = warp_sum(loss);
-    if (lane == 0 && loss != 0.f) atomicAdd(P.loss_sum, (double)loss);
+    k2_strip_warp<S, SPLIT, CS, false>(P, st, st, true, n, GY0, GX0, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

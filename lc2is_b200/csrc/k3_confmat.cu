@@ -14,6 +14,7 @@
 //                pixel block that shares one set of bilinear (2x2) / bicubic (4x4) taps.
 //   k3_low_gen - any output size (compute_gt_mIOU's per-image original sizes): 1 pixel/thread.
 #include "common.cuh"
+#include "k2_strip.cuh"
 #include <type_traits>
 
 namespace lc2is {
@@ -481,6 +482,172 @@ __device__ __forceinline__ float k3_strip_value(const float4 q, float ly, float 
     return fmaf((float)j, rl * rsx, fmaf(rl, lx0, L));
 }
 
+// One row (S pixels) of one group per lane.  st4 = the group's tap quad of class 0, CS4 = float4 stride between
+// classes; (ly, lx0, rsx): lambda_y of the row and lambda_x(j) = lx0 + j * rsx.  FUSED: called by the argmax warps of the
+// fused K2+K3 kernel - the staged taps are index-CLAMPED there (K2's convention; identical for finite logits), so
+// non-finite taps are handled by the exact per-pixel path on the global low-resolution map with ATen's taps.
+// SYNC: 0 = the caller has synchronised, 1 = wait for this lane's cp.async + __syncwarp, 2 = ... + __syncthreads.
+template <int S, bool PACKED, int CS4, bool FUSED, int SYNC>
+__device__ __forceinline__ void k3_strip_rows(const K3SParams& P, const float4* st4, int n, int ky, int kx, int i,
+                                              bool group_in, float ly, float lx0, float rsx) {
+    constexpr int CH = 8;                                   // classes per chunk
+    const int C = P.C;
+    const int y = S * ky + S / 2 + i, x0 = S * kx + S / 2;
+    const bool row_in = group_in && y >= 0 && y < P.H;
+    // the row's labels (issued before the taps are waited for)
+    unsigned lw16[PACKED ? S / 2 : 1];
+    long long lab64[PACKED ? 1 : S];
+    if constexpr (PACKED) {
+        using V = typename std::conditional<S == 16, uint4, uint2>::type;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int x = x0 + hh * (S / 2);
+            const bool in = row_in && x >= 0 && x < P.W;
+            V t = {};
+            if (in) t = __ldg(reinterpret_cast<const V*>((const unsigned short*)P.labels + ((size_t)n * P.H + y) * P.W + x));
+            const unsigned* wv = reinterpret_cast<const unsigned*>(&t);
+#pragma unroll
+            for (int k = 0; k < S / 4; ++k) lw16[hh * (S / 4) + k] = in ? wv[k] : 0xffffffffu;
+        }
+    } else {
+        const int ryl = P.H / P.lh, rxl = P.W / P.lw;
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const int x = x0 + j;
+            lab64[j] = (row_in && x >= 0 && x < P.W)
+                           ? __ldg((const long long*)P.labels + ((size_t)n * P.lh + y / ryl) * P.lw + x / rxl) : -1;
+        }
+    }
+    if constexpr (SYNC >= 1) asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+    if constexpr (SYNC == 1) __syncwarp();
+    if constexpr (SYNC == 2) __syncthreads();
+
+    // ---- non-finite taps? ------------------------------------------------------------------------------------
+    bool exotic = false;
+    for (int c = i; c < C; c += S) {
+        const float4 q = st4[c * CS4];
+        exotic |= !(fabsf(q.x) < INFINITY) | !(fabsf(q.y) < INFINITY) | !(fabsf(q.z) < INFINITY) | !(fabsf(q.w) < INFINITY);
+    }
+    if constexpr (FUSED) {
+        // clamped staging hides ATen's second tap of the top / left border groups (row / column 1, weight 0):
+        // look at it on the global map (0 * inf = NaN poisons those pixels in the reference)
+        if (group_in && (ky < 0 || kx < 0)) {
+            const int ya = ky < 0 ? 0 : ky, xa = kx < 0 ? 0 : kx;
+            const int yb = min(ya + 1, P.h - 1), xb = min(xa + 1, P.w - 1);
+            const float* base = P.low + (size_t)n * C * P.h * P.w;
+            for (int c = i; c < C; c += S) {
+                const float* pc = base + (size_t)c * P.h * P.w;
+                const float t1 = __ldg(pc + ya * P.w + xb), t2 = __ldg(pc + yb * P.w + xa), t3 = __ldg(pc + yb * P.w + xb);
+                exotic |= !(fabsf(t1) < INFINITY) | !(fabsf(t2) < INFINITY) | !(fabsf(t3) < INFINITY);
+            }
+        }
+    }
+    exotic = __any_sync(0xffffffffu, exotic);
+
+    int bidx[S];
+    if (!exotic) {
+        // ---- phase 1: running maximum per pixel, chunk of the first maximum -------------------------------
+        float best[S];
+        int bch[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) { best[j] = -INFINITY; bch[j] = 0; }
+        float2 J2[S / 2];
+#pragma unroll
+        for (int k = 0; k < S / 2; ++k) J2[k] = make_float2((float)(2 * k), (float)(2 * k + 1));
+        const int nch = (C + CH - 1) / CH;
+        const float4* qp = st4;
+#pragma unroll 1
+        for (int k = 0; k < nch; ++k) {
+            float cm[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) cm[j] = -INFINITY;
+#pragma unroll
+            for (int cc = 0; cc < CH; cc += 2) {
+                const float4 qa = qp[0], qb = qp[CS4];
+                qp += 2 * CS4;
+                const float La = fmaf(ly, qa.z - qa.x, qa.x), Ra = fmaf(ly, qa.w - qa.y, qa.y);
+                const float Lb = fmaf(ly, qb.z - qb.x, qb.x), Rb = fmaf(ly, qb.w - qb.y, qb.y);
+                const float rla = Ra - La, rlb = Rb - Lb;
+                const float2 va0 = make_float2(fmaf(rla, lx0, La), fmaf(rla, lx0, La)), da = make_float2(rla * rsx, rla * rsx);
+                const float2 vb0 = make_float2(fmaf(rlb, lx0, Lb), fmaf(rlb, lx0, Lb)), db = make_float2(rlb * rsx, rlb * rsx);
+#pragma unroll
+                for (int jj = 0; jj < S / 2; ++jj) {
+                    const float2 va = ffma2f(J2[jj], da, va0), vb = ffma2f(J2[jj], db, vb0);
+                    cm[2 * jj] = fmaxf(fmaxf(va.x, vb.x), cm[2 * jj]);
+                    cm[2 * jj + 1] = fmaxf(fmaxf(va.y, vb.y), cm[2 * jj + 1]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < S; ++j)
+                if (cm[j] > best[j]) { best[j] = cm[j]; bch[j] = k; }
+        }
+        // ---- phase 2: first class of the winning chunk that reaches the maximum ---------------------------
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+            const int c0 = bch[j] * CH;
+            float bv = -INFINITY;
+            int bi = c0;
+#pragma unroll
+            for (int cc = 0; cc < CH; ++cc) {
+                const float v = k3_strip_value(st4[(c0 + cc) * CS4], ly, lx0, rsx, j);
+                if (v > bv) { bv = v; bi = c0 + cc; }
+            }
+            bidx[j] = bi;
+        }
+    } else {
+        // exact per-pixel path with the NaN / +inf rule (rare)
+#pragma unroll 1
+        for (int j = 0; j < S; ++j) {
+            ArgmaxState a;
+            am_init(a);
+            if constexpr (FUSED) {
+                // ATen's taps on the global map: index0 = max(k,0), index1 = min(index0+1, size-1), lambda = 0 at k = -1
+                const int ya = ky < 0 ? 0 : ky, xa = kx < 0 ? 0 : kx;
+                const int yb = min(ya + 1, P.h - 1), xb = min(xa + 1, P.w - 1);
+                const float tyy = ky < 0 ? 0.f : ly, tx = kx < 0 ? 0.f : lx0 + (float)j * rsx;
+                const float* base = P.low + (size_t)n * C * P.h * P.w;
+                for (int c = 0; c < C && group_in; ++c) {
+                    const float* pc = base + (size_t)c * P.h * P.w;
+                    const float qx = __ldg(pc + ya * P.w + xa), qy = __ldg(pc + ya * P.w + xb);
+                    const float qz = __ldg(pc + yb * P.w + xa), qw = __ldg(pc + yb * P.w + xb);
+                    const float r0 = fmaf(qy, tx, qx * (1.f - tx)), r1 = fmaf(qw, tx, qz * (1.f - tx));
+                    am_update(a, fmaf(r1, tyy, r0 * (1.f - tyy)), c);
+                }
+            } else {
+                const float tx = lx0 + (float)j * rsx;
+                for (int c = 0; c < C; ++c) {
+                    const float4 q = st4[c * CS4];
+                    const float r0 = fmaf(q.y, tx, q.x * (1.f - tx)), r1 = fmaf(q.w, tx, q.z * (1.f - tx));
+                    am_update(a, fmaf(r1, ly, r0 * (1.f - ly)), c);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < S; ++jj)
+                if (jj == j) bidx[jj] = am_result(a);
+        }
+    }
+
+    // ---- labels, predictions, counts ---------------------------------------------------------------------------
+    // one warp-aggregated (match.any) 64-bit reduction per distinct (target, prediction) pair of a pixel column.
+    // (Per-thread run-length reductions without the warp aggregation measured faster under ncu's isolated,
+    // cache-flushed launch but 20 us slower inside the step.)
+    unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        const int x = x0 + j;
+        bool valid = row_in && x >= 0 && x < P.W;
+        int t = 0;
+        const int pr = bidx[j];
+        if (valid) {
+            if (P.pred_out) P.pred_out[((size_t)n * P.H + y) * P.W + x] = pr;
+            if constexpr (PACKED) t = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0x7fffu);   // bit 15: ignore flag of the CE
+            else { const long long tl = lab64[j]; t = (tl >= 0 && tl < C) ? (int)tl : C; }
+            valid = t < C;
+        }
+        hist_add(nullptr, P.confmat, pimg, C, valid, t, pr);
+    }
+}
+
 template <int S, bool PACKED>
 __global__ void __launch_bounds__(128)
 k3_strip_kernel(const K3SParams P) {
@@ -527,132 +694,82 @@ k3_strip_kernel(const K3SParams P) {
     const int n = group_in ? (int)(gid / gpi) : 0;
     const int rem = group_in ? (int)(gid - (long long)n * gpi) : 0;
     const int ky = rem / (P.w + 1) - 1, kx = rem % (P.w + 1) - 1;
-    const int y = S * ky + S / 2 + i, x0 = S * kx + S / 2;
-    const bool row_in = group_in && y >= 0 && y < P.H;
     const float ly = ky < 0 ? 0.f : ((float)i + 0.5f) * RS;
     const float lx0 = kx < 0 ? 0.f : LX0, rsx = kx < 0 ? 0.f : RS;      // lambda_x(j) = lx0 + j * rsx
-    // the row's labels (issued before the taps are waited for)
-    unsigned lw16[PACKED ? S / 2 : 1];
-    long long lab64[PACKED ? 1 : S];
-    if constexpr (PACKED) {
-        using V = typename std::conditional<S == 16, uint4, uint2>::type;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const int x = x0 + hh * (S / 2);
-            const bool in = row_in && x >= 0 && x < P.W;
-            V t = {};
-            if (in) t = __ldg(reinterpret_cast<const V*>((const unsigned short*)P.labels + ((size_t)n * P.H + y) * P.W + x));
-            const unsigned* wv = reinterpret_cast<const unsigned*>(&t);
-#pragma unroll
-            for (int k = 0; k < S / 4; ++k) lw16[hh * (S / 4) + k] = in ? wv[k] : 0xffffffffu;
+    k3_strip_rows<S, PACKED, GPW, false, 1>(P, reinterpret_cast<const float4*>(st) + gl, n, ky, kx, i, group_in, ly, lx0, rsx);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k23_fused: K2 (split form) and K3 of the x16 geometry in ONE kernel, warp-specialised.
+// K2 is bound by the FP32 (FMA) pipe, K3 by the ALU pipe / issue slots, and the phases of equal warps coincide
+// (every warp runs the same program on the same amount of work), so neither kernel overlaps its own idle phases;
+// launched on two streams the block scheduler does not co-schedule them either.  Here a CTA of 8 warps stages the
+// taps of 16 groups ONCE; warps 4-7 ("CE warps") run k2_strip_warp on one 2x2 tile each and write their tap
+// gradients to a second shared tile (not in place: the other warps are still reading the taps), warps 0-3 ("argmax
+// warps") run k3_strip_rows over the same 16 groups in two rounds of 8 groups (one row per lane).  Two CTAs per SM:
+// 8 CE + 8 argmax warps share each SM's schedulers.  (The CE warps are the long pole; the warp arbiter favours the
+// higher warp ids.)
+template <int S>
+__global__ void __launch_bounds__(256, 2)
+k23_fused_kernel(const K2SParams P2, const K3SParams P3) {
+    static_assert(S == 16, "fused kernel: x16 geometry");
+    constexpr int NG = 16, CSF = NG * 4, CH = 8;            // groups per CTA, floats per class, K3's class chunk
+    constexpr float RS = 1.f / S, LX0 = 0.5f / S;
+    extern __shared__ float smem[];
+    const int C = P2.C;
+    float* taps = smem;                                     // [C + CH][16 groups][4 taps]
+    float* outq = smem + (size_t)(C + CH) * CSF;            // [C][16 groups][4 tap gradients]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = P2.nty * P2.ntx;
+    const long long ntiles = (long long)P2.B * tiles_per_img;
+    const size_t plane = (size_t)P2.h * P2.w;
+    // warp tile w (0..3) of this CTA -> (image, tile row, tile column)
+    auto tile_of = [&](int w, int& n, int& GY0, int& GX0) -> bool {
+        const long long wt = (long long)blockIdx.x * 4 + w;
+        if (wt >= ntiles) { n = 0; GY0 = 0; GX0 = 0; return false; }
+        n = (int)(wt / tiles_per_img);
+        const int trem = (int)(wt - (long long)n * tiles_per_img);
+        const int tyi = trem / P2.ntx;
+        GY0 = tyi * 2; GX0 = (trem - tyi * P2.ntx) * 2;
+        return true;
+    };
+    // ---- stage (whole CTA): thread -> fixed (group, tap), 4 classes per sweep; index-clamped taps --------------
+    {
+        const int r = threadIdx.x % CSF, gq = r >> 2, tap = r & 3;
+        int n, GY0, GX0;
+        const bool act = tile_of(gq >> 2, n, GY0, GX0);
+        const int ky = GY0 + ((gq & 3) >> 1) - 1, kx = GX0 + (gq & 1) - 1;
+        const bool ok = act && ky < P2.h && kx < P2.w;
+        const int yy = clampi2(ky + (tap >> 1), 0, P2.h - 1), xx = clampi2(kx + (tap & 1), 0, P2.w - 1);
+        const float* src = P2.low + (size_t)n * C * plane + (size_t)yy * P2.w + xx;
+        float* dst = taps + r;
+        for (int c = threadIdx.x / CSF; c < C; c += 256 / CSF) {
+            if (ok) cp_async4(dst + c * CSF, src + (size_t)c * plane);
+            else dst[c * CSF] = 0.f;
         }
+        for (int c = C + threadIdx.x / CSF; c < C + CH; c += 256 / CSF) dst[c * CSF] = -3.0e38f;   // never wins
+    }
+    if (warp >= 4) {
+        const int cw = warp - 4;
+        int n, GY0, GX0;
+        const bool act = tile_of(cw, n, GY0, GX0);
+        k2_strip_warp<S, true, CSF, true>(P2, taps + cw * 16, outq + cw * 16, act, n, GY0, GX0, lane);
     } else {
-        const int ryl = P.H / P.lh, rxl = P.W / P.lw;
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-            const int x = x0 + j;
-            lab64[j] = (row_in && x >= 0 && x < P.W)
-                           ? __ldg((const long long*)P.labels + ((size_t)n * P.lh + y / ryl) * P.lw + x / rxl) : -1;
-        }
-    }
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    const float4* st4 = reinterpret_cast<const float4*>(st) + gl;      // + c * GPW
-
-    // ---- non-finite taps? ------------------------------------------------------------------------------------
-    bool exotic = false;
-    for (int c = i; c < C; c += S) {
-        const float4 q = st4[c * GPW];
-        exotic |= !(fabsf(q.x) < INFINITY) | !(fabsf(q.y) < INFINITY) | !(fabsf(q.z) < INFINITY) | !(fabsf(q.w) < INFINITY);
-    }
-    exotic = __any_sync(0xffffffffu, exotic);
-
-    int bidx[S];
-    if (!exotic) {
-        // ---- phase 1: running maximum per pixel, chunk of the first maximum -------------------------------
-        float best[S];
-        int bch[S];
-#pragma unroll
-        for (int j = 0; j < S; ++j) { best[j] = -INFINITY; bch[j] = 0; }
-        float2 J2[S / 2];
-#pragma unroll
-        for (int k = 0; k < S / 2; ++k) J2[k] = make_float2((float)(2 * k), (float)(2 * k + 1));
-        const int nch = (C + CH - 1) / CH;
-        const float4* qp = st4;
+        const int aw = warp;
 #pragma unroll 1
-        for (int k = 0; k < nch; ++k) {
-            float cm[S];
-#pragma unroll
-            for (int j = 0; j < S; ++j) cm[j] = -INFINITY;
-#pragma unroll
-            for (int cc = 0; cc < CH; cc += 2) {
-                const float4 qa = qp[0], qb = qp[GPW];
-                qp += 2 * GPW;
-                const float La = fmaf(ly, qa.z - qa.x, qa.x), Ra = fmaf(ly, qa.w - qa.y, qa.y);
-                const float Lb = fmaf(ly, qb.z - qb.x, qb.x), Rb = fmaf(ly, qb.w - qb.y, qb.y);
-                const float rla = Ra - La, rlb = Rb - Lb;
-                const float2 va0 = make_float2(fmaf(rla, lx0, La), fmaf(rla, lx0, La)), da = make_float2(rla * rsx, rla * rsx);
-                const float2 vb0 = make_float2(fmaf(rlb, lx0, Lb), fmaf(rlb, lx0, Lb)), db = make_float2(rlb * rsx, rlb * rsx);
-#pragma unroll
-                for (int jj = 0; jj < S / 2; ++jj) {
-                    const float2 va = ffma2f(J2[jj], da, va0), vb = ffma2f(J2[jj], db, vb0);
-                    cm[2 * jj] = fmaxf(fmaxf(va.x, vb.x), cm[2 * jj]);
-                    cm[2 * jj + 1] = fmaxf(fmaxf(va.y, vb.y), cm[2 * jj + 1]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < S; ++j)
-                if (cm[j] > best[j]) { best[j] = cm[j]; bch[j] = k; }
+        for (int round = 0; round < 2; ++round) {
+            const int g = round * 8 + aw * 2 + lane / S, i = lane % S;     // group 0..15 of the CTA, row of the group
+            int n, GY0, GX0;
+            const bool act = tile_of(g >> 2, n, GY0, GX0);
+            const int ky = GY0 + ((g & 3) >> 1) - 1, kx = GX0 + (g & 1) - 1;
+            const bool group_in = act && ky < P2.h && kx < P2.w;
+            const float ly = ((float)i + 0.5f) * RS;
+            const float4* st4 = reinterpret_cast<const float4*>(taps) + g;
+            if (round == 0)
+                k3_strip_rows<S, true, CSF / 4, true, 2>(P3, st4, n, ky, kx, i, group_in, ly, LX0, RS);
+            else
+                k3_strip_rows<S, true, CSF / 4, true, 0>(P3, st4, n, ky, kx, i, group_in, ly, LX0, RS);
         }
-        // ---- phase 2: first class of the winning chunk that reaches the maximum ---------------------------
-#pragma unroll
-        for (int j = 0; j < S; ++j) {
-            const int c0 = bch[j] * CH;
-            float bv = -INFINITY;
-            int bi = c0;
-#pragma unroll
-            for (int cc = 0; cc < CH; ++cc) {
-                const float v = k3_strip_value(st4[(c0 + cc) * GPW], ly, lx0, rsx, j);
-                if (v > bv) { bv = v; bi = c0 + cc; }
-            }
-            bidx[j] = bi;
-        }
-    } else {
-        // exact per-pixel path with the NaN / +inf rule (rare)
-#pragma unroll 1
-        for (int j = 0; j < S; ++j) {
-            ArgmaxState a;
-            am_init(a);
-            const float tx = lx0 + (float)j * rsx;
-            for (int c = 0; c < C; ++c) {
-                const float4 q = st4[c * GPW];
-                const float r0 = fmaf(q.y, tx, q.x * (1.f - tx)), r1 = fmaf(q.w, tx, q.z * (1.f - tx));
-                am_update(a, fmaf(r1, ly, r0 * (1.f - ly)), c);
-            }
-#pragma unroll
-            for (int jj = 0; jj < S; ++jj)
-                if (jj == j) bidx[jj] = am_result(a);
-        }
-    }
-
-    // ---- labels, predictions, counts ---------------------------------------------------------------------------
-    // one warp-aggregated (match.any) 64-bit reduction per distinct (target, prediction) pair of a pixel column.
-    // (Per-thread run-length reductions without the warp aggregation measured faster under ncu's isolated,
-    // cache-flushed launch but 20 us slower inside the step.)
-    unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
-#pragma unroll
-    for (int j = 0; j < S; ++j) {
-        const int x = x0 + j;
-        bool valid = row_in && x >= 0 && x < P.W;
-        int t = 0;
-        const int pr = bidx[j];
-        if (valid) {
-            if (P.pred_out) P.pred_out[((size_t)n * P.H + y) * P.W + x] = pr;
-            if constexpr (PACKED) t = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0x7fffu);   // bit 15: ignore flag of the CE
-            else { const long long tl = lab64[j]; t = (tl >= 0 && tl < C) ? (int)tl : C; }
-            valid = t < C;
-        }
-        hist_add(nullptr, P.confmat, pimg, C, valid, t, pr);
     }
 }
 
@@ -787,6 +904,45 @@ static int launch_k3_strip(const float* d_low, int N, int C, int h, int w, int H
 }  // namespace lc2is
 
 using namespace lc2is;
+
+// K2 (split form) + K3 fused for the x16 geometry: d_loss_sum += sum(lse - target logit); d_grad_low ACCUMULATES the
+// un-scaled softmax term (or NULL); d_confmat / d_per_image ACCUMULATE; d_pred optional.
+extern "C" int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W) {
+    int s = 0;
+    if (!fast_scale(h, w, H, W, &s) || s != 16) return 0;
+    const size_t smem = ((size_t)(C + 8) + C) * 64 * sizeof(float);
+    return smem <= 110 * 1024 ? 1 : 0;                      // two CTAs per SM
+}
+
+extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* d_labels_packed,
+                                            int B, int C, int h, int w, int H, int W,
+                                            double* d_loss_sum, float* d_grad_low,
+                                            int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                                            lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (B < 0 || C <= 0 || h <= 0 || w <= 0 || H <= 0 || W <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (B == 0) return 0;
+    if (!d_low || !d_labels_packed || !d_loss_sum || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if ((uintptr_t)d_labels_packed % 16) return fail(LC2IS_ERR_ARG, "packed labels must be 16-byte aligned%s");
+    if (!lc2is_ce_argmax_fused_supported(C, h, w, H, W))
+        return fail(LC2IS_ERR_UNSUPPORTED, "fused K2+K3 needs scale 16 and a class count that fits two CTAs per SM%s");
+    K2SParams P2;
+    P2.low = d_low; P2.labels = nullptr; P2.labels16 = d_labels_packed; P2.grad_low = d_grad_low;
+    P2.loss_sum = d_loss_sum; P2.grad_scale = nullptr; P2.ignore_index = 0;
+    P2.B = B; P2.C = C; P2.h = h; P2.w = w; P2.H = H; P2.W = W;
+    P2.nty = (h + 1 + 1) / 2; P2.ntx = (w + 1 + 1) / 2;
+    K3SParams P3;
+    P3.low = d_low; P3.labels = d_labels_packed; P3.confmat = (unsigned long long*)d_confmat;
+    P3.per_image = (unsigned long long*)d_per_image; P3.pred_out = (long long*)d_pred;
+    P3.N = B; P3.C = C; P3.h = h; P3.w = w; P3.H = H; P3.W = W; P3.lh = H; P3.lw = W;
+    const size_t smem = ((size_t)(C + 8) + C) * 64 * sizeof(float);
+    const long long tiles = (long long)B * P2.nty * P2.ntx;
+    const unsigned grid = (unsigned)((tiles + 3) / 4);
+    if (int e = set_smem(k23_fused_kernel<16>, smem)) return e;
+    k23_fused_kernel<16><<<grid, 256, smem, (cudaStream_t)stream>>>(P2, P3);
+    LC2IS_CHECK_LAUNCH("k23_fused_kernel");
+    return 0;
+}
 
 extern "C" int lc2is_argmax_confmat_lowres_packed(const float* d_low, int N, int C, int h, int w, int H, int W,
                                                   const uint16_t* d_labels_packed,

@@ -209,3 +209,20 @@ def argmax_confmat_packed(low: Tensor, labels_packed: Tensor, size: Tuple[int, i
     check(lib.lc2is_argmax_confmat_lowres_packed(ptr(low), N, C, h, w, H, W, ptr(labels_packed), ptr(confmat), ptr(pi),
                                                  ptr(pred), stream_ptr()), "lc2is_argmax_confmat_lowres_packed")
     return confmat, pi, pred
+
+
+def ce_argmax_fused(low: Tensor, labels_packed: Tensor, size: Tuple[int, int], loss_sum: Tensor, grad: Optional[Tensor],
+                    confmat: Optional[Tensor] = None, per_image: bool = False, want_pred: bool = False):
+    """Fused K2 (split form) + K3 for the x16 geometry: accumulates into loss_sum / grad (un-scaled softmax term) /
+    confmat.  -> (confmat, per_image | None, pred | None)."""
+    low = _req(low, torch.float32, "low")
+    N, C, h, w = low.shape
+    H, W = int(size[0]), int(size[1])
+    dev = low.device
+    if confmat is None:
+        confmat = torch.zeros(C, C, dtype=torch.int64, device=dev)
+    pi = torch.zeros(N, 3, C, dtype=torch.int64, device=dev) if per_image else None
+    pred = torch.empty(N, H, W, dtype=torch.int64, device=dev) if want_pred else None
+    check(lib.lc2is_ce_argmax_fused_packed(ptr(low), ptr(labels_packed), N, C, h, w, H, W, ptr(loss_sum), ptr(grad),
+                                           ptr(confmat), ptr(pi), ptr(pred), stream_ptr()), "lc2is_ce_argmax_fused_packed")
+    return confmat, pi, pred

@@ -48,6 +48,8 @@ class HeadStep:
         self.logits = e(B, C, h, w)
         self.split = bool(lib.lc2is_ce_split_supported(h, w, H, W))     # label prepass + packed-label K2 / K3
         self.labels_packed = e(B, H, W, dt=torch.uint16) if self.split else None
+        # x16: K2 and K3 run as ONE warp-specialised kernel (complementary pipes share the SMs)
+        self.fused = bool(self.split and lib.lc2is_ce_argmax_fused_supported(C, h, w, H, W))
         self.grad_v = e(B, self.hw, D, dt=torch.bfloat16)
         # Everything a step accumulates into lives in ONE flat buffer that is zeroed with a single fill:
         #   [ grad bucket: grad_t (C*D) | loss_sum as fp32 (1) | pad ] [ grad_low (B*C*h*w) ]
@@ -130,7 +132,11 @@ class HeadStep:
         self._mark("K2 upsample+CE")
         if self.k2_events is not None:
             self.k2_events[0].record()
-        if self.split:
+        if self.fused:
+            check(lib.lc2is_ce_argmax_fused_packed(ptr(self.logits), ptr(self.labels_packed), B, C, h, w, H, W,
+                                                   ptr(self.loss_sum), glow, ptr(self.confmat), None, None, st),
+                  "ce_argmax_fused_packed")
+        elif self.split:
             check(lib.lc2is_upsample_ce_packed(ptr(self.logits), ptr(self.labels_packed), B, C, h, w, H, W,
                                                ptr(self.loss_sum), glow, st), "upsample_ce_packed")
         else:
@@ -153,7 +159,9 @@ class HeadStep:
             self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
             w_b = dp.allreduce_sum_async(self.bucket.flat)       # ... and hides behind K3
         self._mark("K3 argmax+confmat")
-        if self.split:
+        if self.fused:
+            pass                                                  # done inside the fused kernel
+        elif self.split:
             check(lib.lc2is_argmax_confmat_lowres_packed(ptr(self.logits), B, C, h, w, H, W, ptr(self.labels_packed),
                                                          ptr(self.confmat), None, None, st), "argmax_confmat_packed")
         else:

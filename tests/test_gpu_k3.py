@@ -191,3 +191,50 @@ def test_strip_kernel_non_finite_taps_and_ties():
     cm, _, pred = ops.argmax_confmat(low.to(DEV), labels.to(DEV), want_pred=True, size=(H, H), mode="bilinear")
     assert torch.equal(pred.cpu(), pred_ref)
     assert torch.equal(cm.cpu(), O.confusion_matrix(pred_ref, labels, C))
+
+
+@pytest.mark.parametrize("N,C,h,ign,frac", [(3, 151, 6, 0, 0.1), (2, 150, 32, 0, 0.1), (1, 19, 3, 5, 0.3), (5, 37, 5, 0, 0.0)])
+def test_fused_ce_argmax_kernel_matches_separate_kernels_and_oracle(N, C, h, ign, frac):
+    """k23_fused_kernel (x16): the warp-specialised K2+K3 kernel gives the loss / gradient of the split K2 path and
+    the bit-exact confusion matrix / per-image counts / masks of K3 (dyadic logits)."""
+    s = 16
+    H = s * h
+    low = synthetic.make_dyadic_logits(N, C, h, h)
+    labels = synthetic.make_labels(N, H, H, C, block=8, ignore_frac=frac, ignore_index=ign)
+    labels[0, :2] = C + 3
+    dl, dlab = low.to(DEV), labels.to(DEV)
+    loss_sum, n_valid, grad, packed = ops.upsample_ce_split(dl, dlab, ign)           # separate kernels
+    assert ops._lib.lib.lc2is_ce_argmax_fused_supported(C, h, h, H, H)
+    ls2 = torch.zeros(1, dtype=torch.float64, device=DEV)
+    g2 = torch.zeros_like(dl)
+    _lib_check = ops.check
+    _lib_check(ops.lib.lc2is_ce_labels_prepass(dlab.data_ptr(), N, C, h, h, H, H, ign, packed.data_ptr(), None,
+                                               g2.data_ptr(), torch.cuda.current_stream().cuda_stream), "prepass")
+    cm, pi, pred = ops.ce_argmax_fused(dl, packed, (H, H), ls2, g2, per_image=True, want_pred=True)
+    assert abs(float(ls2) - float(loss_sum)) <= 1e-6 * abs(float(loss_sum))
+    assert float((g2 - grad).abs().max()) <= 1e-5 * float(grad.abs().max())
+    up = F.interpolate(low, mode="bilinear", scale_factor=s)
+    pred_ref = O.argmax_reference(up)
+    assert torch.equal(pred.cpu(), pred_ref)
+    assert torch.equal(cm.cpu(), O.confusion_matrix(pred_ref, labels, C))
+    assert torch.equal(pi.cpu(), _per_image_ref(pred_ref, labels, C))
+    ref_loss, ref_grad, nv = O.auxiliary_loss_and_grad(low, torch.where((labels >= 0) & (labels < C), labels, torch.full_like(labels, ign)), ign)
+    assert abs(float(ls2) / nv - float(ref_loss)) <= 2e-6 * abs(float(ref_loss))
+    assert float((g2.cpu() / nv - ref_grad).abs().max()) <= 1e-5 * float(ref_grad.abs().max()) + 1e-9
+
+
+def test_fused_kernel_non_finite_taps():
+    N, C, h, s = 1, 21, 4, 16
+    H = s * h
+    low = torch.zeros(N, C, h, h)
+    low[0, 3] = 0.5; low[0, 12] = 0.5; low[0, 20] = 0.5
+    low[0, 7, 1, 1] = float("inf")
+    low[0, 9, 2, 3] = float("nan")
+    labels = torch.randint(0, C, (N, H, H), generator=torch.Generator().manual_seed(3))
+    up = F.interpolate(low, mode="bilinear", scale_factor=s)
+    pred_ref = O.argmax_reference(up)
+    _, _, _, packed = ops.upsample_ce_split(low.to(DEV), labels.to(DEV), 0, want_grad=False)
+    ls = torch.zeros(1, dtype=torch.float64, device=DEV)
+    cm, _, pred = ops.ce_argmax_fused(low.to(DEV), packed, (H, H), ls, None, want_pred=True)
+    assert torch.equal(pred.cpu(), pred_ref)
+    assert torch.equal(cm.cpu(), O.confusion_matrix(pred_ref, labels, C))
