@@ -339,29 +339,40 @@ def run_b200(a):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    split = step.split
-    # algorithmic bytes of the K2 launch: read low + accumulate grad_low (fp32) + the label map it reads
-    # (packed uint16 from the label prepass on the split path, int64 otherwise) + the loss scalar
-    k2_bytes = 2 * B * C * h * w * 4 + B * H * W * (2 if split else 8) + 8
-    k2_name = "k2_strip_kernel<16, true>" if split and H // h == 16 else (
-        "k2_strip_kernel<8, true>" if split else "k2_fast_kernel / k2_generic_kernel")
+    split, fused = step.split, getattr(step, "fused", False)
+    # Dominant launch: on the x16 geometry K2 (fused upsample + softmax-CE fwd/bwd) and K3 (argmax + confusion matrix)
+    # are ONE warp-specialised kernel.  Algorithmic bytes of that launch: read low + accumulate grad_low (fp32) + the
+    # packed uint16 label map (read by the CE warps and by the argmax warps) + the loss scalar.
+    if fused:
+        k2_bytes = 2 * B * C * h * w * 4 + 2 * B * H * W * 2 + 8
+        k2_name = "k23_fused_kernel<16>"
+        k2_desc = "lc2is_ce_argmax_fused_packed: bilinear upsample + softmax-CE fwd/bwd + argmax + confusion matrix"
+    else:
+        k2_bytes = 2 * B * C * h * w * 4 + B * H * W * (2 if split else 8) + 8
+        k2_name = ("k2_strip_kernel<16, true>" if H // h == 16 else "k2_strip_kernel<8, true>") if split else \
+            "k2_fast_kernel / k2_generic_kernel"
+        k2_desc = "lc2is_upsample_ce_packed: fused bilinear upsample + softmax-CE fwd+bwd"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath) and a.geometry == "A" and B == 16 and C == 150:
         traffic = json.load(open(tpath)).get(k2_name)                 # from one `ncu --set full` capture
     achieved = k2_bytes / (k2_ms * 1e-3) / 1e9
-    roofline = {"kernel": f"{k2_name} (lc2is_upsample_ce_packed: fused bilinear upsample + softmax-CE fwd+bwd)",
+    roofline = {"kernel": f"{k2_name} ({k2_desc})",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": k2_bytes, "kernel_us": k2_ms * 1e3,
-                "note": "K2 is FP32-pipe bound (packed FFMA2 at 2 warp-inst/clk/SM), not HBM-bound: see DESIGN.md; "
-                        f"{B * C * H * W / (k2_ms * 1e-3) / 1e12:.3f} T softmax-elements/s"}
-    # the bound that does bind K2: 4 packed fp32x2 instructions per pixel pair and class (pass A: add + mul,
-    # pass B: two fma) at the measured packed issue rate of 2.0 warp-inst/clk/SM (tools/micro/k2loops.cu)
+                "note": "instruction-bound, not HBM-bound (the upsampled [B,C,H,W] tensor never exists): see "
+                        f"`compute` and DESIGN.md; {B * C * H * W / (k2_ms * 1e-3) / 1e12:.3f} T upsampled elements/s"}
+    # The bounds that do bind.  CE part: 4 packed fp32x2 instructions per pixel pair and class (pass A: add + mul,
+    # pass B: two fma) at the measured packed issue rate of 2.0 warp-inst/clk/SM (tools/micro/k2loops.cu).
+    # Argmax part (fused kernel only): one FFMA2 and one FMNMX3 per pixel pair and class at 4 issue slots/clk/SM.
     sm_hz = (clocks.get("sm_mhz") or 1965) * 1e6
-    alg_inst = B * C * H * W / 2 * 4 / 32
-    alg_us = alg_inst / (2.0 * 148 * sm_hz) * 1e6
-    roofline["fp32_pipe"] = {"algorithmic_packed_warp_inst": alg_inst, "peak_warp_inst_per_clk_per_sm": 2.0,
-                             "algorithmic_us": alg_us, "frac": alg_us / (k2_ms * 1e3)}
+    ce_inst = B * C * H * W / 2 * 4 / 32
+    ce_us = ce_inst / (2.0 * 148 * sm_hz) * 1e6
+    am_inst = B * C * H * W / 2 * 2 / 32 if fused else 0.0
+    am_us = am_inst / (4.0 * 148 * sm_hz) * 1e6
+    roofline["compute"] = {"ce_packed_fp32_warp_inst": ce_inst, "ce_us_at_2_per_clk_per_sm": ce_us,
+                           "argmax_warp_inst": am_inst, "argmax_us_at_4_per_clk_per_sm": am_us,
+                           "frac": (ce_us + am_us) / (k2_ms * 1e3)}
 
     cpu_baseline = None
     if not a.no_cpu_baseline and world == 1:
