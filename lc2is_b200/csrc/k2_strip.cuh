@@ -151,7 +151,7 @@ __device__ __noinline__ float k2_strip_slow(const float* st, int cs, int gl, uns
 // CSF = floats per class of the tile the warp's quads live in (16 for the stand-alone kernel's per-warp tile, 64 for
 // the 16-group CTA tile of the fused K2+K3 kernel); st = the warp's first tap quad of class 0, so = the same position
 // in the tile that receives the tap gradients (so == st: in place).  CTA_SYNC: the taps were staged by the whole CTA.
-template <int S, bool SPLIT, int CSF, bool CTA_SYNC>
+template <int S, bool SPLIT, int CSF, bool CTA_SYNC, int UNR = 2>
 __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, float* so, bool active, int n, int GY0,
                                               int GX0, int lane) {
     constexpr int TPG = S / 2;                              // threads (lanes) per group
@@ -294,7 +294,7 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, flo
             float2 eN, rN;
             row_exp(st4[0], eN, rN);
             float4 qn = *qp;
-#pragma unroll 2
+#pragma unroll UNR
             for (int c = 0; c < C; ++c) {
                 float2 e2 = eN;
                 const float2 r2 = rN;
@@ -370,7 +370,7 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, flo
             float2 eN, rN;
             row_exp(st4[0], eN, rN);
             float4 qn = *qp;
-#pragma unroll 2
+#pragma unroll UNR
             for (int c = 0; c < C; ++c) {
                 const float2 e2 = eN, r2 = rN;
                 row_exp(qn, eN, rN);                         // class c+1: read before this class's in-place store

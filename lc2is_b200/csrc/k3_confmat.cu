@@ -709,6 +709,9 @@ k3_strip_kernel(const K3SParams P) {
 // warps") run k3_strip_rows over the same 16 groups in two rounds of 8 groups (one row per lane).  Two CTAs per SM:
 // 8 CE + 8 argmax warps share each SM's schedulers.  (The CE warps are the long pole; the warp arbiter favours the
 // higher warp ids.)
+#ifndef K23_UNR
+#define K23_UNR 4
+#endif
 template <int S>
 __global__ void __launch_bounds__(256, 2)
 k23_fused_kernel(const K2SParams P2, const K3SParams P3) {
@@ -753,7 +756,7 @@ k23_fused_kernel(const K2SParams P2, const K3SParams P3) {
         const int cw = warp - 4;
         int n, GY0, GX0;
         const bool act = tile_of(cw, n, GY0, GX0);
-        k2_strip_warp<S, true, CSF, true>(P2, taps + cw * 16, outq + cw * 16, act, n, GY0, GX0, lane);
+        k2_strip_warp<S, true, CSF, true, K23_UNR>(P2, taps + cw * 16, outq + cw * 16, act, n, GY0, GX0, lane);
     } else {
         const int aw = warp;
 #pragma unroll 1

@@ -86,3 +86,36 @@ def test_submit_wait_pipeline_matches_blocking_call():
     for k, g in zip(seq, got):
         assert g[1] == ref[k][1] and torch.equal(g[2], ref[k][2])
         assert abs(g[0] - ref[k][0]) <= 2e-6 * abs(ref[k][0])
+
+
+def test_config5_open_vocab_shape_against_eager_torch():
+    """BASELINE config 5 shape (1024^2 input = 64x64 patch grid, C=847 open-vocabulary prototypes), one image per
+    step: HeadStep (K1 with N-tiling, split K2 / K3 strip kernels - the fused kernel does not fit 847 classes)
+    against eager torch on the same device (the CPU oracle would need 3.5 GB for the upsampled map)."""
+    import torch.nn.functional as F
+    B, h, H, C = 1, 64, 1024, 847
+    v, t, labels = _inputs(B, h, H, C)
+    step = HeadStep(B, h, h, H, H, C, ignore_index=0)
+    assert step.split and not step.fused
+    vd, td, ld = v.to(DEV), t.to(DEV), labels.to(DEV)
+    step(vd, td, ld)
+    torch.cuda.synchronize()
+    # eager reference on the kernel's own logits (bf16-operand GEMM) for loss / confusion matrix ...
+    low = step.logits.detach().clone().requires_grad_(True)
+    up = F.interpolate(low, mode="bilinear", size=H)
+    ref_loss = F.cross_entropy(up, ld, ignore_index=0)
+    ref_loss.backward()
+    assert abs(float(step.loss) - float(ref_loss)) <= 3e-6 * float(ref_loss)
+    nv = int((ld != 0).sum())
+    assert int(step.n_valid) == nv
+    g = step.grad_low / nv
+    assert float((g - low.grad).abs().max()) <= 2e-5 * float(low.grad.abs().max())
+    pred = up.detach().argmax(1)
+    cm_ref = torch.bincount((ld * C + pred).flatten(), minlength=C * C).view(C, C)
+    # fp32 evaluation order may flip near-ties: totals exact, matrix equal up to a handful of pixels
+    assert int(step.confmat.sum()) == B * H * H
+    assert torch.equal(step.confmat.sum(1), torch.bincount(ld.flatten(), minlength=C))
+    assert int((step.confmat - cm_ref).abs().sum()) <= 2e-5 * B * H * H
+    # ... and the fp32 reference logits for K1 (bf16 operands: 4e-3 absolute, SURVEY 8c)
+    ref_low = O.cosine_logits(v.float(), t, hw_shape=(h, h))
+    assert float((step.logits.cpu() - ref_low).abs().max()) < 4e-3
