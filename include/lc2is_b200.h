@@ -200,9 +200,15 @@ int lc2is_argmax_confmat_lowres_packed(const float* d_low, int N, int C, int h, 
 int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W);
 int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* d_labels_packed,
                                  int B, int C, int h, int w, int H, int W,
-                                 double* d_loss_sum, float* d_grad_low,
+                                 double* d_loss_sum, float* d_grad_low, int onehot,
                                  int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                  lc2is_stream_t stream);
+/* onehot != 0: the argmax warps also add the un-scaled -onehot term to d_grad_low (they hold the row's labels
+ * anyway), so the labels only need packing + counting ahead of the kernel:
+ * lc2is_pack_labels: int64 [n] -> packed uint16 [n] (same encoding as lc2is_ce_labels_prepass), n_valid += #counted.
+ * n % 8 == 0. */
+int lc2is_pack_labels(const int64_t* d_labels, int64_t n, int C, int64_t ignore_index,
+                      uint16_t* d_labels_packed, int64_t* d_n_valid, lc2is_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Whole step from HOST buffers (the end-to-end path bench.py times as `e2e`).  Replaces one

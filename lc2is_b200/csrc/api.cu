@@ -51,6 +51,8 @@ __global__ void finalize_loss_kernel(const double* loss_sum, const long long* n_
     *out = (float)(*loss_sum / (double)(*n_valid));
 }
 
+__global__ void set_i64_kernel(long long* p, long long v) { *p = v; }
+
 }  // namespace lc2is
 
 using namespace lc2is;
@@ -81,17 +83,22 @@ extern "C" int lc2is_finalize_loss(const double* d_loss_sum, const int64_t* d_n_
 // 8 bytes per pixel would make the PCIe copy of the labels the longest stage of the step).  Same encoding as
 // k2_labels_prepass_kernel: class id; bit 15 = label == ignore_index; 0xFFFF = outside [0,C).
 namespace {
-void pack_labels_scalar(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+// (every variant returns the number of COUNTED labels: a class id other than ignore_index)
+long long pack_labels_scalar(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+    long long cnt = 0;
     for (size_t i = 0; i < n; ++i) {
         const uint64_t v = (uint64_t)src[i];
         const bool inr = v < (uint64_t)C;
         uint16_t o = inr ? (uint16_t)v : (uint16_t)0xFFFF;
         if (inr && src[i] == ign) o |= 0x8000;
+        cnt += inr && src[i] != ign;
         dst[i] = o;
     }
+    return cnt;
 }
-__attribute__((target("avx2")))
-void pack_labels_avx2(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+__attribute__((target("avx2,popcnt")))
+long long pack_labels_avx2(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+    long long cnt = 0;
     const __m256i vC = _mm256_set1_epi64x((long long)C - 1), vign = _mm256_set1_epi64x(ign);
     const __m256i zero = _mm256_setzero_si256(), ffff = _mm256_set1_epi64x(0xFFFF), flag = _mm256_set1_epi64x(0x8000);
     const __m256i idx = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6);
@@ -102,7 +109,9 @@ void pack_labels_avx2(const int64_t* src, uint16_t* dst, size_t n, int C, int64_
         for (int k = 0; k < 4; ++k) {
             const __m256i v = _mm256_loadu_si256((const __m256i*)(src + i + 4 * k));
             const __m256i bad = _mm256_or_si256(_mm256_cmpgt_epi64(zero, v), _mm256_cmpgt_epi64(v, vC));
-            __m256i r = _mm256_or_si256(v, _mm256_and_si256(_mm256_cmpeq_epi64(v, vign), flag));
+            const __m256i isign = _mm256_cmpeq_epi64(v, vign);
+            cnt += 4 - __builtin_popcount((unsigned)_mm256_movemask_pd(_mm256_castsi256_pd(_mm256_or_si256(bad, isign))));
+            __m256i r = _mm256_or_si256(v, _mm256_and_si256(isign, flag));
             r = _mm256_blendv_epi8(r, ffff, bad);
             q[k] = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(r, idx));   // low 32 bits of the 4 lanes
         }
@@ -116,18 +125,18 @@ void pack_labels_avx2(const int64_t* src, uint16_t* dst, size_t n, int C, int64_
         }
     }
     _mm_sfence();
-    pack_labels_scalar(src + i, dst + i, n - i, C, ign);
+    return cnt + pack_labels_scalar(src + i, dst + i, n - i, C, ign);
 }
-void pack_labels_range(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
-    static const bool have_avx2 = __builtin_cpu_supports("avx2");
-    if (have_avx2) pack_labels_avx2(src, dst, n, C, ign);
-    else pack_labels_scalar(src, dst, n, C, ign);
+long long pack_labels_range(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+    static const bool have_avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
+    return have_avx2 ? pack_labels_avx2(src, dst, n, C, ign) : pack_labels_scalar(src, dst, n, C, ign);
 }
 
 // A small persistent worker pool (created on first use, joined at process exit).
 class PackPool {
 public:
-    struct Task { const int64_t* src; uint16_t* dst; size_t n; int C; int64_t ign; std::atomic<int>* pending; };
+    struct Task { const int64_t* src; uint16_t* dst; size_t n; int C; int64_t ign; std::atomic<int>* pending;
+                  std::atomic<long long>* counted; };
     explicit PackPool(int nthreads) {
         for (int i = 0; i < nthreads; ++i) workers_.emplace_back([this] { run(); });
     }
@@ -151,7 +160,8 @@ private:
                 if (q_.empty()) return;
                 t = q_.front(); q_.pop_front();
             }
-            pack_labels_range(t.src, t.dst, t.n, t.C, t.ign);
+            const long long c = pack_labels_range(t.src, t.dst, t.n, t.C, t.ign);
+            if (t.counted) t.counted->fetch_add(c, std::memory_order_relaxed);
             t.pending->fetch_sub(1, std::memory_order_release);
         }
     }
@@ -177,7 +187,8 @@ PackPool& pack_pool() {
     return pool;
 }
 // split [0,n) into pieces for the pool; *pending counts the pieces still running
-void pack_submit(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign, std::atomic<int>* pending) {
+void pack_submit(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign, std::atomic<int>* pending,
+                 std::atomic<long long>* counted = nullptr) {
     PackPool& p = pack_pool();
     const int pieces = p.size();
     const size_t per = ((n + pieces - 1) / pieces + 63) / 64 * 64;
@@ -185,7 +196,7 @@ void pack_submit(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign
     for (size_t o = 0; o < n; o += per) ++cnt;
     pending->store(cnt, std::memory_order_relaxed);
     for (size_t o = 0; o < n; o += per)
-        p.submit({src + o, dst + o, per < n - o ? per : n - o, C, ign, pending});
+        p.submit({src + o, dst + o, per < n - o ? per : n - o, C, ign, pending, counted});
 }
 inline void pack_wait(std::atomic<int>* pending) {
     while (pending->load(std::memory_order_acquire) > 0) _mm_pause();
@@ -276,6 +287,7 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
     // Power-of-two scales 8 / 16 run the split form of K2 (label prepass + packed-label kernels); other
     // geometries the one-call K2 and the int64-label K3.
     const bool split = lc2is_ce_split_supported(h, w, H, W) != 0;
+    const bool fused = split && lc2is_ce_argmax_fused_supported(C, h, w, H, W) != 0;   // one K2+K3 kernel (x16)
 
     // The batch is cut into chunks: chunk i+1 is copied host->device on `copy_stream` while the
     // kernels of chunk i run on `stream` (engine.py:75 / :145 copy the whole batch up front).
@@ -300,13 +312,14 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
     const int nchunk = piped ? (B < want_chunks ? B : want_chunks) : 1;
     const int bc = (B + nchunk - 1) / nchunk;
     std::atomic<int> pack_pending[MAXCH];
+    std::atomic<long long> pack_counted{0};
     if (hpack)
         for (int i = 0; i < nchunk; ++i) {
             const int b0 = i * bc, nb = (b0 + bc <= B ? bc : B - b0);
             pack_pending[i].store(0);
             if (nb > 0)
                 pack_submit(h_labels + (size_t)b0 * H * W, h_scratch + (size_t)b0 * H * W, (size_t)nb * H * W, C,
-                            ignore_index, &pack_pending[i]);
+                            ignore_index, &pack_pending[i], &pack_counted);
         }
     cudaEvent_t ev_start = nullptr, ev_copy[MAXCH] = {};
     auto cleanup = [&]() {
@@ -359,7 +372,13 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         t_chunk[i] = now() - t_begin;
         float* lg = d_logits + (size_t)b0 * C * hw;
         float* gl = do_backward ? d_glow + (size_t)b0 * C * hw : nullptr;
-        if (hpack)
+        // labels: the fused K2+K3 kernel only needs them packed and counted (its argmax warps add the -onehot term);
+        // the separate kernels need the label prepass (count, packing, -onehot)
+        if (fused) {
+            if (!hpack)
+                STEP_RC(lc2is_pack_labels(d_labels + lab_off, (int64_t)nb * H * W, C, ignore_index, d_packed + lab_off,
+                                          d_nvalid, stream));
+        } else if (hpack)
             STEP_RC(lc2is_ce_labels_prepass_packed(d_packed + lab_off, nb, C, h, w, H, W, d_nvalid, gl, stream));
         else if (split)
             STEP_RC(lc2is_ce_labels_prepass(d_labels + lab_off, nb, C, h, w, H, W, ignore_index, d_packed + lab_off,
@@ -371,8 +390,8 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         STEP_RC(lc2is_cosine_logits_fwd(d_v + v_off, LC2IS_BF16, nb, hw, D, d_that, 1, C, 1, logit_scale,
                                         d_vhat + v_off, d_invv + (size_t)b0 * hw, lg, stream));
         mark("k1", st);
-        if (split && lc2is_ce_argmax_fused_supported(C, h, w, H, W)) {
-            STEP_RC(lc2is_ce_argmax_fused_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, d_cm,
+        if (fused) {
+            STEP_RC(lc2is_ce_argmax_fused_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, 1, d_cm,
                                                  nullptr, nullptr, stream));
         } else if (split) {
             STEP_RC(lc2is_upsample_ce_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, stream));
@@ -386,6 +405,10 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         }
     }
     mark("k2k3", st);
+    if (fused && hpack) {            // the host threads counted the valid labels while packing
+        set_i64_kernel<<<1, 1, 0, st>>>((long long*)d_nvalid, pack_counted.load());
+        lc2is::g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     STEP_RC(lc2is_mean_scale(d_nvalid, 1.0f, d_gscale, stream));
     if (do_backward) {
         STEP_CUDA(cudaMemsetAsync(ws + L.grad_t, 0, (size_t)C * D * 4, st));

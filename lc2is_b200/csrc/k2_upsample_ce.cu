@@ -578,6 +578,45 @@ k2_labels_prepass_kernel(const LT* __restrict__ labels,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Pack + count only (what the fused K2+K3 path needs from the labels ahead of time): int64 -> packed uint16 (same
+// encoding as k2_labels_prepass_kernel) and n_valid += #counted.  A pure stream: 8 labels (64 B in, 16 B out) per thread.
+__global__ void __launch_bounds__(256)
+k2_pack_labels_kernel(const long long* __restrict__ labels, long long n8, int C, long long ignore,
+                      unsigned short* __restrict__ packed, unsigned long long* __restrict__ n_valid) {
+    int cnt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const longlong2* src = reinterpret_cast<const longlong2*>(labels) + 4 * i;
+        longlong2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = __ldcs(src + k);
+        unsigned w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            unsigned word = 0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const unsigned long long tl = (unsigned long long)(e ? v[k].y : v[k].x);
+                const bool inr = tl < (unsigned long long)C, ok = inr && tl != (unsigned long long)ignore;
+                cnt += ok;
+                word |= (unsigned)(inr ? (ok ? (unsigned)tl : ((unsigned)tl | 0x8000u)) : 0xffffu) << (16 * e);
+            }
+            w[k] = word;
+        }
+        reinterpret_cast<uint4*>(packed)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __shared__ int red_c[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) red_c[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long tc = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tc += red_c[i];
+        if (tc && n_valid) atomicAdd(n_valid, (unsigned long long)tc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // generic path: any (h,w)->(H,W); one pixel per thread; exact 3-pass softmax; global atomics.
 __global__ void __launch_bounds__(256)
 k2_generic_kernel(const float* __restrict__ low, const long long* __restrict__ labels,
@@ -818,6 +857,27 @@ extern "C" int lc2is_ce_labels_prepass(const int64_t* d_labels,
     else if (s == 8) launch(k2_labels_prepass_kernel<8, long long>);
     else launch(k2_labels_prepass_kernel<16, long long>);
     LC2IS_CHECK_LAUNCH("k2_labels_prepass_kernel");
+    return 0;
+}
+
+extern "C" int lc2is_pack_labels(const int64_t* d_labels, int64_t n, int C, int64_t ignore_index,
+                                 uint16_t* d_labels_packed, int64_t* d_n_valid, lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (n < 0 || C <= 0) return fail(LC2IS_ERR_SHAPE, "bad n / C%s");
+    if (C >= 0x7fff) return fail(LC2IS_ERR_UNSUPPORTED, "packed labels hold class ids < 32767%s");
+    if (n == 0) return 0;
+    if (!d_labels || !d_labels_packed) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (n % 8) return fail(LC2IS_ERR_SHAPE, "lc2is_pack_labels: n must be a multiple of 8%s");
+    if (((uintptr_t)d_labels % 16) || ((uintptr_t)d_labels_packed % 16))
+        return fail(LC2IS_ERR_ARG, "labels must be 16-byte aligned%s");
+    const long long n8 = n / 8;
+    long long blocks = (n8 + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    k2_pack_labels_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)d_labels, n8, C, (long long)ignore_index, (unsigned short*)d_labels_packed,
+        (unsigned long long*)d_n_valid);
+    LC2IS_CHECK_LAUNCH("k2_pack_labels_kernel");
     return 0;
 }
 

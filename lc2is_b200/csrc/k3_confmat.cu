@@ -474,6 +474,7 @@ struct K3SParams {
     unsigned long long* per_image;
     long long* pred_out;
     int N, C, h, w, H, W, lh, lw;
+    float* onehot_grad;           // fused kernel only: [N,C,h,w] fp32, receives the un-scaled -onehot term (or null)
 };
 
 __device__ __forceinline__ float k3_strip_value(const float4 q, float ly, float lx0, float rsx, int j) {
@@ -522,6 +523,36 @@ __device__ __forceinline__ void k3_strip_rows(const K3SParams& P, const float4* 
     if constexpr (SYNC == 1) __syncwarp();
     if constexpr (SYNC == 2) __syncthreads();
 
+    if constexpr (FUSED && PACKED) {
+        // -onehot term of dL/dlogits for this row: exact integer tap weights (lambda * 2S), run-length aggregated along
+        // the row (the job of k2_labels_prepass_kernel when K2 and K3 run as separate kernels)
+        if (P.onehot_grad != nullptr && row_in) {
+            constexpr float WSC = 1.f / (float)(4 * S * S);
+            const int lyi = 2 * i + 1;
+            const int Ya = clampi(ky, 0, P.h - 1), Yb = clampi(ky + 1, 0, P.h - 1);
+            const int Xa = clampi(kx, 0, P.w - 1), Xb = clampi(kx + 1, 0, P.w - 1);
+            const size_t plane = (size_t)P.h * P.w;
+            float* gbase = P.onehot_grad + (size_t)n * C * plane;
+            const size_t oA = (size_t)Ya * P.w + Xa, oB = (size_t)Ya * P.w + Xb, oC = (size_t)Yb * P.w + Xa, oD = (size_t)Yb * P.w + Xb;
+            int cur = -1, sw0 = 0, sw1 = 0;
+            auto flush = [&]() {
+                if (cur < 0) return;
+                float* gp = gbase + (size_t)cur * plane;
+                atomicAdd(gp + oA, -(float)((2 * S - lyi) * sw0) * WSC); atomicAdd(gp + oB, -(float)((2 * S - lyi) * sw1) * WSC);
+                atomicAdd(gp + oC, -(float)(lyi * sw0) * WSC);           atomicAdd(gp + oD, -(float)(lyi * sw1) * WSC);
+            };
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const int lab = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+                if (lab < C) {                                              // counted: class id without the ignore flag
+                    if (lab != cur) { flush(); cur = lab; sw0 = 0; sw1 = 0; }
+                    sw0 += 2 * S - (2 * j + 1);
+                    sw1 += 2 * j + 1;
+                }
+            }
+            flush();
+        }
+    }
     // ---- non-finite taps? ------------------------------------------------------------------------------------
     bool exotic = false;
     for (int c = i; c < C; c += S) {
@@ -887,7 +918,7 @@ static int launch_k3_strip(const float* d_low, int N, int C, int h, int w, int H
     K3SParams P;
     P.low = d_low; P.labels = labels; P.confmat = (unsigned long long*)d_confmat;
     P.per_image = (unsigned long long*)d_per_image; P.pred_out = (long long*)d_pred;
-    P.N = N; P.C = C; P.h = h; P.w = w; P.H = H; P.W = W; P.lh = lh; P.lw = lw;
+    P.N = N; P.C = C; P.h = h; P.w = w; P.H = H; P.W = W; P.lh = lh; P.lw = lw; P.onehot_grad = nullptr;
     const long long ngroups = (long long)N * (h + 1) * (w + 1);
     const long long warps = (ngroups + (32 / s) - 1) / (32 / s);
     const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
@@ -909,7 +940,8 @@ static int launch_k3_strip(const float* d_low, int N, int C, int h, int w, int H
 using namespace lc2is;
 
 // K2 (split form) + K3 fused for the x16 geometry: d_loss_sum += sum(lse - target logit); d_grad_low ACCUMULATES the
-// un-scaled softmax term (or NULL); d_confmat / d_per_image ACCUMULATE; d_pred optional.
+// un-scaled softmax term (or NULL) - and, with onehot != 0, the -onehot term as well (then the labels only need
+// lc2is_pack_labels, not the label prepass); d_confmat / d_per_image ACCUMULATE; d_pred optional.
 extern "C" int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W) {
     int s = 0;
     if (!fast_scale(h, w, H, W, &s) || s != 16) return 0;
@@ -919,7 +951,7 @@ extern "C" int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W
 
 extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* d_labels_packed,
                                             int B, int C, int h, int w, int H, int W,
-                                            double* d_loss_sum, float* d_grad_low,
+                                            double* d_loss_sum, float* d_grad_low, int onehot,
                                             int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                             lc2is_stream_t stream) {
     if (int e = ensure_device()) return e;
@@ -938,6 +970,7 @@ extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* 
     P3.low = d_low; P3.labels = d_labels_packed; P3.confmat = (unsigned long long*)d_confmat;
     P3.per_image = (unsigned long long*)d_per_image; P3.pred_out = (long long*)d_pred;
     P3.N = B; P3.C = C; P3.h = h; P3.w = w; P3.H = H; P3.W = W; P3.lh = H; P3.lw = W;
+    P3.onehot_grad = onehot ? d_grad_low : nullptr;
     const size_t smem = ((size_t)(C + 8) + C) * 64 * sizeof(float);
     const long long tiles = (long long)B * P2.nty * P2.ntx;
     const unsigned grid = (unsigned)((tiles + 3) / 4);

@@ -211,8 +211,20 @@ def argmax_confmat_packed(low: Tensor, labels_packed: Tensor, size: Tuple[int, i
     return confmat, pi, pred
 
 
+def pack_labels(labels: Tensor, C: int, ignore_index: int, n_valid: Optional[Tensor] = None):
+    """int64 labels -> (packed uint16 of the same shape, n_valid int64[1] accumulated)."""
+    labels = _req(labels, torch.int64, "labels")
+    packed = torch.empty(labels.shape, dtype=torch.uint16, device=labels.device)
+    if n_valid is None:
+        n_valid = torch.zeros(1, dtype=torch.int64, device=labels.device)
+    check(lib.lc2is_pack_labels(ptr(labels), labels.numel(), C, int(ignore_index), ptr(packed), ptr(n_valid), stream_ptr()),
+          "lc2is_pack_labels")
+    return packed, n_valid
+
+
 def ce_argmax_fused(low: Tensor, labels_packed: Tensor, size: Tuple[int, int], loss_sum: Tensor, grad: Optional[Tensor],
-                    confmat: Optional[Tensor] = None, per_image: bool = False, want_pred: bool = False):
+                    confmat: Optional[Tensor] = None, per_image: bool = False, want_pred: bool = False,
+                    onehot: bool = False):
     """Fused K2 (split form) + K3 for the x16 geometry: accumulates into loss_sum / grad (un-scaled softmax term) /
     confmat.  -> (confmat, per_image | None, pred | None)."""
     low = _req(low, torch.float32, "low")
@@ -224,5 +236,6 @@ def ce_argmax_fused(low: Tensor, labels_packed: Tensor, size: Tuple[int, int], l
     pi = torch.zeros(N, 3, C, dtype=torch.int64, device=dev) if per_image else None
     pred = torch.empty(N, H, W, dtype=torch.int64, device=dev) if want_pred else None
     check(lib.lc2is_ce_argmax_fused_packed(ptr(low), ptr(labels_packed), N, C, h, w, H, W, ptr(loss_sum), ptr(grad),
-                                           ptr(confmat), ptr(pi), ptr(pred), stream_ptr()), "lc2is_ce_argmax_fused_packed")
+                                           int(onehot), ptr(confmat), ptr(pi), ptr(pred), stream_ptr()),
+          "lc2is_ce_argmax_fused_packed")
     return confmat, pi, pred

@@ -114,7 +114,11 @@ class HeadStep:
         self._acc.zero_()                                        # bucket, grad_low, scalars: one fill
         glow = ptr(self.grad_low) if self.backward else None
         self._mark("label prepass / count")
-        if self.split:
+        if self.fused:
+            # the fused K2+K3 kernel only needs the labels packed and counted (its argmax warps add the -onehot term)
+            check(lib.lc2is_pack_labels(ptr(labels), labels.numel(), C, self.ignore_index, ptr(self.labels_packed),
+                                        ptr(self.n_valid), st), "pack_labels")
+        elif self.split:
             # un-scaled gradients accumulate into grad_low (prepass: -onehot, K2: +softmax); 1/N_valid is applied
             # by K1b, so the valid-count all-reduce hides behind K0 / K1 / K2
             check(lib.lc2is_ce_labels_prepass(ptr(labels), B, C, h, w, H, W, self.ignore_index,
@@ -134,7 +138,7 @@ class HeadStep:
             self.k2_events[0].record()
         if self.fused:
             check(lib.lc2is_ce_argmax_fused_packed(ptr(self.logits), ptr(self.labels_packed), B, C, h, w, H, W,
-                                                   ptr(self.loss_sum), glow, ptr(self.confmat), None, None, st),
+                                                   ptr(self.loss_sum), glow, 1, ptr(self.confmat), None, None, st),
                   "ce_argmax_fused_packed")
         elif self.split:
             check(lib.lc2is_upsample_ce_packed(ptr(self.logits), ptr(self.labels_packed), B, C, h, w, H, W,

@@ -207,10 +207,9 @@ def test_fused_ce_argmax_kernel_matches_separate_kernels_and_oracle(N, C, h, ign
     assert ops._lib.lib.lc2is_ce_argmax_fused_supported(C, h, h, H, H)
     ls2 = torch.zeros(1, dtype=torch.float64, device=DEV)
     g2 = torch.zeros_like(dl)
-    _lib_check = ops.check
-    _lib_check(ops.lib.lc2is_ce_labels_prepass(dlab.data_ptr(), N, C, h, h, H, H, ign, packed.data_ptr(), None,
-                                               g2.data_ptr(), torch.cuda.current_stream().cuda_stream), "prepass")
-    cm, pi, pred = ops.ce_argmax_fused(dl, packed, (H, H), ls2, g2, per_image=True, want_pred=True)
+    packed2, nv2 = ops.pack_labels(dlab, C, ign)                 # pack + count only; -onehot comes from the argmax warps
+    assert torch.equal(packed2, packed) and int(nv2) == int(n_valid)
+    cm, pi, pred = ops.ce_argmax_fused(dl, packed2, (H, H), ls2, g2, per_image=True, want_pred=True, onehot=True)
     assert abs(float(ls2) - float(loss_sum)) <= 1e-6 * abs(float(loss_sum))
     assert float((g2 - grad).abs().max()) <= 1e-5 * float(grad.abs().max())
     up = F.interpolate(low, mode="bilinear", scale_factor=s)
