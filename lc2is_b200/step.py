@@ -58,8 +58,9 @@ class HeadStep:
         nb_pad = (nb + 3) // 4 * 4
         ngl = B * C * self.hw
         ngl_pad = (ngl + 3) // 4 * 4
-        self._acc = torch.zeros(4 * (nb_pad + ngl_pad) + 32, dtype=torch.uint8, device=dev)
-        f32 = self._acc[: 4 * (nb_pad + ngl_pad)].view(torch.float32)
+        self._acc32 = torch.zeros(nb_pad + ngl_pad + 8, dtype=torch.float32, device=dev)   # zeroed as fp32: 16-byte stores
+        self._acc = self._acc32.view(torch.uint8)
+        f32 = self._acc32[: nb_pad + ngl_pad]
         self.bucket = dp.GradBucket([(1, C, D), (1,)], dev, flat=f32[:nb])
         self.grad_t = self.bucket.views[0]
         self.grad_low = f32[nb_pad:nb_pad + ngl].view(B, C, h, w)
@@ -111,7 +112,7 @@ class HeadStep:
         B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
         dist_on = self.distributed
         self._mark("zero-fill")
-        self._acc.zero_()                                        # bucket, grad_low, scalars: one fill
+        self._acc32.zero_()                                      # bucket, grad_low, scalars: one fill
         glow = ptr(self.grad_low) if self.backward else None
         self._mark("label prepass / count")
         if self.fused:
