@@ -40,10 +40,7 @@ rownorm_kernel(const T* __restrict__ x, long long n_sets, int rows_per_set, int 
             continue;
         }
         const T* xi = x + ((size_t)set * rows_per_set + row) * D;
-        float ss = 0.f;
-        // 8 elements per lane per step (D % 8 == 0)
-        for (int d = lane * 8; d < D; d += 256) {
-            float v[8];
+        auto load8 = [&](int d, float (&v)[8]) {
             if constexpr (sizeof(T) == 4) {
                 float4 a = __ldg(reinterpret_cast<const float4*>(xi + d));
                 float4 b = __ldg(reinterpret_cast<const float4*>(xi + d) + 1);
@@ -57,6 +54,42 @@ rownorm_kernel(const T* __restrict__ x, long long n_sets, int rows_per_set, int 
                     v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
                 }
             }
+        };
+        auto store8 = [&](int d, const float (&v)[8], float denom) {
+            __nv_bfloat162 p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                p[i] = __floats2bfloat162_rn(normalize ? v[2 * i] / denom : v[2 * i],
+                                             normalize ? v[2 * i + 1] / denom : v[2 * i + 1]);
+            *reinterpret_cast<uint4*>(o + d) = *reinterpret_cast<uint4*>(p);
+        };
+        float ss = 0.f;
+        // 8 elements per lane per step (D % 8 == 0); rows of up to 1024 elements stay in registers between the
+        // norm and the scaling (one pass over memory)
+        if (D <= 1024) {
+            float v[4][8];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int d = lane * 8 + it * 256;
+                if (d < D) {
+                    load8(d, v[it]);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ss = fmaf(v[it][i], v[it][i], ss);
+                }
+            }
+            ss = warp_sum(ss);
+            const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
+            if (lane == 0 && inv_norm) inv_norm[(size_t)set * rows_per_set + row] = 1.f / denom;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int d = lane * 8 + it * 256;
+                if (d < D) store8(d, v[it], denom);
+            }
+            continue;
+        }
+        for (int d = lane * 8; d < D; d += 256) {
+            float v[8];
+            load8(d, v);
 #pragma unroll
             for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
         }
@@ -65,25 +98,8 @@ rownorm_kernel(const T* __restrict__ x, long long n_sets, int rows_per_set, int 
         if (lane == 0 && inv_norm) inv_norm[(size_t)set * rows_per_set + row] = 1.f / denom;
         for (int d = lane * 8; d < D; d += 256) {
             float v[8];
-            if constexpr (sizeof(T) == 4) {
-                float4 a = __ldg(reinterpret_cast<const float4*>(xi + d));
-                float4 b = __ldg(reinterpret_cast<const float4*>(xi + d) + 1);
-                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-            } else {
-                uint4 a = __ldg(reinterpret_cast<const uint4*>(xi + d));
-                unsigned w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    v[2 * i] = __uint_as_float(w[i] << 16);
-                    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-                }
-            }
-            __nv_bfloat162 p[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                p[i] = __floats2bfloat162_rn(normalize ? v[2 * i] / denom : v[2 * i],
-                                             normalize ? v[2 * i + 1] / denom : v[2 * i + 1]);
-            *reinterpret_cast<uint4*>(o + d) = *reinterpret_cast<uint4*>(p);
+            load8(d, v);
+            store8(d, v, denom);
         }
     }
 }

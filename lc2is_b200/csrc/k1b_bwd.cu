@@ -67,51 +67,76 @@ k1b_prep_kernel(const __nv_bfloat16* __restrict__ G, const float* __restrict__ L
 // one float4 of G and of the logits per lane; class sums leave with one reduction per (class, CTA), pixel sums meet in
 // shared memory and leave with one reduction per (pixel, slice) (r is zeroed by the caller).
 constexpr int PREPF_PX = 128, PREPF_W = 8, PREPF_CS = 4;
+constexpr int PREPF_CPW = 8;                  // classes per warp and class round
 __global__ void __launch_bounds__(PREPF_W * 32)
 k1b_prep_f32_kernel(const float* __restrict__ G, const float* __restrict__ L, int B, int C, int C_pad, int hw,
-                    int n_sets, int want_proj, __nv_bfloat16* __restrict__ Gb, float* __restrict__ r,
+                    int n_sets, int want_proj, int px_blocks, __nv_bfloat16* __restrict__ Gb, float* __restrict__ r,
                     float* __restrict__ rt) {
+    // px_blocks consecutive 128-pixel blocks per CTA: the class sums of a warp stay in registers across them, so rt
+    // receives one reduction per (class, CTA) - with one block per CTA the 128^2 grid would hammer 150 addresses
+    // with 300 K reductions
     __shared__ float racc_s[PREPF_W][PREPF_PX];
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.x * PREPF_PX + lane * 4;
-    const bool in = p < hw;                                  // hw % 4 == 0
     const int cper = ((C_pad + PREPF_CS - 1) / PREPF_CS + PREPF_W - 1) / PREPF_W * PREPF_W;
     const int c_lo = blockIdx.z * cper, c_hi = min(C_pad, c_lo + cper);
-    const float* g = G + (size_t)b * C * hw + p;
-    const float* l = L + (size_t)b * C * hw + p;
-    __nv_bfloat16* gb = Gb + (size_t)b * C_pad * hw + p;
     float* rts = rt + (size_t)(n_sets > 1 ? b : 0) * C;
-    float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 5
-    for (int c = c_lo + warp; c < c_hi; c += PREPF_W) {
-        float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), lv = gv;
-        if (c < C && in) {
-            gv = __ldcs(reinterpret_cast<const float4*>(g + (size_t)c * hw));
-            if (want_proj) lv = __ldg(reinterpret_cast<const float4*>(l + (size_t)c * hw));
-        }
-        if (in) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x, gv.y), hi = __floats2bfloat162_rn(gv.z, gv.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<unsigned*>(&lo); pk.y = *reinterpret_cast<unsigned*>(&hi);
-            *reinterpret_cast<uint2*>(gb + (size_t)c * hw) = pk;
-        }
-        if (want_proj && c < C) {
-            const float4 pr = make_float4(gv.x * lv.x, gv.y * lv.y, gv.z * lv.z, gv.w * lv.w);
-            racc.x += pr.x; racc.y += pr.y; racc.z += pr.z; racc.w += pr.w;
-            const float s = warp_sum((pr.x + pr.y) + (pr.z + pr.w));
-            if (lane == 0 && s != 0.f) atomicAdd(rts + c, s);
-        }
-    }
-    if (!want_proj) return;
-    *reinterpret_cast<float4*>(&racc_s[warp][lane * 4]) = racc;
-    __syncthreads();
-    if (threadIdx.x < PREPF_PX) {
-        const int pp = blockIdx.x * PREPF_PX + threadIdx.x;
-        float t = 0.f;
+    // class rounds of PREPF_W * PREPF_CPW classes (one round up to C_pad = 256)
+    for (int cr = c_lo; cr < c_hi; cr += PREPF_W * PREPF_CPW) {
+        float csum[PREPF_CPW];
 #pragma unroll
-        for (int w = 0; w < PREPF_W; ++w) t += racc_s[w][threadIdx.x];
-        if (pp < hw) atomicAdd(r + (size_t)b * hw + pp, t);
+        for (int k = 0; k < PREPF_CPW; ++k) csum[k] = 0.f;
+        for (int pb = 0; pb < px_blocks; ++pb) {
+            const int p0 = (blockIdx.x * px_blocks + pb) * PREPF_PX;
+            if (p0 >= hw) break;
+            const int p = p0 + lane * 4;
+            const bool in = p < hw;                              // hw % 4 == 0
+            const float* g = G + (size_t)b * C * hw + p;
+            const float* l = L + (size_t)b * C * hw + p;
+            __nv_bfloat16* gb = Gb + (size_t)b * C_pad * hw + p;
+            float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < PREPF_CPW; ++k) {
+                const int c = cr + warp + k * PREPF_W;
+                if (c >= c_hi) break;
+                float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), lv = gv;
+                if (c < C && in) {
+                    gv = __ldcs(reinterpret_cast<const float4*>(g + (size_t)c * hw));
+                    if (want_proj) lv = __ldg(reinterpret_cast<const float4*>(l + (size_t)c * hw));
+                }
+                if (in) {
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x, gv.y), hi = __floats2bfloat162_rn(gv.z, gv.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<unsigned*>(&lo); pk.y = *reinterpret_cast<unsigned*>(&hi);
+                    *reinterpret_cast<uint2*>(gb + (size_t)c * hw) = pk;
+                }
+                if (want_proj && c < C) {
+                    const float4 pr = make_float4(gv.x * lv.x, gv.y * lv.y, gv.z * lv.z, gv.w * lv.w);
+                    racc.x += pr.x; racc.y += pr.y; racc.z += pr.z; racc.w += pr.w;
+                    csum[k] += (pr.x + pr.y) + (pr.z + pr.w);
+                }
+            }
+            if (want_proj) {
+                *reinterpret_cast<float4*>(&racc_s[warp][lane * 4]) = racc;
+                __syncthreads();
+                if (threadIdx.x < PREPF_PX) {
+                    const int pp = p0 + threadIdx.x;
+                    float t = 0.f;
+#pragma unroll
+                    for (int w = 0; w < PREPF_W; ++w) t += racc_s[w][threadIdx.x];
+                    if (pp < hw) atomicAdd(r + (size_t)b * hw + pp, t);
+                }
+                __syncthreads();
+            }
+        }
+        if (want_proj) {
+#pragma unroll
+            for (int k = 0; k < PREPF_CPW; ++k) {
+                const int c = cr + warp + k * PREPF_W;
+                const float s = warp_sum(csum[k]);
+                if (lane == 0 && c < c_hi && c < C && s != 0.f) atomicAdd(rts + c, s);
+            }
+        }
     }
 }
 
@@ -464,9 +489,14 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, c
     const void* d_grad_logits_bf16 = d_grad_logits;
     if (g_dtype == LC2IS_F32) {
         d_grad_logits_bf16 = ws + L.gbf;
-        dim3 grid((hw + PREPF_PX - 1) / PREPF_PX, B, PREPF_CS);
+        const int nblk = (hw + PREPF_PX - 1) / PREPF_PX;
+        int px_blocks = nblk / 16;                           // >= 16 CTAs per image and class slice
+        if (px_blocks < 1) px_blocks = 1;
+        if (px_blocks > 16) px_blocks = 16;
+        dim3 grid((nblk + px_blocks - 1) / px_blocks, B, PREPF_CS);
         k1b_prep_f32_kernel<<<grid, PREPF_W * 32, 0, st>>>((const float*)d_grad_logits, d_logits, B, C, C_pad, hw,
-                                                           n_sets, normalize, (__nv_bfloat16*)(ws + L.gbf), d_r, d_rt);
+                                                           n_sets, normalize, px_blocks, (__nv_bfloat16*)(ws + L.gbf),
+                                                           d_r, d_rt);
         LC2IS_CHECK_LAUNCH("k1b_prep_f32_kernel");
     } else if (normalize) {
         dim3 grid((hw + PREP_PX - 1) / PREP_PX, B);
