@@ -1,33 +1,67 @@
-"""Turn gpurun_out/ captures into the tracked summaries under profiles/ (round tag as argv[1])."""
-import csv, os, subprocess, sys, json
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-os.makedirs("profiles", exist_ok=True)
-# 1. launch list of the bench step
-src = "gpurun_out/launches.csv"
-if os.path.exists(src):
-    rows = list(csv.reader(open(src)))
-    hdr = [r for r in rows if "Kernel Name" in r][0]
-    i0 = rows.index(hdr); kn = hdr.index("Kernel Name"); mv = hdr.index("Metric Value")
-    body = rows[i0 + 1:]
-    # one full step = from one k2_count_valid to the next
-    idx = [i for i, r in enumerate(body) if "k2_count_valid" in r[kn]]
-    step = body[idx[0]:idx[1]] if len(idx) >= 2 else body
-    tot = sum(float(r[mv].replace(",", "")) for r in step)
-    with open(f"profiles/{tag}_launch_list.md", "w") as f:
-        f.write(f"# {tag}: every launch of ONE bench step (cfg2 G-A, B=16, C=150), `ncu --metrics gpu__time_duration.sum --clock-control none`\n\n")
-        f.write("command: `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline` (per-launch times are cold-cache and serialised: compare shares)\n\n")
-        f.write("| us | share | kernel |\n|---:|---:|---|\n")
-        for r in step:
-            t = float(r[mv].replace(",", "")) / 1000
-            f.write(f"| {t:.1f} | {t * 1000 / tot * 100:.1f}% | `{r[kn][:110]}` |\n")
-        f.write(f"\nsum = {tot / 1000:.1f} us over {len(step)} launches\n")
-    os.system(f"cp {src} profiles/{tag}_launch_list.csv")
-# 2. ncu --set full summaries
-for name, rep in (("k2", "gpurun_out/k2_r1.ncu-rep"), ("k3full", "gpurun_out/k3full_r1.ncu-rep"), ("k1", "gpurun_out/k1_r1.ncu-rep")):
-    if not os.path.exists(rep): continue
-    out = subprocess.run([sys.executable, "tools/ncu_summary.py", rep], capture_output=True, text=True).stdout
-    ops = subprocess.run([sys.executable, "tools/ncu_opcodes.py", rep, "16"], capture_output=True, text=True).stdout
-    lines = subprocess.run([sys.executable, "tools/ncu_lines.py", rep, "15"], capture_output=True, text=True).stdout
-    with open(f"profiles/{tag}_{name}_ncu_full.txt", "w") as f:
-        f.write(f"# {tag} {name}: ncu --set full --clock-control none --import-source on (one launch)\n\n## metrics\n{out}\n## executed SASS opcodes\n{ops}\n## hottest source lines (stall samples)\n{lines}")
-print(os.listdir("profiles"))
+"""Turn gpurun_out/ captures into the tracked summaries under profiles/.
+usage: make_profiles.py TAG launches.csv step.ncu-rep"""
+import csv, json, re, subprocess, sys
+tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+# ---- 1. launch list of one bench step (between two finalize_loss launches)
+rows = list(csv.reader(open(launches)))
+hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
+H = rows[hdr]; ki = H.index('Kernel Name'); vi = H.index('Metric Value')
+L = [(r[ki], float(r[vi]) / 1e3) for r in rows[hdr + 1:] if len(r) > vi]
+fin = [i for i, (k, v) in enumerate(L) if 'finalize_loss' in k]
+a, b = fin[-2] + 1, fin[-1] + 1
+tot = sum(v for k, v in L[a:b])
+open(f'profiles/{tag}_launch_list.csv', 'w').write("us,kernel\n" + "\n".join(f"{v:.1f},\"{k}\"" for k, v in L[a:b]) + "\n")
+md = [f"# {tag}: every launch of ONE bench step (cfg2 G-A, B=16, C=150), `ncu --metrics gpu__time_duration.sum --clock-control none`", "",
+      "command: `python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu-baseline` (per-launch times are cold-cache and serialised: compare shares;",
+      "in-situ section times of the same step are in the bench line's `section_us` with `--kernel-times`)", "",
+      "| us | share | kernel |", "|---:|---:|---|"]
+md += [f"| {v:.1f} | {v / tot * 100:.1f}% | `{k[:110]}` |" for k, v in L[a:b]]
+md += ["", f"sum = {tot:.1f} us over {b - a} launches"]
+open(f'profiles/{tag}_launch_list.md', 'w').write("\n".join(md) + "\n")
+# ---- 2. ncu --set full summaries
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rr = list(csv.reader(out.splitlines())); h, units = rr[0], rr[1]
+mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+traffic = {}
+for r in rr[2:]:
+    nm = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").strip()
+    ir, iw = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+    traffic[nm] = int(float(r[ir]) * mul[units[ir]] + float(r[iw]) * mul[units[iw]])
+summ = subprocess.run([sys.executable, "tools/ncu_summary.py", rep], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+kern = None; h2 = None; data = {}
+for r in csv.reader(src.splitlines()):
+    if r and r[0] == "Kernel Name": kern = r[1]; data[kern] = []; continue
+    if r and r[0] == "Address": h2 = r; continue
+    if h2 and len(r) == len(h2) and kern: data[kern].append(r)
+ix = {k: i for i, k in enumerate(h2)}
+def opmix(d):
+    ti = sum(int(r[ix["Instructions Executed"]]) for r in d); o = {}
+    for r in d:
+        t = r[ix["Source"]].split(); op = t[1] if t and t[0].startswith("@") else (t[0] if t else "?")
+        o[op] = o.get(op, 0) + int(r[ix["Instructions Executed"]])
+    lines = [f"total {ti}"] + [f"{n / ti * 100:5.1f}% {n:11d}  {op}" for op, n in sorted(o.items(), key=lambda kv: -kv[1])[:18]]
+    st = {}
+    for s_ in [c for c in h2 if c.startswith("stall_") and "Not" not in c]:
+        st[s_[6:]] = sum(int(r[ix[s_]]) for r in d)
+    t = sum(st.values()) or 1
+    return "\n".join(lines + ["", "warp-state samples: " + ", ".join(f"{k} {v / t * 100:.1f}%" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:8])])
+names = {"k23_fused": "k23fused", "k2_strip": "k2", "k3_strip": "k3strip", "prepass": "prepass", "prep_f32": "k1bprep", "pack_labels": "packlabels"}
+for blk in summ.split("-" * 60):
+    m = re.search(r"Kernel Name = (.*)", blk)
+    if not m: continue
+    kn = m.group(1); key = [v for k, v in names.items() if k in kn]
+    if not key: continue
+    dk = [k for k in data if k.split("(")[0].split("::")[-1].split("<")[0] in kn][0]
+    open(f"profiles/{tag}_{key[0]}_ncu_full.txt", "w").write(
+        f"# {tag} {key[0]}: ncu --set full --clock-control none --import-source on (one launch inside the step: "
+        f"`python tools/run_one.py step A 16`, cfg2 G-A B=16 C=150)\n\n## metrics\n{blk.strip()}\n\n## executed SASS opcodes\n{opmix(data[dk])}\n")
+try: tj = json.load(open("profiles/traffic.json"))
+except Exception: tj = {}
+tj["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, cfg2 G-A B=16 C=150 (profiles/r01_*_ncu_full.txt)"
+for k, v in traffic.items():
+    if "k23_fused" in k: tj["k23_fused_kernel<16>"] = v
+    elif "pack_labels" in k: tj["k2_pack_labels_kernel"] = v
+    elif "prep_f32" in k: tj["k1b_prep_f32_kernel"] = v
+json.dump(tj, open("profiles/traffic.json", "w"), indent=1)
+print(open(f'profiles/{tag}_launch_list.md').read()); print(tj)
