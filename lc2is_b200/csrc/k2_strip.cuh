@@ -149,17 +149,16 @@ __device__ __noinline__ float k2_strip_slow(const float* st, int cs, int gl, uns
 }
 
 // CSF = floats per class of the tile the warp's quads live in (16 for the stand-alone kernel's per-warp tile, 64 for
-// the 16-group CTA tile of the fused K2+K3 kernel); st = the warp's first tap quad of class 0, so = the same position
-// in the tile that receives the tap gradients (so == st: in place).  CTA_SYNC: the taps were staged by the whole CTA.
+// the 16-group CTA tile of the fused K2+K3 kernel); st = the warp's first tap quad of class 0.
+// CTA_SYNC: the taps were staged by the whole CTA (barrier instead of a warp sync).
 template <int S, bool SPLIT, int CSF, bool CTA_SYNC, int UNR = 2>
-__device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, float* so, bool active, int n, int GY0,
+__device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, bool active, int n, int GY0,
                                               int GX0, int lane) {
     constexpr int TPG = S / 2;                              // threads (lanes) per group
     constexpr int GPW = 32 / TPG;                           // groups per warp: 4 (S=16) / 8 (S=8)
     constexpr int WGX = GPW / 2;                            // warp tile = 2 x WGX groups
     constexpr int CS = CSF;                                 // floats per class in the tile
     constexpr int CS4 = CSF / 4;
-    constexpr int NCX = WGX + 1, NCELL = 3 * NCX;           // source cells touched by the warp tile
     constexpr float RS = 1.f / S;
     constexpr float LX0 = 0.5f / S;                         // lambda_x of the group's first column
     const int C = P.C;
@@ -264,7 +263,6 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, flo
     };
 
     float loss = 0.f;
-    bool wrote = false;                                     // the warp's quads hold tap gradients
     if constexpr (SPLIT) {
         // -sum of the target logits of the strip (the -onehot gradient came from the label prepass)
         if (vm) {
@@ -359,12 +357,27 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, flo
                 flush();
             }
         }
-        // ---- pass B: tap gradients of every class, stored in place ---------------------------------------------
+        // ---- pass B: tap gradients of every class -----------------------------------------------------------------
+        // The TPG lanes of a group add their four tap gradients with a shuffle butterfly (lane role*(TPG/4) of the
+        // group ends up with tap `role`); two more shuffles merge the taps that neighbouring groups of the warp tile
+        // share (horizontally, then vertically), and the (2+1) x (WGX+1) lanes that then hold one source cell each
+        // send it to L2 as ONE float reduction per (class, cell) - 9 instead of 16 per 2x2 tile, no shared-memory
+        // round trip.
         if (gb) {
-            __syncwarp();                                   // every lane has read its target taps
             const int role = (u * 4) / TPG;
             const bool writer = (u % (TPG / 4)) == 0;
-            float* stw = so + gl * 4 + role;
+            const int gy_ = gl / WGX, gx_ = gl % WGX, ry = role >> 1, rx = role & 1;
+            // horizontal: (gx_, rx = 0) with gx_ >= 1 takes (gx_ - 1, rx = 1); vertical: (gy_ = 1, ry = 0) takes (gy_ = 0, ry = 1)
+            const bool h_dst = writer && rx == 0 && gx_ >= 1;
+            const int h_src = ((gy_ * WGX + (gx_ >= 1 ? gx_ - 1 : 0)) * TPG) + (ry * 2 + 1) * (TPG / 4);
+            const bool holder_x = writer && (rx == 0 || gx_ == WGX - 1);          // holds a complete column cell
+            const bool v_dst = holder_x && gy_ == 1 && ry == 0;
+            const int v_src = ((0 * WGX + gx_) * TPG) + (2 + rx) * (TPG / 4);
+            const bool holder = holder_x && ((gy_ == 0 && ry == 0) || gy_ == 1);   // one lane per source cell
+            const int cy = gy_ + ry, cx = gx_ + rx;                                // cell of the warp tile
+            const int uy = GY0 - 1 + cy, ux = GX0 - 1 + cx;                        // unclamped source cell
+            float* dst = (holder && uy <= P.h && ux <= P.w)
+                             ? gb + (size_t)clampi2(uy, 0, P.h - 1) * P.w + clampi2(ux, 0, P.w - 1) : nullptr;
             const float2 omy = make_float2(1.f - ly2.x, 1.f - ly2.y);
             const float4* qp = st4 + CS4;
             float2 eN, rN;
@@ -373,7 +386,7 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, flo
 #pragma unroll UNR
             for (int c = 0; c < C; ++c) {
                 const float2 e2 = eN, r2 = rN;
-                row_exp(qn, eN, rN);                         // class c+1: read before this class's in-place store
+                row_exp(qn, eN, rN);                         // class c+1
                 qp += CS4;
                 qn = *qp;                                    // class c+2
                 float2 h2 = U2[S - 1], d2 = h2;
@@ -390,43 +403,16 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, flo
                 const float2 a2 = fmul2(omy, N2), b2 = fmul2(omy, X2), c2 = fmul2(ly2, N2), d2y = fmul2(ly2, X2);
                 float A = a2.x + a2.y, Bv = b2.x + b2.y, Cv = c2.x + c2.y, Dv = d2y.x + d2y.y;
                 group_reduce4<TPG>(A, Bv, Cv, Dv, u);
-                if (writer) stw[c * CS] = grp_any ? A : 0.f;  // no valid pixel -> exactly zero (taps may be NaN)
+                A = grp_any ? A : 0.f;                       // no valid pixel -> exactly zero (taps may be NaN)
+                const float hx = __shfl_sync(0xffffffffu, A, h_src);
+                if (h_dst) A += hx;
+                const float vx = __shfl_sync(0xffffffffu, A, v_src);
+                if (v_dst) A += vx;
+                if (dst) atomicAdd(dst + (size_t)c * plane, A);
             }
-            wrote = true;
         }
     } else if (warp_any) {
         loss += k2_strip_slow<S, SPLIT>(st, CS, gl, vm, n, y0, x0, u, P, gs, gA, gB, gC, gD);
-    }
-    if (gb && wrote) {
-        __syncwarp();
-        // ---- combine: one L2 reduction per (class, source cell of the warp tile) -------------------------------
-        // lane -> fixed cell (lane % NCELL), classes strided by 32 / NCELL
-        constexpr int CPI = 32 / NCELL;                     // classes per iteration: 3 (S=16) / 2 (S=8)
-        const int cell = lane % NCELL, c0 = lane / NCELL;
-        const int cy = cell / NCX, cx = cell - cy * NCX;
-        const int uy = GY0 - 1 + cy, ux = GX0 - 1 + cx;     // unclamped source cell
-        if (c0 < CPI && uy <= P.h && ux <= P.w) {
-            int o[4];
-            int no = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int gy_ = cy - (k >> 1), gx_ = cx - (k & 1);
-                if (gy_ >= 0 && gy_ < 2 && gx_ >= 0 && gx_ < WGX) o[no++] = (gy_ * WGX + gx_) * 4 + k;
-            }
-#pragma unroll
-            for (int k = 1; k < 4; ++k)
-                if (k >= no) o[k] = o[0];
-            float* dst = gb + (size_t)clampi2(uy, 0, P.h - 1) * P.w + clampi2(ux, 0, P.w - 1) + (size_t)c0 * plane;
-            const float* sc = so + c0 * CS;
-            for (int c = c0; c < C; c += CPI) {
-                float v = sc[o[0]];
-                if (no > 1) v += sc[o[1]];
-                if (no > 2) v += sc[o[2]] + sc[o[3]];
-                atomicAdd(dst, v);
-                sc += CPI * CS;
-                dst += (size_t)CPI * plane;
-            }
-        }
     }
     loss = warp_sum(loss);
     if (lane == 0 && loss != 0.f) atomicAdd(P.loss_sum, (double)loss);

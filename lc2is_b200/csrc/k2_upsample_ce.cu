@@ -446,7 +446,7 @@ k2_strip_kernel(const K2SParams P) {
             else dst[c * CS] = 0.f;
         }
     }
-    k2_strip_warp<S, SPLIT, CS, false>(P, st, st, true, n, GY0, GX0, lane);
+    k2_strip_warp<S, SPLIT, CS, false>(P, st, true, n, GY0, GX0, lane);
 }
 
 // ---------------------------------------------------------------------------------------------

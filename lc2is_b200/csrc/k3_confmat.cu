@@ -737,14 +737,14 @@ k3_strip_kernel(const K3SParams P) {
 // launched on two streams the block scheduler does not co-schedule them either.  Here a CTA of 8 warps stages the
 // taps of 16 groups ONCE; warps 4-7 ("CE warps") run k2_strip_warp on one 2x2 tile each and write their tap
 // gradients to a second shared tile (not in place: the other warps are still reading the taps), warps 0-3 ("argmax
-// warps") run k3_strip_rows over the same 16 groups in two rounds of 8 groups (one row per lane).  Two CTAs per SM:
-// 8 CE + 8 argmax warps share each SM's schedulers.  (The CE warps are the long pole; the warp arbiter favours the
+// warps") run k3_strip_rows over the same 16 groups in two rounds of 8 groups (one row per lane).  Three CTAs per SM:
+// 12 CE + 12 argmax warps share each SM's schedulers.  (The CE warps are the long pole; the warp arbiter favours the
 // higher warp ids.)
 #ifndef K23_UNR
-#define K23_UNR 4
+#define K23_UNR 2
 #endif
 template <int S>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 k23_fused_kernel(const K2SParams P2, const K3SParams P3) {
     static_assert(S == 16, "fused kernel: x16 geometry");
     constexpr int NG = 16, CSF = NG * 4, CH = 8;            // groups per CTA, floats per class, K3's class chunk
@@ -752,7 +752,6 @@ k23_fused_kernel(const K2SParams P2, const K3SParams P3) {
     extern __shared__ float smem[];
     const int C = P2.C;
     float* taps = smem;                                     // [C + CH][16 groups][4 taps]
-    float* outq = smem + (size_t)(C + CH) * CSF;            // [C][16 groups][4 tap gradients]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_img = P2.nty * P2.ntx;
     const long long ntiles = (long long)P2.B * tiles_per_img;
@@ -787,7 +786,7 @@ k23_fused_kernel(const K2SParams P2, const K3SParams P3) {
         const int cw = warp - 4;
         int n, GY0, GX0;
         const bool act = tile_of(cw, n, GY0, GX0);
-        k2_strip_warp<S, true, CSF, true, K23_UNR>(P2, taps + cw * 16, outq + cw * 16, act, n, GY0, GX0, lane);
+        k2_strip_warp<S, true, CSF, true, K23_UNR>(P2, taps + cw * 16, act, n, GY0, GX0, lane);
     } else {
         const int aw = warp;
 #pragma unroll 1
@@ -945,8 +944,8 @@ using namespace lc2is;
 extern "C" int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W) {
     int s = 0;
     if (!fast_scale(h, w, H, W, &s) || s != 16) return 0;
-    const size_t smem = ((size_t)(C + 8) + C) * 64 * sizeof(float);
-    return smem <= 110 * 1024 ? 1 : 0;                      // two CTAs per SM
+    const size_t smem = (size_t)(C + 8) * 64 * sizeof(float);
+    return smem <= 72 * 1024 ? 1 : 0;                       // three CTAs per SM
 }
 
 extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* d_labels_packed,
@@ -960,7 +959,7 @@ extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* 
     if (!d_low || !d_labels_packed || !d_loss_sum || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
     if ((uintptr_t)d_labels_packed % 16) return fail(LC2IS_ERR_ARG, "packed labels must be 16-byte aligned%s");
     if (!lc2is_ce_argmax_fused_supported(C, h, w, H, W))
-        return fail(LC2IS_ERR_UNSUPPORTED, "fused K2+K3 needs scale 16 and a class count that fits two CTAs per SM%s");
+        return fail(LC2IS_ERR_UNSUPPORTED, "fused K2+K3 needs scale 16 and a class count whose tap tile fits three CTAs per SM%s");
     K2SParams P2;
     P2.low = d_low; P2.labels = nullptr; P2.labels16 = d_labels_packed; P2.grad_low = d_grad_low;
     P2.loss_sum = d_loss_sum; P2.grad_scale = nullptr; P2.ignore_index = 0;
@@ -971,7 +970,7 @@ extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* 
     P3.per_image = (unsigned long long*)d_per_image; P3.pred_out = (long long*)d_pred;
     P3.N = B; P3.C = C; P3.h = h; P3.w = w; P3.H = H; P3.W = W; P3.lh = H; P3.lw = W;
     P3.onehot_grad = onehot ? d_grad_low : nullptr;
-    const size_t smem = ((size_t)(C + 8) + C) * 64 * sizeof(float);
+    const size_t smem = (size_t)(C + 8) * 64 * sizeof(float);
     const long long tiles = (long long)B * P2.nty * P2.ntx;
     const unsigned grid = (unsigned)((tiles + 3) / 4);
     if (int e = set_smem(k23_fused_kernel<16>, smem)) return e;
