@@ -251,38 +251,54 @@ k1b_dv_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ C
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
             const int d0 = nt * DV_BN;
-            for (int col = 0; col < DV_BN; col += 16) {
-                if (d0 + col >= P.D) break;
-                uint32_t acc[16];
-                tc::tmem_ld16(taddr + col, acc);
-                tc::tmem_ld_wait();
-                if (rvalid) {
-                    float o[16];
-                    if (P.normalize) {
-                        const uint4* vp = reinterpret_cast<const uint4*>(P.v_hat + m * P.D + d0 + col);
-                        uint4 v0 = __ldg(vp), v1 = __ldg(vp + 1);
-                        unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            // v_hat of four 16-channel chunks is fetched ahead of the TMEM reads: one global-memory round trip per 64
+            // channels instead of one per 16 on the critical path of the tile
+            for (int col0 = 0; col0 < DV_BN; col0 += 64) {
+                if (d0 + col0 >= P.D) break;
+                uint4 vh[4][2];
+                if (rvalid && P.normalize) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float va = __uint_as_float(w[j] << 16), vb = __uint_as_float(w[j] & 0xffff0000u);
-                            o[2 * j] = (__uint_as_float(acc[2 * j]) * sg - va * rr) * inv;
-                            o[2 * j + 1] = (__uint_as_float(acc[2 * j + 1]) * sg - vb * rr) * inv;
+                    for (int k = 0; k < 4; ++k) {
+                        if (d0 + col0 + 16 * k < P.D) {
+                            const uint4* vp = reinterpret_cast<const uint4*>(P.v_hat + m * P.D + d0 + col0 + 16 * k);
+                            vh[k][0] = __ldg(vp); vh[k][1] = __ldg(vp + 1);
                         }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(acc[j]) * sg;
                     }
-                    if (P.out_f32) {
-                        float4* op = reinterpret_cast<float4*>((float*)P.grad_v + m * P.D + d0 + col);
+                }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                    } else {
-                        __nv_bfloat162 pk[8];
+                for (int k = 0; k < 4; ++k) {
+                    const int col = col0 + 16 * k;
+                    if (d0 + col >= P.D) break;
+                    uint32_t acc[16];
+                    tc::tmem_ld16(taddr + col, acc);
+                    tc::tmem_ld_wait();
+                    if (rvalid) {
+                        float o[16];
+                        if (P.normalize) {
+                            const uint4 v0 = vh[k][0], v1 = vh[k][1];
+                            unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) pk[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
-                        uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)P.grad_v + m * P.D + d0 + col);
-                        op[0] = *reinterpret_cast<uint4*>(&pk[0]);
-                        op[1] = *reinterpret_cast<uint4*>(&pk[4]);
+                            for (int j = 0; j < 8; ++j) {
+                                const float va = __uint_as_float(w[j] << 16), vb = __uint_as_float(w[j] & 0xffff0000u);
+                                o[2 * j] = (__uint_as_float(acc[2 * j]) * sg - va * rr) * inv;
+                                o[2 * j + 1] = (__uint_as_float(acc[2 * j + 1]) * sg - vb * rr) * inv;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(acc[j]) * sg;
+                        }
+                        if (P.out_f32) {
+                            float4* op = reinterpret_cast<float4*>((float*)P.grad_v + m * P.D + d0 + col);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                        } else {
+                            __nv_bfloat162 pk[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) pk[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+                            uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)P.grad_v + m * P.D + d0 + col);
+                            op[0] = *reinterpret_cast<uint4*>(&pk[0]);
+                            op[1] = *reinterpret_cast<uint4*>(&pk[4]);
+                        }
                     }
                 }
             }
