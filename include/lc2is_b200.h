@@ -98,6 +98,18 @@ int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, const float*
                             int normalize, float logit_scale, const float* d_grad_scale,
                             void* d_grad_v, int gv_dtype, float* d_grad_t,
                             void* d_ws, lc2is_stream_t stream);
+/* Same with flags.  LC2IS_BWD_REUSE_PREP: the workspace already holds the projections and the bf16 operand of an
+ * earlier call on the same inputs - for running the backward as two calls, d_grad_t first (d_grad_v = NULL) and
+ * d_grad_v second (d_grad_t = NULL, this flag), so that a data-parallel caller can all-reduce the prototype gradient
+ * while the patch-gradient GEMM runs. */
+#define LC2IS_BWD_REUSE_PREP 1
+int lc2is_cosine_logits_bwd_ex(const void* d_grad_logits, int g_dtype, const float* d_logits,
+                               const void* d_v_hat, const float* d_inv_norm_v,
+                               const void* d_t_hat, const float* d_inv_norm_t,
+                               int B, int hw, int D, int n_sets, int C,
+                               int normalize, float logit_scale, const float* d_grad_scale,
+                               void* d_grad_v, int gv_dtype, float* d_grad_t,
+                               void* d_ws, lc2is_stream_t stream, int flags);
 
 /* fp32 [B,C,hw] -> bf16 [B,C_pad,hw] (zero pad rows); for callers whose dL/dlogits did not
  * come from K2. */

@@ -474,13 +474,13 @@ extern "C" int64_t lc2is_cosine_logits_bwd_workspace(int B, int hw, int D, int n
     return (int64_t)bwd_layout(B, hw, D, n_sets, C).total;
 }
 
-extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, const float* d_logits,
+extern "C" int lc2is_cosine_logits_bwd_ex(const void* d_grad_logits, int g_dtype, const float* d_logits,
                                        const void* d_v_hat, const float* d_inv_norm_v,
                                        const void* d_t_hat, const float* d_inv_norm_t,
                                        int B, int hw, int D, int n_sets, int C,
                                        int normalize, float logit_scale, const float* d_grad_scale,
                                        void* d_grad_v, int gv_dtype, float* d_grad_t,
-                                       void* d_ws, lc2is_stream_t stream) {
+                                       void* d_ws, lc2is_stream_t stream, int flags) {
     if (int e = ensure_device()) return e;
     if (B < 0 || hw <= 0 || C <= 0 || D <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
     if (B == 0) return 0;
@@ -499,12 +499,15 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, c
     float* d_r = (float*)(ws + L.r);
     float* d_rt = (float*)(ws + L.rt);
     float* d_dtraw = (float*)(ws + L.dt_raw);
-    LC2IS_CUDA(cudaMemsetAsync(ws + L.r, 0, L.gbf - L.r, st));              // r, rt and dt_raw
+    const bool reuse = (flags & LC2IS_BWD_REUSE_PREP) != 0;
+    if (reuse && d_grad_t) return fail(LC2IS_ERR_ARG, "LC2IS_BWD_REUSE_PREP is for a dV-only call (d_grad_t must be NULL)%s");
+    if (!reuse) LC2IS_CUDA(cudaMemsetAsync(ws + L.r, 0, L.gbf - L.r, st));  // r, rt and dt_raw
 
     // ---- projections r, rt (and the bf16 operand copy of an fp32 gradient) -------------------------
-    const void* d_grad_logits_bf16 = d_grad_logits;
-    if (g_dtype == LC2IS_F32) {
-        d_grad_logits_bf16 = ws + L.gbf;
+    const void* d_grad_logits_bf16 = g_dtype == LC2IS_F32 ? (const void*)(ws + L.gbf) : d_grad_logits;
+    if (reuse) {
+        // projections / bf16 operand are in the workspace already
+    } else if (g_dtype == LC2IS_F32) {
         const int nblk = (hw + PREPF_PX - 1) / PREPF_PX;
         int px_blocks = nblk / 16;                           // >= 16 CTAs per image and class slice
         if (px_blocks < 1) px_blocks = 1;
@@ -578,4 +581,16 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, c
         LC2IS_CHECK_LAUNCH("k1b_dt_finish_kernel");
     }
     return 0;
+}
+
+extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, const float* d_logits,
+                                       const void* d_v_hat, const float* d_inv_norm_v,
+                                       const void* d_t_hat, const float* d_inv_norm_t,
+                                       int B, int hw, int D, int n_sets, int C,
+                                       int normalize, float logit_scale, const float* d_grad_scale,
+                                       void* d_grad_v, int gv_dtype, float* d_grad_t,
+                                       void* d_ws, lc2is_stream_t stream) {
+    return lc2is_cosine_logits_bwd_ex(d_grad_logits, g_dtype, d_logits, d_v_hat, d_inv_norm_v, d_t_hat, d_inv_norm_t, B, hw,
+                                      D, n_sets, C, normalize, logit_scale, d_grad_scale, d_grad_v, gv_dtype, d_grad_t,
+                                      d_ws, stream, 0);
 }

@@ -153,16 +153,26 @@ class HeadStep:
         if w_valid is not None:
             w_valid.wait()                                        # stream-level wait, no host sync
         check(lib.lc2is_mean_scale(ptr(self.n_valid), 1.0, ptr(self.gscale), st), "mean_scale")
-        if self.backward:
+        w_b = None
+        if self.backward and dist_on:
+            # data-parallel: prototype gradient first, its all-reduce hides behind the patch-gradient GEMM
+            args = (ptr(self.grad_low), F32, ptr(self.logits), ptr(self.v_hat), ptr(self.inv_v), ptr(self.t_hat),
+                    ptr(self.inv_t), B, hw, D, 1, C, int(self.normalize), self.logit_scale, ptr(self.gscale))
+            check(lib.lc2is_cosine_logits_bwd_ex(*args, None, BF16, ptr(self.grad_t), ptr(self.bwd_ws), st, 0),
+                  "cosine_logits_bwd(dT)")
+            self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
+            w_b = dp.allreduce_sum_async(self.bucket.flat)
+            check(lib.lc2is_cosine_logits_bwd_ex(*args, ptr(self.grad_v), BF16, None, ptr(self.bwd_ws), st, 1),
+                  "cosine_logits_bwd(dV)")
+        elif self.backward:
             check(lib.lc2is_cosine_logits_bwd(ptr(self.grad_low), F32, ptr(self.logits), ptr(self.v_hat),
                                               ptr(self.inv_v), ptr(self.t_hat), ptr(self.inv_t), B, hw, D, 1, C,
                                               int(self.normalize), self.logit_scale, ptr(self.gscale),
                                               ptr(self.grad_v), BF16, ptr(self.grad_t), ptr(self.bwd_ws), st),
                   "cosine_logits_bwd")
-        w_b = None
-        if dist_on:
-            self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
-            w_b = dp.allreduce_sum_async(self.bucket.flat)       # ... and hides behind K3
+        elif dist_on:
+            self.bucket.views[1].copy_(self.loss_sum)
+            w_b = dp.allreduce_sum_async(self.bucket.flat)
         self._mark("K3 argmax+confmat")
         if self.fused:
             pass                                                  # done inside the fused kernel
