@@ -119,3 +119,36 @@ def test_config5_open_vocab_shape_against_eager_torch():
     # ... and the fp32 reference logits for K1 (bf16 operands: 4e-3 absolute)
     ref_low = O.cosine_logits(v.float(), t, hw_shape=(h, h))
     assert float((step.logits.cpu() - ref_low).abs().max()) < 4e-3
+
+
+def test_new_entries_reject_unsupported_geometries_loudly():
+    """The split / fused / packed entries are specialised (power-of-two scales); anything else must come back as an
+    error code with a message - never a silent fallback."""
+    from lc2is_b200 import _lib
+    lib = _lib.lib
+    assert lib.lc2is_ce_split_supported(32, 32, 512, 512) == 1 and lib.lc2is_ce_split_supported(16, 16, 128, 128) == 1
+    assert lib.lc2is_ce_split_supported(32, 32, 128, 128) == 0 and lib.lc2is_ce_split_supported(13, 13, 37, 37) == 0
+    assert lib.lc2is_ce_argmax_fused_supported(150, 32, 32, 512, 512) == 1
+    assert lib.lc2is_ce_argmax_fused_supported(847, 64, 64, 1024, 1024) == 0       # tap tile too large
+    assert lib.lc2is_ce_argmax_fused_supported(150, 16, 16, 128, 128) == 0         # x8
+    low = torch.zeros(1, 5, 8, 8, device=DEV)
+    lab = torch.zeros(1, 32, 32, dtype=torch.int64, device=DEV)                    # x4
+    pk = torch.zeros(1, 32, 32, dtype=torch.uint16, device=DEV)
+    ls = torch.zeros(1, dtype=torch.float64, device=DEV)
+    cm = torch.zeros(5, 5, dtype=torch.int64, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.lc2is_upsample_ce_packed(low.data_ptr(), pk.data_ptr(), 1, 5, 8, 8, 32, 32, ls.data_ptr(), None, st) == -4
+    assert "scale" in _lib.last_error()
+    assert lib.lc2is_ce_argmax_fused_packed(low.data_ptr(), pk.data_ptr(), 1, 5, 8, 8, 32, 32, ls.data_ptr(), None, 1,
+                                            cm.data_ptr(), None, None, st) == -4
+    assert lib.lc2is_argmax_confmat_lowres_packed(low.data_ptr(), 1, 5, 8, 8, 32, 32, pk.data_ptr(), cm.data_ptr(), None,
+                                                  None, st) == -4
+    assert lib.lc2is_pack_labels(lab.data_ptr(), 7, 5, 0, pk.data_ptr(), None, st) == -2          # n % 8
+    assert lib.lc2is_upsample_ce_packed(None, pk.data_ptr(), 1, 5, 2, 2, 32, 32, ls.data_ptr(), None, st) == -1
+    # the x4 geometry still works end to end through the general entries (HeadStep picks them itself)
+    step = HeadStep(1, 8, 8, 32, 32, 5, ignore_index=0)
+    assert not step.split and not step.fused
+    v = synthetic.make_patch_embeddings(1, 64, 512).to(DEV)
+    step(v, synthetic.make_prototypes(5, 512).to(DEV), torch.randint(0, 5, (1, 32, 32), device=DEV))
+    torch.cuda.synchronize()
+    assert torch.isfinite(step.loss).all() and int(step.confmat.sum()) == 32 * 32
