@@ -76,6 +76,12 @@ int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int hw, int D,
                             void* d_v_hat, float* d_inv_norm_v, float* d_logits,
                             lc2is_stream_t stream);
 
+/* TextToPatch.visual / .textual forward (model/text_patch.py:11-12,16-17): y[M,N] = x[M,K] W[N,K]^T + b[N] on the
+ * logits GEMM's tcgen05 / TMEM / TMA pipeline.  x, W bf16 (W in nn.Linear's own [out,in] layout), b fp32 or NULL,
+ * y bf16 or fp32 row major.  K % 64 == 0, N % 16 == 0. */
+int lc2is_linear_fwd(const void* d_x_bf16, const void* d_w_bf16, const float* d_bias,
+                     long long M, int N, int K, void* d_y, int y_dtype, lc2is_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K1b cosine_logits_bwd.  Replaces autograd of the K1 lines (loss.backward(), engine.py:100).
  * d_grad_logits: dL/dlogits, g_dtype LC2IS_BF16: [B, C_pad, hw] bf16 (rows C..C_pad-1 zero; K2's

@@ -112,12 +112,18 @@ constexpr int K1_A_BYTES = K1_BM * K1_BK * 2;
 constexpr int K1_MAX_STAGES = 8;
 
 struct K1Params {
-    float* out;            // [B, C, hw]
+    float* out;            // EPI 0: [B, C, hw] fp32 (class-plane major)
+    void* out_rm;          // EPI 1: [M, C] row major, bf16 or fp32
+    const float* bias;     // EPI 1: [C] or null
+    int out_f32;           // EPI 1
     int B, hw, C, C_pad, n_sets;
     int NB, n_ntiles, tiles_per_img, num_kb, stages;
     float scale;
 };
 
+// EPI 0: the cosine-logits epilogue (class-plane major fp32).  EPI 1: the linear-projection epilogue of
+// TextToPatch.visual (model/text_patch.py:12,17): row-major out[m, n] = acc + bias[n], bf16 or fp32.
+template <int EPI>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const K1Params P) {
@@ -214,10 +220,31 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint32_t r[16];
                 tc::tmem_ld16(taddr + col, r);
                 tc::tmem_ld_wait();
+                if constexpr (EPI == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = n0 + col + j;
-                    if (rvalid && c < P.C) __stcs(orow + (size_t)c * P.hw, __uint_as_float(r[j]) * P.scale);
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = n0 + col + j;
+                        if (rvalid && c < P.C) __stcs(orow + (size_t)c * P.hw, __uint_as_float(r[j]) * P.scale);
+                    }
+                } else if (rvalid) {
+                    // row-major: lane = row, 16 consecutive output channels (C % 16 == 0 for this epilogue)
+                    const size_t m = (size_t)b * P.hw + p;
+                    float o[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        o[j] = __uint_as_float(r[j]) * P.scale + (P.bias ? __ldg(P.bias + n0 + col + j) : 0.f);
+                    if (P.out_f32) {
+                        float4* op = reinterpret_cast<float4*>((float*)P.out_rm + m * P.C + n0 + col);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    } else {
+                        __nv_bfloat162 pk[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pk[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+                        uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)P.out_rm + m * P.C + n0 + col);
+                        op[0] = *reinterpret_cast<uint4*>(&pk[0]);
+                        op[1] = *reinterpret_cast<uint4*>(&pk[4]);
+                    }
                 }
             }
             tc::tc_fence_before();
@@ -330,7 +357,8 @@ extern "C" int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int 
 
     // ---- K1: GEMM ------------------------------------------------------------------------------------
     K1Params P;
-    P.out = d_logits; P.B = B; P.hw = hw; P.C = C; P.C_pad = class_pad(C); P.n_sets = n_sets;
+    P.out = d_logits; P.out_rm = nullptr; P.bias = nullptr; P.out_f32 = 0;
+    P.B = B; P.hw = hw; P.C = C; P.C_pad = class_pad(C); P.n_sets = n_sets;
     const int n_ntiles0 = (P.C_pad + 255) / 256;
     P.NB = ((P.C_pad + n_ntiles0 - 1) / n_ntiles0 + 15) / 16 * 16;
     P.n_ntiles = (P.C_pad + P.NB - 1) / P.NB;
@@ -348,11 +376,54 @@ extern "C" int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int 
     CUtensorMap tmA, tmB;
     if (int e = make_tmap_2d_bf16(&tmA, d_v_hat, (uint64_t)M, (uint64_t)D, K1_BM, K1_BK)) return e;
     if (int e = make_tmap_2d_bf16(&tmB, d_t_hat, (uint64_t)n_sets * P.C_pad, (uint64_t)D, P.NB, K1_BK)) return e;
-    LC2IS_CUDA(cudaFuncSetAttribute(k1_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LC2IS_CUDA(cudaFuncSetAttribute(k1_logits_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_tiles = B * P.tiles_per_img * P.n_ntiles;
     int grid = sm_count();
     if (grid > total_tiles) grid = total_tiles;
-    k1_logits_kernel<<<grid, K1_THREADS, smem, st>>>(tmA, tmB, P);
+    k1_logits_kernel<0><<<grid, K1_THREADS, smem, st>>>(tmA, tmB, P);
     LC2IS_CHECK_LAUNCH("k1_logits_kernel");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// TextToPatch.visual / .textual forward (model/text_patch.py:11-12,16-17): y = x W^T + b on the same tcgen05 / TMEM /
+// TMA pipeline as the logits GEMM (A = x [M,K] bf16 K-major, B = W [N,K] bf16 K-major - nn.Linear's own layout).
+extern "C" int lc2is_linear_fwd(const void* d_x_bf16, const void* d_w_bf16, const float* d_bias,
+                                long long M, int N, int K, void* d_y, int y_dtype, lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (!d_x_bf16 || !d_w_bf16 || !d_y) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (M < 0 || N <= 0 || K <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (K % K1_BK) return fail(LC2IS_ERR_SHAPE, "K must be a multiple of 64 (got %s%lld)", "", K);
+    if (N % 16) return fail(LC2IS_ERR_SHAPE, "N must be a multiple of 16 (got %s%lld)", "", N);
+    if (M > 0x7fffffffLL / 2) return fail(LC2IS_ERR_SHAPE, "M too large%s");
+    if (y_dtype != LC2IS_F32 && y_dtype != LC2IS_BF16) return fail(LC2IS_ERR_ARG, "y_dtype%s");
+    if (((uintptr_t)d_x_bf16 | (uintptr_t)d_w_bf16 | (uintptr_t)d_y) % 16) return fail(LC2IS_ERR_ARG, "pointers must be 16-byte aligned%s");
+    if (M == 0) return 0;
+    K1Params P;
+    P.out = nullptr; P.out_rm = d_y; P.bias = d_bias; P.out_f32 = y_dtype == LC2IS_F32;
+    P.B = 1; P.hw = (int)M; P.C = N; P.C_pad = N; P.n_sets = 1;
+    const int n_ntiles0 = (N + 255) / 256;
+    P.NB = ((N + n_ntiles0 - 1) / n_ntiles0 + 15) / 16 * 16;
+    P.n_ntiles = (N + P.NB - 1) / P.NB;
+    P.tiles_per_img = (int)((M + K1_BM - 1) / K1_BM);
+    P.num_kb = K / K1_BK;
+    P.scale = 1.f;
+    const int stage_bytes = K1_A_BYTES + P.NB * 128;
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > K1_MAX_STAGES) stages = K1_MAX_STAGES;
+    if (stages > P.num_kb * 2) stages = P.num_kb * 2;
+    if (stages < 2) stages = 2;
+    P.stages = stages;
+    size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    if (smem < 120 * 1024) smem = 120 * 1024;
+    CUtensorMap tmA, tmB;
+    if (int e = make_tmap_2d_bf16(&tmA, d_x_bf16, (uint64_t)M, (uint64_t)K, K1_BM, K1_BK)) return e;
+    if (int e = make_tmap_2d_bf16(&tmB, d_w_bf16, (uint64_t)N, (uint64_t)K, P.NB, K1_BK)) return e;
+    LC2IS_CUDA(cudaFuncSetAttribute(k1_logits_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int total_tiles = P.tiles_per_img * P.n_ntiles;
+    int grid = sm_count();
+    if (grid > total_tiles) grid = total_tiles;
+    k1_logits_kernel<1><<<grid, K1_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, P);
+    LC2IS_CHECK_LAUNCH("k1_logits_kernel<linear>");
     return 0;
 }

@@ -44,6 +44,20 @@ def proto_normalize(t: Tensor, normalize: bool = True) -> Tuple[Tensor, Tensor]:
     return t_hat, inv
 
 
+# ---- TextToPatch projection ------------------------------------------------------------------
+def linear_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, out_dtype=torch.bfloat16) -> Tensor:
+    """y = x W^T + b on the tcgen05 pipeline.  x [M,K] bf16, weight [N,K] bf16 (nn.Linear layout), bias fp32 [N]."""
+    x = _req(x, torch.bfloat16, "x")
+    weight = _req(weight, torch.bfloat16, "weight")
+    M, K = x.shape
+    N = weight.shape[0]
+    if bias is not None:
+        bias = _req(bias, torch.float32, "bias")
+    y = torch.empty(M, N, dtype=out_dtype, device=x.device)
+    check(lib.lc2is_linear_fwd(ptr(x), ptr(weight), ptr(bias), M, N, K, ptr(y), _dt(y), stream_ptr()), "lc2is_linear_fwd")
+    return y
+
+
 # ---- K1 -----------------------------------------------------------------------------------
 def cosine_logits_fwd(v: Tensor, t_hat: Tensor, C: int, hw_shape: Tuple[int, int], normalize: bool = True,
                       logit_scale: float = 1.0) -> Tuple[Tensor, Tensor, Tensor]:

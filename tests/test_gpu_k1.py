@@ -127,3 +127,40 @@ def test_fused_head_loss_matches_oracle():
     ev = float((vd.grad.cpu() - 0.4 * ref["grad_v"]).abs().max() / (0.4 * ref["grad_v"]).abs().max())
     et = float((td.grad.cpu() - 0.4 * ref["grad_t"]).abs().max() / (0.4 * ref["grad_t"]).abs().max())
     assert ev < 3e-2 and et < 3e-2, (ev, et)
+
+
+@pytest.mark.parametrize("M,K,N,out_dtype", [(300, 768, 512, torch.bfloat16), (1024, 768, 512, torch.float32),
+                                              (129, 64, 16, torch.float32), (5000, 384, 272, torch.bfloat16)])
+def test_linear_projection_gemm(M, K, N, out_dtype):
+    """lc2is_linear_fwd (TextToPatch.visual forward on the tcgen05 pipeline): against an fp32 matmul of the same
+    bf16-rounded operands (accumulation order only) and against the fp32 nn.Linear (bf16 operand rounding)."""
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) * K ** -0.5
+    b = torch.randn(N, generator=g)
+    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    y = ops.linear_fwd(xb.to(DEV), wb.to(DEV), b.to(DEV), out_dtype).float().cpu()
+    ref_same = xb.float() @ wb.float().t() + b
+    ref_fp32 = x @ w.t() + b
+    tol = 2e-5 if out_dtype == torch.float32 else 1.0 / 128          # bf16 output rounding
+    assert float((y - ref_same).abs().max()) <= tol * float(ref_same.abs().max())
+    assert float((y - ref_fp32).abs().max()) <= 2e-2 * float(ref_fp32.abs().max())
+
+
+def test_text_to_patch_module_matches_reference_module(golden_dir):
+    """TextToPatch (model/text_patch.py:4-18) with the reference's weights: same parameter names, text first, visual
+    projection forward on the tcgen05 GEMM, gradients through torch."""
+    from lc2is_b200.model.text_patch import TextToPatch
+    torch.manual_seed(3)
+    m = TextToPatch(768, 512, 512).to(DEV)
+    assert sorted(k for k, _ in m.named_parameters()) == ["textual.bias", "textual.weight", "visual.bias", "visual.weight"]
+    img = torch.randn(2, 64, 768, device=DEV, requires_grad=True)
+    text = torch.randn(151, 512, device=DEV)
+    t_f, v_f = m(img, text)
+    assert t_f.shape == (151, 512) and v_f.shape == (2, 64, 512)
+    ref_v = torch.nn.functional.linear(img, m.visual.weight, m.visual.bias)
+    assert float((v_f - ref_v).abs().max()) <= 2e-2 * float(ref_v.abs().max())
+    v_f.square().mean().backward()
+    ref_g = torch.autograd.grad(ref_v.square().mean(), [img, m.visual.weight, m.visual.bias])
+    for got, ref in ((img.grad, ref_g[0]), (m.visual.weight.grad, ref_g[1]), (m.visual.bias.grad, ref_g[2])):
+        assert float((got - ref).abs().max()) <= 3e-2 * float(ref.abs().max())
