@@ -284,6 +284,8 @@ def run_b200(a):
             for i in range(1, n):
                 hv, hl = host_sets[(first + i) % nset]
                 hstep.submit(hv, t_pin, hl)
+                if i + 1 < n:                               # loader-style prefetch: the library's host threads pack the
+                    hstep.prefetch(host_sets[(first + i + 1) % nset][1])   # next batch's labels while this thread waits
                 out = hstep.wait()
                 finish(out)
             out = hstep.wait()
@@ -323,8 +325,9 @@ def run_b200(a):
         e2e = {"value": world * B * e_steps / (ms_pipe * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": hstep.h2d_bytes, "d2h_bytes_per_step": hstep.d2h_bytes,
                "steps": e_steps, "ms_per_step": ms_pipe / e_steps,
-               "api": "lc2is_head_step_host_submit / _wait, 2 steps in flight (pinned host buffers in: bf16 V, "
-                      "fp32 T, int64 labels narrowed to uint16 by the library's host threads; loss/n_valid/confmat out)",
+               "api": "lc2is_head_step_host_submit / _wait, 2 steps in flight, labels of the next batch packed in the "
+                      "background (lc2is_pack_labels_host_begin/_end); pinned host buffers in: bf16 V, fp32 T, int64 labels "
+                      "narrowed to uint16 by the library's host threads; loss/n_valid/confmat out",
                "blocking_call": {"api": "lc2is_head_step_host", "ms_per_step": ms_block / e_steps,
                                  "value": world * B * e_steps / (ms_block * 1e-3)}}
 

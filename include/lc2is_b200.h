@@ -174,6 +174,11 @@ int lc2is_ce_labels_prepass_packed(const uint16_t* d_labels_packed, int B, int C
 /* HOST function: narrow an int64 label map (host memory) to the packed uint16 form on the library's
  * worker threads (see lc2is_pack_threads).  Blocks until done. */
 int lc2is_pack_labels_host(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index, uint16_t* h_out);
+/* Asynchronous form for a prefetching loader: _begin returns at once, _end blocks until the labels are packed and
+ * releases the handle.  lc2is_head_step_host[_submit] accept labels packed this way: h_labels = NULL, h_scratch = them. */
+int lc2is_pack_labels_host_begin(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index, uint16_t* h_out,
+                                 void** handle);
+int lc2is_pack_labels_host_end(void* handle);
 /* number of worker threads the packing pool uses (hardware threads / LOCAL_WORLD_SIZE - 2, 1..12) */
 int lc2is_pack_threads(void);
 int lc2is_upsample_ce_packed(const float* d_low, const uint16_t* d_labels_packed,
@@ -218,11 +223,12 @@ int lc2is_argmax_confmat_lowres_packed(const float* d_low, int N, int C, int h, 
 int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W);
 int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* d_labels_packed,
                                  int B, int C, int h, int w, int H, int W,
-                                 double* d_loss_sum, float* d_grad_low, int onehot,
+                                 double* d_loss_sum, float* d_grad_low, int onehot, int64_t* d_n_valid,
                                  int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                  lc2is_stream_t stream);
 /* onehot != 0: the argmax warps also add the un-scaled -onehot term to d_grad_low (they hold the row's labels
- * anyway), so the labels only need packing + counting ahead of the kernel:
+ * anyway), so the labels only need packing + counting ahead of the kernel (d_n_valid != NULL: the CE warps count too -
+ * for labels that arrive packed from the host):
  * lc2is_pack_labels: int64 [n] -> packed uint16 [n] (same encoding as lc2is_ce_labels_prepass), n_valid += #counted.
  * n % 8 == 0. */
 int lc2is_pack_labels(const int64_t* d_labels, int64_t n, int C, int64_t ignore_index,

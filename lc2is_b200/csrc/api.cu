@@ -51,8 +51,6 @@ __global__ void finalize_loss_kernel(const double* loss_sum, const long long* n_
     *out = (float)(*loss_sum / (double)(*n_valid));
 }
 
-__global__ void set_i64_kernel(long long* p, long long v) { *p = v; }
-
 }  // namespace lc2is
 
 using namespace lc2is;
@@ -205,6 +203,25 @@ inline void pack_wait(std::atomic<int>* pending) {
 
 extern "C" int lc2is_pack_threads(void) { return pack_threads_default(); }
 
+// Asynchronous form: begin returns at once (the pool packs in the background), end blocks until done.
+extern "C" int lc2is_pack_labels_host_begin(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index,
+                                            uint16_t* h_out, void** handle) {
+    if (!handle) return fail(LC2IS_ERR_ARG, "handle is NULL%s");
+    if (n < 0 || C <= 0 || C >= 0x7fff) return fail(LC2IS_ERR_SHAPE, "bad n / C%s");
+    if (!h_labels || !h_out) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    std::atomic<int>* pending = new std::atomic<int>(0);
+    if (n > 0) pack_submit(h_labels, h_out, (size_t)n, C, ignore_index, pending);
+    *handle = (void*)pending;
+    return 0;
+}
+extern "C" int lc2is_pack_labels_host_end(void* handle) {
+    if (!handle) return fail(LC2IS_ERR_ARG, "handle is NULL%s");
+    std::atomic<int>* pending = (std::atomic<int>*)handle;
+    pack_wait(pending);
+    delete pending;
+    return 0;
+}
+
 extern "C" int lc2is_pack_labels_host(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index,
                                       uint16_t* h_out) {
     if (n < 0 || C <= 0 || C >= 0x7fff) return fail(LC2IS_ERR_SHAPE, "bad n / C%s");
@@ -259,7 +276,7 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
                              void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
                              uint16_t* h_scratch, int n_chunks, bool async) {
     if (int e = ensure_device()) return e;
-    if (!h_v || !h_t || !h_labels || !h_out_loss || !h_out_n_valid || !h_out_confmat || !d_ws)
+    if (!h_v || !h_t || (!h_labels && !h_scratch) || !h_out_loss || !h_out_n_valid || !h_out_confmat || !d_ws)
         return fail(LC2IS_ERR_ARG, "null pointer%s");
     if (B <= 0) return fail(LC2IS_ERR_SHAPE, "B must be positive%s");
     cudaStream_t st = (cudaStream_t)stream;
@@ -296,6 +313,8 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
     // With a pinned scratch buffer the int64 labels are narrowed to the packed uint16 form on the host
     // (worker pool), chunk by chunk ahead of the copies: 2 bytes per pixel cross PCIe instead of 8.
     const bool hpack = split && h_scratch != nullptr && C < 0x7fff;
+    const bool prepacked = h_labels == nullptr;             // h_scratch already holds the packed labels
+    if (prepacked && !hpack) return fail(LC2IS_ERR_UNSUPPORTED, "pre-packed labels need a split-path geometry (scale 8 / 16)%s");
     constexpr int MAXCH = 8;
     // chunks: a blocking call overlaps copy and compute inside the step (2 chunks with packed labels, 4 with
     // int64 labels: the copy is the longest stage there); a submitted step overlaps with its neighbours and
@@ -312,14 +331,13 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
     const int nchunk = piped ? (B < want_chunks ? B : want_chunks) : 1;
     const int bc = (B + nchunk - 1) / nchunk;
     std::atomic<int> pack_pending[MAXCH];
-    std::atomic<long long> pack_counted{0};
-    if (hpack)
+    for (int i = 0; i < MAXCH; ++i) pack_pending[i].store(0);
+    if (hpack && !prepacked)
         for (int i = 0; i < nchunk; ++i) {
             const int b0 = i * bc, nb = (b0 + bc <= B ? bc : B - b0);
-            pack_pending[i].store(0);
             if (nb > 0)
                 pack_submit(h_labels + (size_t)b0 * H * W, h_scratch + (size_t)b0 * H * W, (size_t)nb * H * W, C,
-                            ignore_index, &pack_pending[i], &pack_counted);
+                            ignore_index, &pack_pending[i]);
         }
     cudaEvent_t ev_start = nullptr, ev_copy[MAXCH] = {};
     auto cleanup = [&]() {
@@ -391,8 +409,9 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
                                         d_vhat + v_off, d_invv + (size_t)b0 * hw, lg, stream));
         mark("k1", st);
         if (fused) {
-            STEP_RC(lc2is_ce_argmax_fused_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, 1, d_cm,
-                                                 nullptr, nullptr, stream));
+            // (labels packed on the host arrive un-counted: the CE warps count them)
+            STEP_RC(lc2is_ce_argmax_fused_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, 1,
+                                                 hpack ? d_nvalid : nullptr, d_cm, nullptr, nullptr, stream));
         } else if (split) {
             STEP_RC(lc2is_upsample_ce_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, stream));
             STEP_RC(lc2is_argmax_confmat_lowres_packed(lg, nb, C, h, w, H, W, d_packed + lab_off, d_cm, nullptr,
@@ -405,10 +424,6 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         }
     }
     mark("k2k3", st);
-    if (fused && hpack) {            // the host threads counted the valid labels while packing
-        set_i64_kernel<<<1, 1, 0, st>>>((long long*)d_nvalid, pack_counted.load());
-        lc2is::g_launches.fetch_add(1, std::memory_order_relaxed);
-    }
     STEP_RC(lc2is_mean_scale(d_nvalid, 1.0f, d_gscale, stream));
     if (do_backward) {
         STEP_CUDA(cudaMemsetAsync(ws + L.grad_t, 0, (size_t)C * D * 4, st));

@@ -103,6 +103,7 @@ struct K2SParams {
     long long ignore_index;
     int B, C, h, w, H, W;
     int nty, ntx;                 // warp tiles per image
+    unsigned long long* n_valid;  // SPLIT: += number of counted pixels (null = the caller counted them already)
 };
 
 template <int S, bool SPLIT>
@@ -222,6 +223,14 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, boo
     cp_async_wait_all();
     if constexpr (CTA_SYNC) __syncthreads(); else __syncwarp();
     if (!active) return;                                    // (after the barrier)
+    if constexpr (SPLIT) {
+        if (P.n_valid != nullptr) {                             // valid count of the warp's strips: one reduction per warp
+            int cnt = __popc(vm);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (lane == 0 && cnt) atomicAdd(P.n_valid, (unsigned long long)cnt);
+        }
+    }
 
     const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
     const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);

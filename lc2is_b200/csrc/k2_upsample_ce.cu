@@ -756,7 +756,7 @@ extern "C" int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_la
     // ---- strip path: s = 8 / 16 -----------------------------------------------------------------------
     if (fast && s >= 8 && ((uintptr_t)d_labels % 16) == 0) {
         K2SParams P;
-        P.low = d_low; P.labels = (const long long*)d_labels; P.labels16 = nullptr; P.grad_low = d_grad_low;
+        P.low = d_low; P.labels = (const long long*)d_labels; P.labels16 = nullptr; P.n_valid = nullptr; P.grad_low = d_grad_low;
         P.loss_sum = d_loss_sum; P.grad_scale = d_grad_scale; P.ignore_index = ignore_index;
         P.B = B; P.C = C; P.h = h; P.w = w; P.H = H; P.W = W;
         // warps are independent; a warp's tile of taps takes C * (32 / (s/2)) * 16 bytes of shared memory
@@ -920,7 +920,7 @@ extern "C" int lc2is_upsample_ce_packed(const float* d_low, const uint16_t* d_la
     if (!fast_scale(h, w, H, W, &s) || (s != 8 && s != 16))
         return fail(LC2IS_ERR_UNSUPPORTED, "split path needs scale 8 or 16 (see lc2is_ce_split_supported)%s");
     K2SParams P;
-    P.low = d_low; P.labels = nullptr; P.labels16 = d_labels_packed; P.grad_low = d_grad_low;
+    P.low = d_low; P.labels = nullptr; P.labels16 = d_labels_packed; P.n_valid = nullptr; P.grad_low = d_grad_low;
     P.loss_sum = d_loss_sum; P.grad_scale = nullptr; P.ignore_index = 0;
     P.B = B; P.C = C; P.h = h; P.w = w; P.H = H; P.W = W;
     const size_t smem_warp = (size_t)(C + 2) * (64 / s) * 16;

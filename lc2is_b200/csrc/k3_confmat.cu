@@ -940,7 +940,8 @@ using namespace lc2is;
 
 // K2 (split form) + K3 fused for the x16 geometry: d_loss_sum += sum(lse - target logit); d_grad_low ACCUMULATES the
 // un-scaled softmax term (or NULL) - and, with onehot != 0, the -onehot term as well (then the labels only need
-// lc2is_pack_labels, not the label prepass); d_confmat / d_per_image ACCUMULATE; d_pred optional.
+// lc2is_pack_labels, not the label prepass); d_n_valid (optional) += #counted pixels, for labels that were packed without
+// counting; d_confmat / d_per_image ACCUMULATE; d_pred optional.
 extern "C" int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W) {
     int s = 0;
     if (!fast_scale(h, w, H, W, &s) || s != 16) return 0;
@@ -950,7 +951,7 @@ extern "C" int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W
 
 extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* d_labels_packed,
                                             int B, int C, int h, int w, int H, int W,
-                                            double* d_loss_sum, float* d_grad_low, int onehot,
+                                            double* d_loss_sum, float* d_grad_low, int onehot, int64_t* d_n_valid,
                                             int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                             lc2is_stream_t stream) {
     if (int e = ensure_device()) return e;
@@ -962,6 +963,7 @@ extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* 
         return fail(LC2IS_ERR_UNSUPPORTED, "fused K2+K3 needs scale 16 and a class count whose tap tile fits three CTAs per SM%s");
     K2SParams P2;
     P2.low = d_low; P2.labels = nullptr; P2.labels16 = d_labels_packed; P2.grad_low = d_grad_low;
+    P2.n_valid = (unsigned long long*)d_n_valid;
     P2.loss_sum = d_loss_sum; P2.grad_scale = nullptr; P2.ignore_index = 0;
     P2.B = B; P2.C = C; P2.h = h; P2.w = w; P2.H = H; P2.W = W;
     P2.nty = (h + 1 + 1) / 2; P2.ntx = (w + 1 + 1) / 2;

@@ -238,7 +238,7 @@ def pack_labels(labels: Tensor, C: int, ignore_index: int, n_valid: Optional[Ten
 
 def ce_argmax_fused(low: Tensor, labels_packed: Tensor, size: Tuple[int, int], loss_sum: Tensor, grad: Optional[Tensor],
                     confmat: Optional[Tensor] = None, per_image: bool = False, want_pred: bool = False,
-                    onehot: bool = False):
+                    onehot: bool = False, n_valid: Optional[Tensor] = None):
     """Fused K2 (split form) + K3 for the x16 geometry: accumulates into loss_sum / grad (un-scaled softmax term) /
     confmat.  -> (confmat, per_image | None, pred | None)."""
     low = _req(low, torch.float32, "low")
@@ -250,6 +250,6 @@ def ce_argmax_fused(low: Tensor, labels_packed: Tensor, size: Tuple[int, int], l
     pi = torch.zeros(N, 3, C, dtype=torch.int64, device=dev) if per_image else None
     pred = torch.empty(N, H, W, dtype=torch.int64, device=dev) if want_pred else None
     check(lib.lc2is_ce_argmax_fused_packed(ptr(low), ptr(labels_packed), N, C, h, w, H, W, ptr(loss_sum), ptr(grad),
-                                           int(onehot), ptr(confmat), ptr(pi), ptr(pred), stream_ptr()),
+                                           int(onehot), ptr(n_valid), ptr(confmat), ptr(pi), ptr(pred), stream_ptr()),
           "lc2is_ce_argmax_fused_packed")
     return confmat, pi, pred

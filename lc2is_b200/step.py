@@ -139,7 +139,7 @@ class HeadStep:
             self.k2_events[0].record()
         if self.fused:
             check(lib.lc2is_ce_argmax_fused_packed(ptr(self.logits), ptr(self.labels_packed), B, C, h, w, H, W,
-                                                   ptr(self.loss_sum), glow, 1, ptr(self.confmat), None, None, st),
+                                                   ptr(self.loss_sum), glow, 1, None, ptr(self.confmat), None, None, st),
                   "ce_argmax_fused_packed")
         elif self.split:
             check(lib.lc2is_upsample_ce_packed(ptr(self.logits), ptr(self.labels_packed), B, C, h, w, H, W,
@@ -197,8 +197,10 @@ class HostStep:
 
     ``hs(v, t, labels)`` blocks until the results are in ``out_loss / out_n_valid / out_confmat``.
     ``hs.submit(v, t, labels)`` / ``hs.wait()`` keep up to ``depth`` steps in flight (each with its own
-    workspace, scratch and output buffers), so the copy of the next batch overlaps the kernels of the
-    previous one, like a prefetching data loader; ``wait()`` returns the oldest step's (loss, n_valid, confmat)."""
+    workspace and output buffers), so the copy of the next batch overlaps the kernels of the previous one, like a
+    prefetching data loader; ``wait()`` returns the oldest step's (loss, n_valid, confmat).  ``hs.prefetch(labels)``
+    starts the host-side packing of the next batch's labels in the background (otherwise submit() packs them itself,
+    blocking the caller for that long)."""
 
     class _Slot:
         def __init__(self, nbytes, B, H, W, C, dev, host_pack):
@@ -206,7 +208,6 @@ class HostStep:
             self.out_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
             self.out_n_valid = torch.zeros(1, dtype=torch.int64).pin_memory()
             self.out_confmat = torch.zeros(C, C, dtype=torch.int64).pin_memory()
-            self.h_scratch = torch.empty(B, H, W, dtype=torch.uint16).pin_memory() if host_pack else None
             self.event = None
             self.keep = None
 
@@ -222,6 +223,12 @@ class HostStep:
         self.host_pack = bool(host_pack and lib.lc2is_ce_split_supported(h, w, H, W) and C < 0x7fff
                               and lib.lc2is_pack_threads() >= 4)
         self.slots = [HostStep._Slot(nbytes, B, H, W, C, dev, self.host_pack) for _ in range(max(1, depth))]
+        # pinned scratch for the packed labels: one more than the steps in flight, so that the labels of the NEXT batch
+        # can be packed (prefetch) while all slots are busy
+        self._scratch = [torch.empty(B, H, W, dtype=torch.uint16).pin_memory() for _ in range(len(self.slots) + 1)] \
+            if self.host_pack else []
+        self._scr_next = 0
+        self._prefetched = None                     # (labels data_ptr, scratch index, pack handle)
         self.copy_stream = torch.cuda.Stream(device=dev) if pipelined else None
         self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + B * H * W * (2 if self.host_pack else 8)
         self.d2h_bytes = 4 + 8 + C * C * 8
@@ -231,6 +238,37 @@ class HostStep:
     def _set_outputs(self, s) -> None:
         self.out_loss, self.out_n_valid, self.out_confmat = s.out_loss, s.out_n_valid, s.out_confmat
 
+    def _take_scratch(self, h_labels):
+        """-> (scratch tensor | None, labels pointer | None): the packed labels if `h_labels` were prefetched."""
+        if not self.host_pack:
+            return None, ptr(h_labels)
+        if self._prefetched is not None and self._prefetched[0] == h_labels.data_ptr():
+            _, k, handle = self._prefetched
+            self._prefetched = None
+            check(lib.lc2is_pack_labels_host_end(handle), "lc2is_pack_labels_host_end")
+            return self._scratch[k], None                    # h_labels = NULL: h_scratch holds them
+        if self._prefetched is not None:                      # a prefetch for other labels: let it finish, drop it
+            check(lib.lc2is_pack_labels_host_end(self._prefetched[2]), "lc2is_pack_labels_host_end")
+            self._prefetched = None
+        k = self._scr_next
+        self._scr_next = (k + 1) % len(self._scratch)
+        return self._scratch[k], ptr(h_labels)
+
+    def prefetch(self, h_labels: torch.Tensor) -> None:
+        """Start packing the labels of the NEXT batch on the library's host threads (returns at once); the following
+        submit() / call with the same tensor uses the packed copy.  A data loader's prefetch."""
+        import ctypes
+        if not self.host_pack or self._prefetched is not None:
+            return
+        B, h, w, D, C, H, W = self.args
+        k = self._scr_next
+        self._scr_next = (k + 1) % len(self._scratch)
+        handle = ctypes.c_void_p()
+        check(lib.lc2is_pack_labels_host_begin(ptr(h_labels), h_labels.numel(), C, self.ignore_index,
+                                               ptr(self._scratch[k]), ctypes.byref(handle)), "lc2is_pack_labels_host_begin")
+        self._prefetched = (h_labels.data_ptr(), k, handle)
+        self._prefetch_keep = h_labels
+
     def _check_inputs(self, h_v, h_labels) -> None:
         assert h_v.dtype == torch.bfloat16 and not h_v.is_cuda and not h_labels.is_cuda
 
@@ -239,11 +277,12 @@ class HostStep:
         self._check_inputs(h_v, h_labels)
         assert not self._inflight, "wait() for the submitted steps first"
         s = self.slots[0]
-        check(lib.lc2is_head_step_host(ptr(h_v), ptr(h_t), ptr(h_labels), B, h, w, D, C, H, W, self.ignore_index,
+        scratch, lab_ptr = self._take_scratch(h_labels)
+        check(lib.lc2is_head_step_host(ptr(h_v), ptr(h_t), lab_ptr, B, h, w, D, C, H, W, self.ignore_index,
                                        self.logit_scale, int(self.backward), ptr(s.out_loss),
                                        ptr(s.out_n_valid), ptr(s.out_confmat), ptr(s.ws), stream_ptr(),
                                        self.copy_stream.cuda_stream if self.copy_stream is not None else None,
-                                       ptr(s.h_scratch)),
+                                       ptr(scratch)),
               "lc2is_head_step_host")
         self._set_outputs(s)
 
@@ -256,10 +295,11 @@ class HostStep:
         s = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
         ev = ctypes.c_void_p()
-        check(lib.lc2is_head_step_host_submit(ptr(h_v), ptr(h_t), ptr(h_labels), B, h, w, D, C, H, W, self.ignore_index,
+        scratch, lab_ptr = self._take_scratch(h_labels)
+        check(lib.lc2is_head_step_host_submit(ptr(h_v), ptr(h_t), lab_ptr, B, h, w, D, C, H, W, self.ignore_index,
                                               self.logit_scale, int(self.backward), ptr(s.out_loss),
                                               ptr(s.out_n_valid), ptr(s.out_confmat), ptr(s.ws), stream_ptr(),
-                                              self.copy_stream.cuda_stream, ptr(s.h_scratch), ctypes.byref(ev)),
+                                              self.copy_stream.cuda_stream, ptr(scratch), ctypes.byref(ev)),
               "lc2is_head_step_host_submit")
         s.event, s.keep = ev, (h_v, h_t, h_labels)          # host buffers must outlive the step
         self._inflight.append(s)

@@ -209,7 +209,10 @@ def test_fused_ce_argmax_kernel_matches_separate_kernels_and_oracle(N, C, h, ign
     g2 = torch.zeros_like(dl)
     packed2, nv2 = ops.pack_labels(dlab, C, ign)                 # pack + count only; -onehot comes from the argmax warps
     assert torch.equal(packed2, packed) and int(nv2) == int(n_valid)
-    cm, pi, pred = ops.ce_argmax_fused(dl, packed2, (H, H), ls2, g2, per_image=True, want_pred=True, onehot=True)
+    nv3 = torch.zeros(1, dtype=torch.int64, device=DEV)
+    cm, pi, pred = ops.ce_argmax_fused(dl, packed2, (H, H), ls2, g2, per_image=True, want_pred=True, onehot=True,
+                                       n_valid=nv3)
+    assert int(nv3) == int(n_valid)                              # the CE warps' own count (host-packed labels)
     assert abs(float(ls2) - float(loss_sum)) <= 1e-6 * abs(float(loss_sum))
     assert float((g2 - grad).abs().max()) <= 1e-5 * float(grad.abs().max())
     up = F.interpolate(low, mode="bilinear", scale_factor=s)

@@ -77,8 +77,10 @@ def test_submit_wait_pipeline_matches_blocking_call():
     got = []
     seq = [0, 1, 2, 0, 1, 2, 1]
     hs.submit(batches[seq[0]][0], t, batches[seq[0]][1])
-    for k in seq[1:]:
+    for j, k in enumerate(seq[1:], start=1):
         hs.submit(batches[k][0], t, batches[k][1])
+        if j + 1 < len(seq) and j % 2 == 0:                    # every other batch: labels packed in the background
+            hs.prefetch(batches[seq[j + 1]][1])
         l, nv, cm = hs.wait()
         got.append((float(l), int(nv), cm.clone()))
     l, nv, cm = hs.wait()
@@ -139,7 +141,7 @@ def test_new_entries_reject_unsupported_geometries_loudly():
     st = torch.cuda.current_stream().cuda_stream
     assert lib.lc2is_upsample_ce_packed(low.data_ptr(), pk.data_ptr(), 1, 5, 8, 8, 32, 32, ls.data_ptr(), None, st) == -4
     assert "scale" in _lib.last_error()
-    assert lib.lc2is_ce_argmax_fused_packed(low.data_ptr(), pk.data_ptr(), 1, 5, 8, 8, 32, 32, ls.data_ptr(), None, 1,
+    assert lib.lc2is_ce_argmax_fused_packed(low.data_ptr(), pk.data_ptr(), 1, 5, 8, 8, 32, 32, ls.data_ptr(), None, 1, None,
                                             cm.data_ptr(), None, None, st) == -4
     assert lib.lc2is_argmax_confmat_lowres_packed(low.data_ptr(), 1, 5, 8, 8, 32, 32, pk.data_ptr(), cm.data_ptr(), None,
                                                   None, st) == -4
