@@ -247,7 +247,8 @@ int lc2is_pack_labels(const int64_t* d_labels, int64_t n, int C, int64_t ignore_
  *   of chunk i+1 overlaps the kernels of chunk i (the 1/N_valid scale is applied at the end, in K1b).
  * h_scratch: optional PINNED host buffer of B*H*W uint16 (NULL = none).  With it (and a power-of-two scale
  *   8 / 16) the int64 labels are narrowed to the packed 2-byte form on the library's host worker threads,
- *   chunk by chunk ahead of the copies, so a quarter of the label bytes cross PCIe.
+ *   chunk by chunk ahead of the copies, so a quarter of the label bytes cross PCIe.  h_labels == NULL: h_scratch
+ *   already holds the packed labels (lc2is_pack_labels_host / _begin + _end, or a loader that writes them itself).
  */
 int64_t lc2is_head_step_workspace(int B, int hw, int D, int C, int H, int W);
 int lc2is_head_step_host(const void* h_v, const float* h_t, const int64_t* h_labels,
