@@ -235,6 +235,30 @@ int lc2is_pack_labels(const int64_t* d_labels, int64_t n, int C, int64_t ignore_
                       uint16_t* d_labels_packed, int64_t* d_n_valid, lc2is_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K4  ContrastiveLoss on the low-resolution logits.  Replaces model/loss.py:39-64
+ *       loss_visual  = CrossEntropyLoss(out [B,C,h,w], labels [B,h,w])            (class axis, ignore_index)
+ *       loss_textual = CrossEntropyLoss(out [B,h,w,C], one_hot(labels,151).float()) (torch takes dim 1 = the image-row
+ *                      axis as the class axis; 'mean' = / (B*w*C))
+ *     and their autograd backward.
+ * d_out      [B, h*w, C] fp32 (the reference's `outputs`), C <= 160.
+ * d_labels   [B, h, w] int64 at the SAME resolution.
+ * d_col_lse / d_col_cnt  [B, w, C] fp32 workspaces written by _fwd and read by _bwd (log-sum-exp over y, and the
+ *            number of rows whose label is c, per column).
+ * d_loss_sums [2] double ACCUMULATED: { sum over counted pixels of the visual CE, un-normalised textual sum }.
+ * d_counts   [2] int64 ACCUMULATED: { counted pixels (label != ignore_index), labels outside [0,C) - F.one_hot raises
+ *            on those in the reference; the Python mirror raises when the second counter is non-zero }.
+ * _bwd: d_coef DEVICE float[2] = { c_visual, c_textual }: d_grad [B,h*w,C] (overwritten) =
+ *            c_visual * d(visual sum)/d out + c_textual * d(textual sum)/d out; for the reference's
+ *            (loss_textual + loss_visual)/2 pass { 0.5/n_counted, 0.5/(B*w*C) }.
+ */
+int lc2is_contrastive_fwd(const float* d_out, const int64_t* d_labels, int B, int h, int w, int C,
+                          int64_t ignore_index, float* d_col_lse, float* d_col_cnt,
+                          double* d_loss_sums, int64_t* d_counts, lc2is_stream_t stream);
+int lc2is_contrastive_bwd(const float* d_out, const int64_t* d_labels, int B, int h, int w, int C,
+                          int64_t ignore_index, const float* d_col_lse, const float* d_col_cnt,
+                          const float* d_coef, float* d_grad, lc2is_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * Whole step from HOST buffers (the end-to-end path bench.py times as `e2e`).  Replaces one
  * iteration of Engine.train_loop / eval_loop over the head (engine.py:75-101,145-163):
  * H2D of the batch, K0..K3, D2H of loss / n_valid / confusion matrix.  Synchronises

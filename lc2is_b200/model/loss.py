@@ -4,14 +4,13 @@
 size + softmax cross-entropy + their backward in one pass, with no upsampled tensor in memory.
 It is also the drop-in for ``nn.CrossEntropyLoss`` applied to ``F.interpolate(score, 'bilinear')``
 (final.py:44 + engine.py:94): feed it the low-resolution score map instead.
-``ContrastiveLoss`` / ``NPairLoss`` (loss.py:23-64) are kept as plain PyTorch (next).
+``ContrastiveLoss`` (loss.py:39-64) runs on the K4 kernels for CUDA inputs (class-axis CE per pixel + the row-axis
+CE against the one-hot target, forward and backward); ``NPairLoss`` (loss.py:23-37) is kept as plain PyTorch.
 """
 from typing import Callable, Optional, Union
 
 import numpy as np
 import torch
-import torch.nn.functional as F
-from einops import rearrange
 from torch import Tensor, nn
 
 from .. import ops
@@ -73,21 +72,62 @@ class NPairLoss(nn.Module):
         return res
 
 
+class _ContrastiveCE(torch.autograd.Function):
+    """Both cross-entropies of loss.py:58-59 on the K4 kernels.  -> (total, loss_visual, loss_textual)."""
+
+    @staticmethod
+    def forward(ctx, outputs: Tensor, labels: Tensor, ignore_index: int):
+        out32 = outputs.float().contiguous()
+        B, hw, C = out32.shape
+        w = labels.shape[2]
+        sums, counts, col_lse, col_cnt = ops.contrastive_fwd(out32, labels, ignore_index)
+        n_counted, n_bad = counts.tolist()            # one sync, like F.one_hot's own range check (loss.py:54)
+        if n_bad:
+            raise RuntimeError("Class values must be smaller than num_classes.")
+        n_text = float(B * w * C)
+        loss_visual = (sums[0] / n_counted if n_counted else sums[0] * float("nan")).float()
+        loss_textual = (sums[1] / n_text).float()
+        ctx.save_for_backward(out32, labels, col_lse, col_cnt)
+        ctx.meta = (ignore_index, n_counted, n_text, outputs.dtype)
+        return (loss_textual + loss_visual) / 2, loss_visual, loss_textual
+
+    @staticmethod
+    def backward(ctx, g_total: Tensor, g_visual: Tensor, g_textual: Tensor):
+        out32, labels, col_lse, col_cnt = ctx.saved_tensors
+        ignore_index, n_counted, n_text, in_dtype = ctx.meta
+        coef = torch.stack([(0.5 * g_total + g_visual) / max(n_counted, 1),
+                            (0.5 * g_total + g_textual) / n_text]).float()
+        grad = ops.contrastive_bwd(out32, labels, ignore_index, col_lse, col_cnt, coef)
+        return grad.to(in_dtype), None, None
+
+
 class ContrastiveLoss(nn.Module):
-    """loss.py:39-64 (PyTorch pass-through, including the 151-way one-hot whose class axis is the
-    image-row axis, loss.py:51-60)."""
+    """loss.py:39-64, including the 151-way one-hot whose class axis torch takes to be the image-row axis
+    (loss.py:51-60).  forward(outputs [B, h*w, 151], labels [B, h, w]) -> (total, loss_visual, loss_textual).
+
+    Runs on the K4 kernels (CUDA tensors only - like AuxiliaryLoss there is deliberately no PyTorch / CPU fallback);
+    covers the default criterion options (no class weights, no label smoothing, reduction 'mean')."""
+
+    NUM_CLASSES = 151        # hard-coded in the reference (loss.py:54)
 
     def __init__(self, weight: Optional[Tensor] = None, size_average=None, ignore_index: int = -100, reduce=None,
                  reduction: str = 'mean', label_smoothing: float = 0) -> None:
         super().__init__()
         self.criterion = nn.CrossEntropyLoss(weight, size_average, ignore_index, reduce, reduction, label_smoothing)
+        if weight is not None or label_smoothing != 0 or self.criterion.reduction != "mean":
+            raise NotImplementedError(
+                "the B200 ContrastiveLoss kernels cover no class weights, no label smoothing, reduction 'mean'; "
+                "there is deliberately no silent PyTorch fallback")
 
     def forward(self, outputs: Tensor, labels: Tensor):
-        H = int(np.sqrt(outputs.shape[1]).item())
-        out_textual = rearrange(outputs, "b (h w) c -> b h w c", h=H)
-        out_visual = rearrange(outputs.transpose(-2, -1), "b c (h w) -> b c h w", h=H)
-        label_textual = F.one_hot(labels, num_classes=151).float()
-        label_visual = labels
-        loss_textual = self.criterion(input=out_textual, target=label_textual)
-        loss_visual = self.criterion(input=out_visual, target=label_visual)
-        return (loss_textual + loss_visual) / 2, loss_visual, loss_textual
+        if self.criterion.ignore_index >= 0:
+            # what the reference's textual term raises (torch: probabilities target + non-negative ignore_index)
+            raise RuntimeError("ignore_index is not supported for floating point target")
+        side = int(np.sqrt(outputs.shape[1]).item())                      # loss.py:47
+        if outputs.dim() != 3 or labels.dim() != 3 or side * side != outputs.shape[1]:
+            raise ValueError("ContrastiveLoss: outputs must be [B, h*h, C] and labels [B, h, h]")
+        if tuple(labels.shape) != (outputs.shape[0], side, side) or outputs.shape[2] != self.NUM_CLASSES:
+            # the reference fails here too: the one-hot target [B,h,w,151] must have the shape of the [B,h,w,C] view
+            raise ValueError(f"ContrastiveLoss: labels {tuple(labels.shape)} / outputs {tuple(outputs.shape)} do not "
+                             f"give a [B,h,w,{self.NUM_CLASSES}] one-hot target of the outputs' shape (loss.py:51-58)")
+        return _ContrastiveCE.apply(outputs, labels, self.criterion.ignore_index)

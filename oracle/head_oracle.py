@@ -14,6 +14,9 @@ Pinning status
   make_golden.py`` imports the reference's own ``model.loss.AuxiliaryLoss`` and
   ``model.text_patch.TextToPatch`` and restates ``model/final.py:41-44`` verbatim;
   ``tests/test_oracle_golden.py`` checks this oracle against those fixtures bit-for-bit.
+* ``contrastive_loss``: pinned against the reference's own ``model.loss.ContrastiveLoss`` (fixture
+  ``tests/golden/contrastive.pt``: three losses + autograd gradient; fp32 tolerance, the restatement sums in another
+  order than ``nn.CrossEntropyLoss``).
 * confusion matrix / IoU (``jaccard_*``): **parity unpinned**.  The reference delegates
   to ``torchmetrics.JaccardIndex`` (un-vendored, version unpinned: requirements.txt:1
   is a placeholder; the ``JaccardIndex(num_classes=..)`` call form without ``task=``
@@ -26,6 +29,7 @@ Pinning status
 """
 from __future__ import annotations
 
+import math
 from typing import List, Optional, Sequence
 
 import torch
@@ -131,6 +135,26 @@ def cosine_logits_backward(v: Tensor, t: Tensor, grad_logits: Tensor, normalize:
 # --------------------------------------------------------------------------------------
 # Stage 3: argmax + confusion matrix + mIoU                 (metrics.py:61-134)
 # --------------------------------------------------------------------------------------
+def contrastive_loss(outputs: Tensor, labels: Tensor, ignore_index: int = -100, num_classes: int = 151):
+    """model/loss.py:45-64 restated term by term (no nn.CrossEntropyLoss call, so that the row-axis softmax of the
+    'textual' term is explicit).  outputs [B, h*w, C], labels [B, h, w] -> (total, loss_visual, loss_textual).
+
+    loss.py:50-51: out_textual = [B,h,w,C] view, out_visual = [B,C,h,w]; :54 one-hot float target [B,h,w,151];
+    :58 CE(out_textual, one-hot): probabilities target, class axis = dim 1 (the image-row axis), 'mean' = divide by
+    B * w * C; :59 CE(out_visual, labels): class-index target with ignore_index, mean over counted pixels."""
+    B, hw, C = outputs.shape
+    h = int(math.isqrt(hw))
+    o = outputs.view(B, h, hw // h, C)
+    onehot = F.one_hot(labels, num_classes=num_classes).to(outputs.dtype)        # raises on labels outside [0,151)
+    logp_rows = o - torch.logsumexp(o, dim=1, keepdim=True)                         # softmax over y
+    loss_textual = -(onehot * logp_rows).sum() / (B * (hw // h) * C)
+    logp_cls = o - torch.logsumexp(o, dim=3, keepdim=True)                          # softmax over classes
+    counted = labels != ignore_index
+    picked = logp_cls.gather(3, labels.clamp(0, C - 1).unsqueeze(-1)).squeeze(-1)
+    loss_visual = -(picked * counted).sum() / counted.sum()
+    return (loss_textual + loss_visual) / 2, loss_visual, loss_textual
+
+
 def argmax_reference(logits: Tensor) -> Tensor:
     """What ``JaccardIndex`` sees in the reference: ``argmax(Softmax2d(x), dim=class)``
     (metrics.py:92 feeds ``softmax2D(output)``; torchmetrics argmaxes float preds).

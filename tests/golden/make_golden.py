@@ -109,6 +109,24 @@ def main():
     torch.save(dict(outputs=out, labels=lab, pred=pred, confmats=cms,
                     miou_label=float(sum(per_img) / len(per_img)), miou_global=float(sum(gi) / len(gi))),
                os.path.join(OUT, "metrics_small.pt"))
+    # ---- 5. ContrastiveLoss (reference class, loss.py:39-64) fwd + autograd bwd of the total ----------------
+    from model.loss import ContrastiveLoss
+    g5 = torch.Generator().manual_seed(1029)
+    cases = {}
+    for name, (b, hh, ign, hi) in {
+        "h8": (2, 8, -100, 151),                      # ignore_index >= 0 raises in the reference (float target)
+        "h6_ign_m1": (1, 6, -1, 151),
+        "h16_few_classes": (2, 16, -100, 5),          # long label runs: several rows of a column share a class
+    }.items():
+        out = (torch.randn(b, hh * hh, 151, generator=g5) * 3).requires_grad_(True)
+        lab = torch.randint(0, hi, (b, hh, hh), generator=g5)
+        total, lv, lt = ContrastiveLoss(ignore_index=ign)(out, lab)
+        total.backward()
+        cases[name] = dict(outputs=out.detach().clone(), labels=lab, ignore_index=ign, total=total.detach().clone(),
+                           loss_visual=lv.detach().clone(), loss_textual=lt.detach().clone(),
+                           grad=out.grad.detach().clone())
+    torch.save(cases, os.path.join(OUT, "contrastive.pt"))
+
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         if f.endswith(".pt"):

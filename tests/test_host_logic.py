@@ -57,12 +57,26 @@ def test_auxiliary_loss_rejects_unsupported_options():
 
 
 def test_passthrough_losses_run():
-    out = torch.randn(2, 16, 151)
-    lab = torch.randint(0, 4, (2, 4, 4))
-    l, lv, lt = ContrastiveLoss()(out, lab)
-    assert l.shape == () and torch.isfinite(l)
     r = NPairLoss()(torch.rand(4, 8), torch.rand(3, 8), torch.rand(5, 8))
     assert r.shape == ()
+
+
+def test_contrastive_loss_surface():
+    from lc2is_b200._lib import Lc2isError
+    with pytest.raises(NotImplementedError):
+        ContrastiveLoss(label_smoothing=0.1)
+    with pytest.raises(NotImplementedError):
+        ContrastiveLoss(reduction="sum")
+    with pytest.raises(RuntimeError, match="floating point target"):     # same as the reference's criterion
+        ContrastiveLoss(ignore_index=0)(torch.randn(2, 16, 151), torch.randint(0, 4, (2, 4, 4)))
+    crit = ContrastiveLoss()
+    assert crit.criterion.ignore_index == -100
+    with pytest.raises(ValueError):                      # C != 151: the reference's one-hot target cannot match
+        crit(torch.randn(2, 16, 150), torch.randint(0, 4, (2, 4, 4)))
+    with pytest.raises(ValueError):                      # labels at another resolution
+        crit(torch.randn(2, 16, 151), torch.randint(0, 4, (2, 8, 8)))
+    with pytest.raises(Lc2isError):                      # no CPU path
+        crit(torch.randn(2, 16, 151), torch.randint(0, 4, (2, 4, 4)))
 
 
 def test_decoder_surface():
