@@ -242,8 +242,8 @@ int lc2is_pack_labels(const int64_t* d_labels, int64_t n, int C, int64_t ignore_
  *     and their autograd backward.
  * d_out      [B, h*w, C] fp32 (the reference's `outputs`), C <= 160.
  * d_labels   [B, h, w] int64 at the SAME resolution.
- * d_col_lse / d_col_cnt  [B, w, C] fp32 workspaces written by _fwd and read by _bwd (log-sum-exp over y, and the
- *            number of rows whose label is c, per column).
+ * d_col_lse / d_col_adj  [B, w, C] fp32 workspaces written by _fwd and read by _bwd: per column, the log-sum-exp over
+ *            y, and that minus ln(#rows whose label is c) (+inf where there is none).
  * d_loss_sums [2] double ACCUMULATED: { sum over counted pixels of the visual CE, un-normalised textual sum }.
  * d_counts   [2] int64 ACCUMULATED: { counted pixels (label != ignore_index), labels outside [0,C) - F.one_hot raises
  *            on those in the reference; the Python mirror raises when the second counter is non-zero }.
@@ -252,10 +252,10 @@ int lc2is_pack_labels(const int64_t* d_labels, int64_t n, int C, int64_t ignore_
  *            (loss_textual + loss_visual)/2 pass { 0.5/n_counted, 0.5/(B*w*C) }.
  */
 int lc2is_contrastive_fwd(const float* d_out, const int64_t* d_labels, int B, int h, int w, int C,
-                          int64_t ignore_index, float* d_col_lse, float* d_col_cnt,
+                          int64_t ignore_index, float* d_col_lse, float* d_col_adj,
                           double* d_loss_sums, int64_t* d_counts, lc2is_stream_t stream);
 int lc2is_contrastive_bwd(const float* d_out, const int64_t* d_labels, int B, int h, int w, int C,
-                          int64_t ignore_index, const float* d_col_lse, const float* d_col_cnt,
+                          int64_t ignore_index, const float* d_col_lse, const float* d_col_adj,
                           const float* d_coef, float* d_grad, lc2is_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------

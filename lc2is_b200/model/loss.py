@@ -80,24 +80,24 @@ class _ContrastiveCE(torch.autograd.Function):
         out32 = outputs.float().contiguous()
         B, hw, C = out32.shape
         w = labels.shape[2]
-        sums, counts, col_lse, col_cnt = ops.contrastive_fwd(out32, labels, ignore_index)
+        sums, counts, col_lse, col_adj = ops.contrastive_fwd(out32, labels, ignore_index)
         n_counted, n_bad = counts.tolist()            # one sync, like F.one_hot's own range check (loss.py:54)
         if n_bad:
             raise RuntimeError("Class values must be smaller than num_classes.")
         n_text = float(B * w * C)
         loss_visual = (sums[0] / n_counted if n_counted else sums[0] * float("nan")).float()
         loss_textual = (sums[1] / n_text).float()
-        ctx.save_for_backward(out32, labels, col_lse, col_cnt)
+        ctx.save_for_backward(out32, labels, col_lse, col_adj)
         ctx.meta = (ignore_index, n_counted, n_text, outputs.dtype)
         return (loss_textual + loss_visual) / 2, loss_visual, loss_textual
 
     @staticmethod
     def backward(ctx, g_total: Tensor, g_visual: Tensor, g_textual: Tensor):
-        out32, labels, col_lse, col_cnt = ctx.saved_tensors
+        out32, labels, col_lse, col_adj = ctx.saved_tensors
         ignore_index, n_counted, n_text, in_dtype = ctx.meta
         coef = torch.stack([(0.5 * g_total + g_visual) / max(n_counted, 1),
                             (0.5 * g_total + g_textual) / n_text]).float()
-        grad = ops.contrastive_bwd(out32, labels, ignore_index, col_lse, col_cnt, coef)
+        grad = ops.contrastive_bwd(out32, labels, ignore_index, col_lse, col_adj, coef)
         return grad.to(in_dtype), None, None
 
 

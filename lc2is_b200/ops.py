@@ -258,7 +258,7 @@ def ce_argmax_fused(low: Tensor, labels_packed: Tensor, size: Tuple[int, int], l
 def contrastive_fwd(outputs: Tensor, labels: Tensor, ignore_index: int):
     """K4 forward (loss.py:39-64).  outputs [B, h*w, C] fp32, labels [B, h, w] int64.
     -> (loss_sums double[2] = {visual sum, textual sum}, counts int64[2] = {counted pixels, out-of-range labels},
-        col_lse [B,w,C], col_cnt [B,w,C]) - no host sync."""
+        col_lse [B,w,C], col_adj [B,w,C] = col_lse - ln(#rows of the column labelled c)) - no host sync."""
     outputs = _req(outputs, torch.float32, "outputs")
     labels = _req(labels, torch.int64, "labels")
     B, hw, C = outputs.shape
@@ -267,14 +267,14 @@ def contrastive_fwd(outputs: Tensor, labels: Tensor, ignore_index: int):
         raise ValueError(f"labels {tuple(labels.shape)} do not match outputs {tuple(outputs.shape)}")
     dev = outputs.device
     col = torch.empty(2, B, w, C, dtype=torch.float32, device=dev)
-    sums = torch.zeros(2, dtype=torch.float64, device=dev)
-    counts = torch.zeros(2, dtype=torch.int64, device=dev)
+    acc = torch.zeros(4, dtype=torch.int64, device=dev)             # one memset: {sums (as double), counts}
+    sums, counts = acc[:2].view(torch.float64), acc[2:]
     check(lib.lc2is_contrastive_fwd(ptr(outputs), ptr(labels), B, h, w, C, int(ignore_index), ptr(col[0]), ptr(col[1]),
                                     ptr(sums), ptr(counts), stream_ptr()), "lc2is_contrastive_fwd")
     return sums, counts, col[0], col[1]
 
 
-def contrastive_bwd(outputs: Tensor, labels: Tensor, ignore_index: int, col_lse: Tensor, col_cnt: Tensor,
+def contrastive_bwd(outputs: Tensor, labels: Tensor, ignore_index: int, col_lse: Tensor, col_adj: Tensor,
                     coef: Tensor) -> Tensor:
     """K4 backward: coef float32[2] (device) = {c_visual, c_textual}; -> grad [B, h*w, C] fp32."""
     outputs = _req(outputs, torch.float32, "outputs")
@@ -283,6 +283,6 @@ def contrastive_bwd(outputs: Tensor, labels: Tensor, ignore_index: int, col_lse:
     B, hw, C = outputs.shape
     _, h, w = labels.shape
     grad = torch.empty_like(outputs)
-    check(lib.lc2is_contrastive_bwd(ptr(outputs), ptr(labels), B, h, w, C, int(ignore_index), ptr(col_lse), ptr(col_cnt),
+    check(lib.lc2is_contrastive_bwd(ptr(outputs), ptr(labels), B, h, w, C, int(ignore_index), ptr(col_lse), ptr(col_adj),
                                     ptr(coef), ptr(grad), stream_ptr()), "lc2is_contrastive_bwd")
     return grad
