@@ -327,7 +327,7 @@ def run_b200(a):
                "steps": e_steps, "ms_per_step": ms_pipe / e_steps,
                "api": "lc2is_head_step_host_submit / _wait, 2 steps in flight, labels of the next batch packed in the "
                       "background (lc2is_pack_labels_host_begin/_end); pinned host buffers in: bf16 V, fp32 T, int64 labels "
-                      "narrowed to uint16 by the library's host threads; loss/n_valid/confmat out",
+                      "narrowed to 1 byte (C <= 254) by the library's host threads and widened on the device; loss/n_valid/confmat out",
                "blocking_call": {"api": "lc2is_head_step_host", "ms_per_step": ms_block / e_steps,
                                  "value": world * B * e_steps / (ms_block * 1e-3)}}
 

@@ -168,17 +168,24 @@ int lc2is_ce_labels_prepass(const int64_t* d_labels,
                             int B, int C, int h, int w, int H, int W, int64_t ignore_index,
                             uint16_t* d_labels_packed, int64_t* d_n_valid,
                             float* d_grad_low, lc2is_stream_t stream);
-/* Same as lc2is_ce_labels_prepass for labels that are already packed (lc2is_pack_labels_host). */
+/* Same as lc2is_ce_labels_prepass for labels that are already in the packed uint16 form. */
 int lc2is_ce_labels_prepass_packed(const uint16_t* d_labels_packed, int B, int C, int h, int w, int H, int W,
                                    int64_t* d_n_valid, float* d_grad_low, lc2is_stream_t stream);
-/* HOST function: narrow an int64 label map (host memory) to the packed uint16 form on the library's
- * worker threads (see lc2is_pack_threads).  Blocks until done. */
-int lc2is_pack_labels_host(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index, uint16_t* h_out);
+/* HOST function: narrow an int64 label map (host memory) to the library's HOST label form on its worker threads (see
+ * lc2is_pack_threads).  Blocks until done.  The host form has lc2is_host_label_bytes(C) bytes per label: 1 for
+ * C <= 254 (class id; 0xFE = label == ignore_index; 0xFF = outside [0,C)), else 2 (the packed uint16 form above).
+ * The whole-step entries take it as `h_scratch`; on the device the one-byte form is widened by lc2is_expand_labels. */
+int lc2is_host_label_bytes(int C);
+int lc2is_pack_labels_host(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index, void* h_out);
 /* Asynchronous form for a prefetching loader: _begin returns at once, _end blocks until the labels are packed and
  * releases the handle.  lc2is_head_step_host[_submit] accept labels packed this way: h_labels = NULL, h_scratch = them. */
-int lc2is_pack_labels_host_begin(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index, uint16_t* h_out,
+int lc2is_pack_labels_host_begin(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index, void* h_out,
                                  void** handle);
 int lc2is_pack_labels_host_end(void* handle);
+/* DEVICE: one-byte host form [n] -> packed uint16 [n]; n_valid += #counted labels (NULL = don't count).  n % 16 == 0,
+ * C <= 254. */
+int lc2is_expand_labels(const uint8_t* d_labels8, int64_t n, int C, int64_t ignore_index,
+                        uint16_t* d_labels_packed, int64_t* d_n_valid, lc2is_stream_t stream);
 /* number of worker threads the packing pool uses (hardware threads / LOCAL_WORLD_SIZE - 2, 1..12) */
 int lc2is_pack_threads(void);
 int lc2is_upsample_ce_packed(const float* d_low, const uint16_t* d_labels_packed,
@@ -269,9 +276,9 @@ int lc2is_contrastive_bwd(const float* d_out, const int64_t* d_labels, int B, in
  * do_backward: also run K1b (gradients stay on the device, in the workspace).
  * copy_stream: optional second stream (NULL = none): the batch is then cut into chunks and the H2D copy
  *   of chunk i+1 overlaps the kernels of chunk i (the 1/N_valid scale is applied at the end, in K1b).
- * h_scratch: optional PINNED host buffer of B*H*W uint16 (NULL = none).  With it (and a power-of-two scale
- *   8 / 16) the int64 labels are narrowed to the packed 2-byte form on the library's host worker threads,
- *   chunk by chunk ahead of the copies, so a quarter of the label bytes cross PCIe.  h_labels == NULL: h_scratch
+ * h_scratch: optional PINNED host buffer of B*H*W*lc2is_host_label_bytes(C) bytes (NULL = none).  With it (and a
+ *   power-of-two scale 8 / 16) the int64 labels are narrowed to the 1- or 2-byte host form on the library's host
+ *   worker threads, chunk by chunk ahead of the copies, so an eighth / a quarter of the label bytes cross PCIe.  h_labels == NULL: h_scratch
  *   already holds the packed labels (lc2is_pack_labels_host / _begin + _end, or a loader that writes them itself).
  */
 int64_t lc2is_head_step_workspace(int B, int hw, int D, int C, int H, int W);
@@ -280,7 +287,7 @@ int lc2is_head_step_host(const void* h_v, const float* h_t, const int64_t* h_lab
                          int64_t ignore_index, float logit_scale, int do_backward,
                          float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                          void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                         uint16_t* h_scratch);
+                         void* h_scratch);
 
 /* The same step without the final synchronisation: everything (host-side label packing, H2D, kernels, D2H
  * of the results) is enqueued and *done_event receives a handle; lc2is_head_step_host_wait blocks until that
@@ -293,7 +300,7 @@ int lc2is_head_step_host_submit(const void* h_v, const float* h_t, const int64_t
                                 int64_t ignore_index, float logit_scale, int do_backward,
                                 float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                                 void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                                uint16_t* h_scratch, void** done_event);
+                                void* h_scratch, void** done_event);
 int lc2is_head_step_host_wait(void* done_event);
 
 #ifdef __cplusplus

@@ -71,6 +71,8 @@ SIGNATURES = {
     "lc2is_head_step_host_wait": (c_int, [_p]),
     "lc2is_ce_labels_prepass_packed": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p]),
     "lc2is_pack_threads": (c_int, []),
+    "lc2is_host_label_bytes": (c_int, [c_int]),
+    "lc2is_expand_labels": (c_int, [_p, c_int64, c_int, c_int64, _p, _p, _p]),
     "lc2is_contrastive_fwd": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int64, _p, _p, _p, _p, _p]),
     "lc2is_contrastive_bwd": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int64, _p, _p, _p, _p, _p]),
     "lc2is_pack_labels_host_begin": (c_int, [_p, c_int64, c_int, c_int64, _p, POINTER(c_void_p)]),

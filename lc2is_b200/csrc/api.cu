@@ -56,7 +56,7 @@ __global__ void finalize_loss_kernel(const double* loss_sum, const long long* n_
 using namespace lc2is;
 
 extern "C" const char* lc2is_last_error(void) { return g_err; }
-extern "C" int lc2is_abi_version(void) { return 2; }
+extern "C" int lc2is_abi_version(void) { return 3; }
 extern "C" int64_t lc2is_launch_count(void) { return g_launches.load(); }
 
 extern "C" int lc2is_mean_scale(const int64_t* d_n_valid, float mult, float* d_scale, lc2is_stream_t stream) {
@@ -79,7 +79,8 @@ extern "C" int lc2is_finalize_loss(const double* d_loss_sum, const int64_t* d_n_
 // ---------------------------------------------------------------------------------------------
 // Host-side label packing (the reference hands int64 label maps over in host memory: data/collator.py:91;
 // 8 bytes per pixel would make the PCIe copy of the labels the longest stage of the step).  Same encoding as
-// k2_labels_prepass_kernel: class id; bit 15 = label == ignore_index; 0xFFFF = outside [0,C).
+// k2_labels_prepass_kernel: class id; bit 15 = label == ignore_index; 0xFFFF = outside [0,C) - or, for C <= 254, one
+// byte per label (below).
 namespace {
 // (every variant returns the number of COUNTED labels: a class id other than ignore_index)
 long long pack_labels_scalar(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
@@ -125,15 +126,110 @@ long long pack_labels_avx2(const int64_t* src, uint16_t* dst, size_t n, int C, i
     _mm_sfence();
     return cnt + pack_labels_scalar(src + i, dst + i, n - i, C, ign);
 }
-long long pack_labels_range(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+// One-byte host form for C <= 254 (half the PCIe bytes again; expanded to the 2-byte form on the device by
+// lc2is_expand_labels): class id; 0xFE = label == ignore_index (a class id); 0xFF = outside [0,C).
+long long pack_labels8_scalar(const int64_t* src, uint8_t* dst, size_t n, int C, int64_t ign) {
+    long long cnt = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t v = (uint64_t)src[i];
+        const bool inr = v < (uint64_t)C;
+        dst[i] = !inr ? (uint8_t)0xFF : (src[i] == ign ? (uint8_t)0xFE : (uint8_t)v);
+        cnt += inr && src[i] != ign;
+    }
+    return cnt;
+}
+__attribute__((target("avx2,popcnt")))
+long long pack_labels8_avx2(const int64_t* src, uint8_t* dst, size_t n, int C, int64_t ign) {
+    long long cnt = 0;
+    const __m256i vC = _mm256_set1_epi64x((long long)C - 1), vign = _mm256_set1_epi64x(ign);
+    const __m256i zero = _mm256_setzero_si256(), ff = _mm256_set1_epi64x(0xFF), fe = _mm256_set1_epi64x(0xFE);
+    const __m256i idx = _mm256_setr_epi32(0, 2, 4, 6, 0, 2, 4, 6);
+    const bool aligned = ((uintptr_t)dst % 16) == 0;
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        __m128i q[4];
+        for (int k = 0; k < 4; ++k) {
+            const __m256i v = _mm256_loadu_si256((const __m256i*)(src + i + 4 * k));
+            const __m256i bad = _mm256_or_si256(_mm256_cmpgt_epi64(zero, v), _mm256_cmpgt_epi64(v, vC));
+            const __m256i isign = _mm256_cmpeq_epi64(v, vign);
+            cnt += 4 - __builtin_popcount((unsigned)_mm256_movemask_pd(_mm256_castsi256_pd(_mm256_or_si256(bad, isign))));
+            __m256i r = _mm256_blendv_epi8(v, fe, isign);
+            r = _mm256_blendv_epi8(r, ff, bad);
+            q[k] = _mm256_castsi256_si128(_mm256_permutevar8x32_epi32(r, idx));   // low 32 bits of the 4 lanes
+        }
+        const __m128i o = _mm_packus_epi16(_mm_packus_epi32(q[0], q[1]), _mm_packus_epi32(q[2], q[3]));
+        if (aligned) _mm_stream_si128((__m128i*)(dst + i), o);       // read next by the copy engine, not by this core
+        else _mm_storeu_si128((__m128i*)(dst + i), o);
+    }
+    _mm_sfence();
+    return cnt + pack_labels8_scalar(src + i, dst + i, n - i, C, ign);
+}
+// AVX-512 forms: vpmovqb / vpmovqw narrow eight labels per instruction and the range / ignore tests are mask
+// compares - about one instruction per label instead of three, which is what bounds a core on this path.
+__attribute__((target("avx512f,avx512bw,avx512vl,popcnt")))
+long long pack_labels8_avx512(const int64_t* src, uint8_t* dst, size_t n, int C, int64_t ign) {
+    long long cnt = 0;
+    const __m512i vC = _mm512_set1_epi64((long long)C), vign = _mm512_set1_epi64(ign);
+    const __m128i fe = _mm_set1_epi8((char)0xFE), ff = _mm_set1_epi8((char)0xFF);
+    const bool aligned = ((uintptr_t)dst % 16) == 0;
+    size_t i = 0;
+    for (; i + 16 <= n; i += 16) {
+        const __m512i a = _mm512_loadu_si512((const void*)(src + i)), b = _mm512_loadu_si512((const void*)(src + i + 8));
+        // unsigned v >= C: outside [0,C), negatives included
+        const unsigned bad = (unsigned)_mm512_cmpge_epu64_mask(a, vC) | ((unsigned)_mm512_cmpge_epu64_mask(b, vC) << 8);
+        const unsigned ig = (unsigned)_mm512_cmpeq_epi64_mask(a, vign) | ((unsigned)_mm512_cmpeq_epi64_mask(b, vign) << 8);
+        __m128i o = _mm_unpacklo_epi64(_mm512_cvtepi64_epi8(a), _mm512_cvtepi64_epi8(b));
+        o = _mm_mask_blend_epi8((__mmask16)ig, o, fe);
+        o = _mm_mask_blend_epi8((__mmask16)bad, o, ff);
+        cnt += 16 - __builtin_popcount(bad | ig);
+        if (aligned) _mm_stream_si128((__m128i*)(dst + i), o);
+        else _mm_storeu_si128((__m128i*)(dst + i), o);
+    }
+    _mm_sfence();
+    return cnt + pack_labels8_scalar(src + i, dst + i, n - i, C, ign);
+}
+__attribute__((target("avx512f,avx512bw,avx512vl,popcnt")))
+long long pack_labels_avx512(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign) {
+    long long cnt = 0;
+    const __m512i vC = _mm512_set1_epi64((long long)C), vign = _mm512_set1_epi64(ign);
+    const __m128i flag = _mm_set1_epi16((short)0x8000), ffff = _mm_set1_epi16((short)0xFFFF);
+    const bool aligned = ((uintptr_t)dst % 16) == 0;
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        const __m512i a = _mm512_loadu_si512((const void*)(src + i));
+        const unsigned bad = (unsigned)_mm512_cmpge_epu64_mask(a, vC);
+        const unsigned ig = (unsigned)_mm512_cmpeq_epi64_mask(a, vign);
+        __m128i o = _mm512_cvtepi64_epi16(a);
+        o = _mm_mask_blend_epi16((__mmask8)ig, o, _mm_or_si128(o, flag));
+        o = _mm_mask_blend_epi16((__mmask8)bad, o, ffff);
+        cnt += 8 - __builtin_popcount(bad | ig);
+        if (aligned) _mm_stream_si128((__m128i*)(dst + i), o);
+        else _mm_storeu_si128((__m128i*)(dst + i), o);
+    }
+    _mm_sfence();
+    return cnt + pack_labels_scalar(src + i, dst + i, n - i, C, ign);
+}
+// bytes = 2: the packed uint16 form; bytes = 1: the one-byte host form
+long long pack_labels_range(const int64_t* src, void* dst, size_t n, int C, int64_t ign, int bytes) {
     static const bool have_avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt");
-    return have_avx2 ? pack_labels_avx2(src, dst, n, C, ign) : pack_labels_scalar(src, dst, n, C, ign);
+    static const bool have_avx512 = have_avx2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
+                                    __builtin_cpu_supports("avx512vl") && !getenv("LC2IS_NO_AVX512");
+    if (have_avx512)
+        return bytes == 1 ? pack_labels8_avx512(src, (uint8_t*)dst, n, C, ign)
+                          : pack_labels_avx512(src, (uint16_t*)dst, n, C, ign);
+    if (bytes == 1)
+        return have_avx2 ? pack_labels8_avx2(src, (uint8_t*)dst, n, C, ign) : pack_labels8_scalar(src, (uint8_t*)dst, n, C, ign);
+    return have_avx2 ? pack_labels_avx2(src, (uint16_t*)dst, n, C, ign) : pack_labels_scalar(src, (uint16_t*)dst, n, C, ign);
+}
+int host_label_bytes(int C) {
+    static const int forced = [] { const char* e = getenv("LC2IS_HOST_LABEL_BYTES"); return e ? atoi(e) : 0; }();
+    return (C <= 254 && forced != 2) ? 1 : 2;
 }
 
 // A small persistent worker pool (created on first use, joined at process exit).
 class PackPool {
 public:
-    struct Task { const int64_t* src; uint16_t* dst; size_t n; int C; int64_t ign; std::atomic<int>* pending;
+    struct Task { const int64_t* src; void* dst; size_t n; int C; int64_t ign; int bytes; std::atomic<int>* pending;
                   std::atomic<long long>* counted; };
     explicit PackPool(int nthreads) {
         for (int i = 0; i < nthreads; ++i) workers_.emplace_back([this] { run(); });
@@ -158,7 +254,7 @@ private:
                 if (q_.empty()) return;
                 t = q_.front(); q_.pop_front();
             }
-            const long long c = pack_labels_range(t.src, t.dst, t.n, t.C, t.ign);
+            const long long c = pack_labels_range(t.src, t.dst, t.n, t.C, t.ign, t.bytes);
             if (t.counted) t.counted->fetch_add(c, std::memory_order_relaxed);
             t.pending->fetch_sub(1, std::memory_order_release);
         }
@@ -176,16 +272,17 @@ int pack_threads_default() {
     const char* lws = getenv("LOCAL_WORLD_SIZE");
     const int ranks = lws ? atoi(lws) : 1;
     n = n / (ranks > 1 ? ranks : 1) - 2;
+    n = n < 1 ? 1 : (n > 12 ? 12 : n);
     const char* e = getenv("LC2IS_PACK_THREADS");
-    if (e) n = atoi(e);
-    return n < 1 ? 1 : (n > 12 ? 12 : n);
+    if (e && atoi(e) > 0) n = atoi(e) > 64 ? 64 : atoi(e);
+    return n;
 }
 PackPool& pack_pool() {
     static PackPool pool(pack_threads_default());
     return pool;
 }
 // split [0,n) into pieces for the pool; *pending counts the pieces still running
-void pack_submit(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign, std::atomic<int>* pending,
+void pack_submit(const int64_t* src, void* dst, size_t n, int C, int64_t ign, int bytes, std::atomic<int>* pending,
                  std::atomic<long long>* counted = nullptr) {
     PackPool& p = pack_pool();
     const int pieces = p.size();
@@ -194,7 +291,7 @@ void pack_submit(const int64_t* src, uint16_t* dst, size_t n, int C, int64_t ign
     for (size_t o = 0; o < n; o += per) ++cnt;
     pending->store(cnt, std::memory_order_relaxed);
     for (size_t o = 0; o < n; o += per)
-        p.submit({src + o, dst + o, per < n - o ? per : n - o, C, ign, pending, counted});
+        p.submit({src + o, (char*)dst + o * bytes, per < n - o ? per : n - o, C, ign, bytes, pending, counted});
 }
 inline void pack_wait(std::atomic<int>* pending) {
     while (pending->load(std::memory_order_acquire) > 0) _mm_pause();
@@ -202,15 +299,16 @@ inline void pack_wait(std::atomic<int>* pending) {
 }  // namespace
 
 extern "C" int lc2is_pack_threads(void) { return pack_threads_default(); }
+extern "C" int lc2is_host_label_bytes(int C) { return host_label_bytes(C); }
 
 // Asynchronous form: begin returns at once (the pool packs in the background), end blocks until done.
 extern "C" int lc2is_pack_labels_host_begin(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index,
-                                            uint16_t* h_out, void** handle) {
+                                            void* h_out, void** handle) {
     if (!handle) return fail(LC2IS_ERR_ARG, "handle is NULL%s");
     if (n < 0 || C <= 0 || C >= 0x7fff) return fail(LC2IS_ERR_SHAPE, "bad n / C%s");
     if (!h_labels || !h_out) return fail(LC2IS_ERR_ARG, "null pointer%s");
     std::atomic<int>* pending = new std::atomic<int>(0);
-    if (n > 0) pack_submit(h_labels, h_out, (size_t)n, C, ignore_index, pending);
+    if (n > 0) pack_submit(h_labels, h_out, (size_t)n, C, ignore_index, host_label_bytes(C), pending);
     *handle = (void*)pending;
     return 0;
 }
@@ -223,12 +321,12 @@ extern "C" int lc2is_pack_labels_host_end(void* handle) {
 }
 
 extern "C" int lc2is_pack_labels_host(const int64_t* h_labels, int64_t n, int C, int64_t ignore_index,
-                                      uint16_t* h_out) {
+                                      void* h_out) {
     if (n < 0 || C <= 0 || C >= 0x7fff) return fail(LC2IS_ERR_SHAPE, "bad n / C%s");
     if (n == 0) return 0;
     if (!h_labels || !h_out) return fail(LC2IS_ERR_ARG, "null pointer%s");
     std::atomic<int> pending{0};
-    pack_submit(h_labels, h_out, (size_t)n, C, ignore_index, &pending);
+    pack_submit(h_labels, h_out, (size_t)n, C, ignore_index, host_label_bytes(C), &pending);
     pack_wait(&pending);
     return 0;
 }
@@ -274,7 +372,7 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
                              int64_t ignore_index, float logit_scale, int do_backward,
                              float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                              void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                             uint16_t* h_scratch, int n_chunks, bool async) {
+                             void* h_scratch, int n_chunks, bool async) {
     if (int e = ensure_device()) return e;
     if (!h_v || !h_t || (!h_labels && !h_scratch) || !h_out_loss || !h_out_n_valid || !h_out_confmat || !d_ws)
         return fail(LC2IS_ERR_ARG, "null pointer%s");
@@ -314,6 +412,10 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
     // (worker pool), chunk by chunk ahead of the copies: 2 bytes per pixel cross PCIe instead of 8.
     const bool hpack = split && h_scratch != nullptr && C < 0x7fff;
     const bool prepacked = h_labels == nullptr;             // h_scratch already holds the packed labels
+    // host form of the packed labels: one byte per label for C <= 254 (expanded to uint16 on the device, next to the
+    // copy: lc2is_expand_labels), else the uint16 form itself
+    const int lb = hpack ? host_label_bytes(C) : 2;
+    uint8_t* d_lab8 = (uint8_t*)d_labels;                   // the int64 area of the workspace is free when hpack
     if (prepacked && !hpack) return fail(LC2IS_ERR_UNSUPPORTED, "pre-packed labels need a split-path geometry (scale 8 / 16)%s");
     constexpr int MAXCH = 8;
     // chunks: a blocking call overlaps copy and compute inside the step (2 chunks with packed labels, 4 with
@@ -336,8 +438,8 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         for (int i = 0; i < nchunk; ++i) {
             const int b0 = i * bc, nb = (b0 + bc <= B ? bc : B - b0);
             if (nb > 0)
-                pack_submit(h_labels + (size_t)b0 * H * W, h_scratch + (size_t)b0 * H * W, (size_t)nb * H * W, C,
-                            ignore_index, &pack_pending[i]);
+                pack_submit(h_labels + (size_t)b0 * H * W, (char*)h_scratch + (size_t)b0 * H * W * lb,
+                            (size_t)nb * H * W, C, ignore_index, lb, &pack_pending[i]);
         }
     cudaEvent_t ev_start = nullptr, ev_copy[MAXCH] = {};
     auto cleanup = [&]() {
@@ -376,8 +478,12 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
                                   cudaMemcpyHostToDevice, cst));
         if (hpack) {
             pack_wait(&pack_pending[i]);
-            STEP_CUDA(cudaMemcpyAsync(d_packed + lab_off, h_scratch + lab_off, (size_t)nb * H * W * 2,
-                                      cudaMemcpyHostToDevice, cst));
+            if (lb == 1)
+                STEP_CUDA(cudaMemcpyAsync(d_lab8 + lab_off, (const uint8_t*)h_scratch + lab_off, (size_t)nb * H * W,
+                                          cudaMemcpyHostToDevice, cst));
+            else
+                STEP_CUDA(cudaMemcpyAsync(d_packed + lab_off, (const uint16_t*)h_scratch + lab_off,
+                                          (size_t)nb * H * W * 2, cudaMemcpyHostToDevice, cst));
         } else {
             STEP_CUDA(cudaMemcpyAsync(d_labels + lab_off, h_labels + lab_off, (size_t)nb * H * W * 8,
                                       cudaMemcpyHostToDevice, cst));
@@ -392,6 +498,11 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         float* gl = do_backward ? d_glow + (size_t)b0 * C * hw : nullptr;
         // labels: the fused K2+K3 kernel only needs them packed and counted (its argmax warps add the -onehot term);
         // the separate kernels need the label prepass (count, packing, -onehot)
+        // (one-byte host labels: widened to the packed form and counted here)
+        const bool counted8 = hpack && lb == 1;
+        if (counted8)
+            STEP_RC(lc2is_expand_labels(d_lab8 + lab_off, (int64_t)nb * H * W, C, ignore_index, d_packed + lab_off,
+                                        fused ? d_nvalid : nullptr, stream));
         if (fused) {
             if (!hpack)
                 STEP_RC(lc2is_pack_labels(d_labels + lab_off, (int64_t)nb * H * W, C, ignore_index, d_packed + lab_off,
@@ -411,7 +522,7 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         if (fused) {
             // (labels packed on the host arrive un-counted: the CE warps count them)
             STEP_RC(lc2is_ce_argmax_fused_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, 1,
-                                                 hpack ? d_nvalid : nullptr, d_cm, nullptr, nullptr, stream));
+                                                 (hpack && !counted8) ? d_nvalid : nullptr, d_cm, nullptr, nullptr, stream));
         } else if (split) {
             STEP_RC(lc2is_upsample_ce_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, stream));
             STEP_RC(lc2is_argmax_confmat_lowres_packed(lg, nb, C, h, w, H, W, d_packed + lab_off, d_cm, nullptr,
@@ -458,7 +569,7 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
                                     int64_t ignore_index, float logit_scale, int do_backward,
                                     float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                                     void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                                    uint16_t* h_scratch) {
+                                    void* h_scratch) {
     return head_step_enqueue(h_v, h_t, h_labels, B, h, w, D, C, H, W, ignore_index, logit_scale, do_backward,
                              h_out_loss, h_out_n_valid, h_out_confmat, d_ws, stream, copy_stream, h_scratch, 0, false);
 }
@@ -468,7 +579,7 @@ extern "C" int lc2is_head_step_host_submit(const void* h_v, const float* h_t, co
                                            int64_t ignore_index, float logit_scale, int do_backward,
                                            float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                                            void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                                           uint16_t* h_scratch, void** done_event) {
+                                           void* h_scratch, void** done_event) {
     if (!done_event) return fail(LC2IS_ERR_ARG, "done_event is NULL%s");
     if (!copy_stream || copy_stream == stream) return fail(LC2IS_ERR_ARG, "submit needs a separate copy stream%s");
     int e = head_step_enqueue(h_v, h_t, h_labels, B, h, w, D, C, H, W, ignore_index, logit_scale, do_backward,

@@ -881,6 +881,59 @@ extern "C" int lc2is_pack_labels(const int64_t* d_labels, int64_t n, int C, int6
     return 0;
 }
 
+namespace lc2is {
+// one-byte host form (C <= 254: class id; 0xFE = label == ignore_index; 0xFF = not a class id) -> packed uint16
+__global__ void __launch_bounds__(256)
+k2_expand_labels_kernel(const uint4* __restrict__ in, long long n16, unsigned ign16, uint4* __restrict__ out,
+                        unsigned long long* __restrict__ n_valid) {
+    int cnt = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 q = __ldcs(in + i);
+        const unsigned wds[4] = {q.x, q.y, q.z, q.w};
+        unsigned o[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const unsigned a = (wds[k] >> (16 * j)) & 0xFFu, b = (wds[k] >> (16 * j + 8)) & 0xFFu;
+                cnt += (a < 0xFEu) + (b < 0xFEu);
+                const unsigned ea = a < 0xFEu ? a : (a == 0xFEu ? ign16 : 0xFFFFu);
+                const unsigned eb = b < 0xFEu ? b : (b == 0xFEu ? ign16 : 0xFFFFu);
+                o[2 * k + j] = ea | (eb << 16);
+            }
+        }
+        out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+        out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+    if (n_valid) {
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_valid, (unsigned long long)cnt);
+    }
+}
+}  // namespace lc2is
+
+extern "C" int lc2is_expand_labels(const uint8_t* d_labels8, int64_t n, int C, int64_t ignore_index,
+                                   uint16_t* d_labels_packed, int64_t* d_n_valid, lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (n < 0 || C <= 0) return fail(LC2IS_ERR_SHAPE, "bad n / C%s");
+    if (C > 254) return fail(LC2IS_ERR_UNSUPPORTED, "one-byte labels hold class ids < 254%s");
+    if (n == 0) return 0;
+    if (!d_labels8 || !d_labels_packed) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (n % 16) return fail(LC2IS_ERR_SHAPE, "lc2is_expand_labels: n must be a multiple of 16%s");
+    if (((uintptr_t)d_labels8 % 16) || ((uintptr_t)d_labels_packed % 16))
+        return fail(LC2IS_ERR_ARG, "labels must be 16-byte aligned%s");
+    const long long n16 = n / 16;
+    long long blocks = (n16 + 255) / 256;
+    const long long cap = (long long)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    const unsigned ign16 = (ignore_index >= 0 && ignore_index < C) ? ((unsigned)ignore_index | 0x8000u) : 0xFFFFu;
+    k2_expand_labels_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)d_labels8, n16, ign16, (uint4*)d_labels_packed, (unsigned long long*)d_n_valid);
+    LC2IS_CHECK_LAUNCH("k2_expand_labels_kernel");
+    return 0;
+}
+
 extern "C" int lc2is_ce_labels_prepass_packed(const uint16_t* d_labels_packed, int B, int C, int h, int w, int H,
                                               int W, int64_t* d_n_valid, float* d_grad_low,
                                               lc2is_stream_t stream) {

@@ -286,3 +286,13 @@ def contrastive_bwd(outputs: Tensor, labels: Tensor, ignore_index: int, col_lse:
     check(lib.lc2is_contrastive_bwd(ptr(outputs), ptr(labels), B, h, w, C, int(ignore_index), ptr(col_lse), ptr(col_adj),
                                     ptr(coef), ptr(grad), stream_ptr()), "lc2is_contrastive_bwd")
     return grad
+
+
+def expand_labels(labels8: Tensor, C: int, ignore_index: int, n_valid: Optional[Tensor] = None) -> Tensor:
+    """One-byte host label form (lc2is_pack_labels_host for C <= 254) -> packed uint16 of the same shape;
+    n_valid (int64[1]) accumulates the counted labels when given."""
+    labels8 = _req(labels8, torch.uint8, "labels8")
+    packed = torch.empty(labels8.shape, dtype=torch.uint16, device=labels8.device)
+    check(lib.lc2is_expand_labels(ptr(labels8), labels8.numel(), C, int(ignore_index), ptr(packed), ptr(n_valid),
+                                  stream_ptr()), "lc2is_expand_labels")
+    return packed

@@ -218,19 +218,21 @@ class HostStep:
         self.args = (B, h, w, D, C, H, W)
         self.ignore_index, self.logit_scale, self.backward = ignore_index, logit_scale, backward
         nbytes = int(lib.lc2is_head_step_workspace(B, h * w, D, C, H, W))
-        # pinned scratch for the host-side int64 -> packed uint16 narrowing of the labels (split geometries)
+        # pinned scratch for the host-side int64 -> 1- / 2-byte narrowing of the labels (split geometries)
         # (needs a few host threads per rank: with fewer than 4 the 8-byte labels cross PCIe as they are)
         self.host_pack = bool(host_pack and lib.lc2is_ce_split_supported(h, w, H, W) and C < 0x7fff
                               and lib.lc2is_pack_threads() >= 4)
         self.slots = [HostStep._Slot(nbytes, B, H, W, C, dev, self.host_pack) for _ in range(max(1, depth))]
         # pinned scratch for the packed labels: one more than the steps in flight, so that the labels of the NEXT batch
         # can be packed (prefetch) while all slots are busy
-        self._scratch = [torch.empty(B, H, W, dtype=torch.uint16).pin_memory() for _ in range(len(self.slots) + 1)] \
-            if self.host_pack else []
+        # (host form: 1 byte per label for C <= 254, else the packed uint16 form - lc2is_host_label_bytes)
+        self.label_bytes = int(lib.lc2is_host_label_bytes(C)) if self.host_pack else 8
+        self._scratch = [torch.empty(B, H, W, self.label_bytes, dtype=torch.uint8).pin_memory()
+                         for _ in range(len(self.slots) + 1)] if self.host_pack else []
         self._scr_next = 0
         self._prefetched = None                     # (labels data_ptr, scratch index, pack handle)
         self.copy_stream = torch.cuda.Stream(device=dev) if pipelined else None
-        self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + B * H * W * (2 if self.host_pack else 8)
+        self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + B * H * W * self.label_bytes
         self.d2h_bytes = 4 + 8 + C * C * 8
         self._next, self._inflight = 0, []
         self._set_outputs(self.slots[0])

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import head_oracle as O
-from lc2is_b200 import metrics, synthetic
+from lc2is_b200 import metrics, ops, synthetic
 from lc2is_b200.step import HeadStep, HostStep
 
 pytestmark = pytest.mark.gpu
@@ -154,3 +154,21 @@ def test_new_entries_reject_unsupported_geometries_loudly():
     step(v, synthetic.make_prototypes(5, 512).to(DEV), torch.randint(0, 5, (1, 32, 32), device=DEV))
     torch.cuda.synchronize()
     assert torch.isfinite(step.loss).all() and int(step.confmat.sum()) == 32 * 32
+
+
+@pytest.mark.parametrize("C,ign", [(150, 0), (254, 253), (7, -100)])
+def test_one_byte_host_labels_expand_to_the_device_packing(C, ign):
+    """lc2is_pack_labels_host (1 byte per label for C <= 254) + lc2is_expand_labels == lc2is_pack_labels on the int64
+    map, bit for bit, including labels outside [0,C) and the counted-pixel total."""
+    from lc2is_b200 import _lib
+    g = torch.Generator().manual_seed(5)
+    lab = torch.randint(-2, C + 3, (2, 64, 64), generator=g)
+    lab[0, :8] = ign
+    assert _lib.lib.lc2is_host_label_bytes(C) == 1
+    h8 = torch.empty(lab.shape, dtype=torch.uint8).pin_memory()
+    _lib.check(_lib.lib.lc2is_pack_labels_host(lab.data_ptr(), lab.numel(), C, ign, h8.data_ptr()), "pack")
+    nv = torch.zeros(1, dtype=torch.int64, device=DEV)
+    got = ops.expand_labels(h8.to(DEV), C, ign, nv)
+    want, nv_ref = ops.pack_labels(lab.to(DEV), C, ign)
+    assert torch.equal(got.cpu().view(torch.int16), want.cpu().view(torch.int16))
+    assert int(nv) == int(nv_ref) == int(((lab >= 0) & (lab < C) & (lab != ign)).sum())

@@ -100,19 +100,34 @@ def test_synthetic_inputs_are_seeded():
 
 
 def test_host_label_packing_matches_device_encoding():
-    """lc2is_pack_labels_host (HOST code, worker pool + AVX2): int64 -> uint16 class id, bit 15 = ignore_index,
-    0xFFFF = not a class id; ragged lengths exercise the scalar tail."""
+    """lc2is_pack_labels_host (HOST code, worker pool + AVX2).  C > 254: int64 -> uint16 class id, bit 15 = ignore_index,
+    0xFFFF = not a class id.  C <= 254: one byte, 0xFE = ignore_index, 0xFF = not a class id.  Ragged lengths exercise
+    the scalar tail."""
     import torch
     from lc2is_b200 import _lib
     g = torch.Generator().manual_seed(9)
-    for n, C, ign in ((1, 5, 0), (17, 151, 0), (100003, 150, -100), (4 * 512 * 512, 847, 3)):
+    for n, C, ign in ((1, 5, 0), (17, 151, 0), (100003, 150, -100), (4 * 512 * 512, 847, 3), (70001, 254, 253),
+                      (33, 255, 0)):
         lab = torch.randint(-3, C + 4, (n,), generator=g)
         lab[:: max(1, n // 7)] = ign
         if n > 3:
             lab[1], lab[2], lab[3] = 2 ** 40, -2 ** 40, 65535
-        out = torch.full((n + 8,), 7, dtype=torch.uint16)
-        _lib.check(_lib.lib.lc2is_pack_labels_host(lab.data_ptr(), n, C, ign, out.data_ptr()), "pack")
+        nb = _lib.lib.lc2is_host_label_bytes(C)
+        assert nb == (1 if C <= 254 else 2)
         inr = (lab >= 0) & (lab < C)
-        ref = torch.where(inr, torch.where(lab == ign, lab | 0x8000, lab), torch.full_like(lab, 0xFFFF))
+        if nb == 2:
+            out = torch.full((n + 8,), 7, dtype=torch.uint16)
+            ref = torch.where(inr, torch.where(lab == ign, lab | 0x8000, lab), torch.full_like(lab, 0xFFFF))
+        else:
+            out = torch.full((n + 8,), 7, dtype=torch.uint8)
+            ref = torch.where(inr, torch.where(lab == ign, torch.full_like(lab, 0xFE), lab), torch.full_like(lab, 0xFF))
+        _lib.check(_lib.lib.lc2is_pack_labels_host(lab.data_ptr(), n, C, ign, out.data_ptr()), "pack")
         assert torch.equal(out[:n].to(torch.int64), ref)
         assert bool((out[n:] == 7).all())                     # nothing written past the end
+        # the asynchronous form writes the same bytes
+        out2 = torch.full_like(out, 7)
+        import ctypes
+        hd = ctypes.c_void_p()
+        _lib.check(_lib.lib.lc2is_pack_labels_host_begin(lab.data_ptr(), n, C, ign, out2.data_ptr(), ctypes.byref(hd)), "begin")
+        _lib.check(_lib.lib.lc2is_pack_labels_host_end(hd), "end")
+        assert torch.equal(out, out2)
