@@ -278,16 +278,22 @@ int lc2is_contrastive_bwd(const float* d_out, const int64_t* d_labels, int B, in
  *   of chunk i+1 overlaps the kernels of chunk i (the 1/N_valid scale is applied at the end, in K1b).
  * h_scratch: optional PINNED host buffer of B*H*W*lc2is_host_label_bytes(C) bytes (NULL = none).  With it (and a
  *   power-of-two scale 8 / 16) the int64 labels are narrowed to the 1- or 2-byte host form on the library's host
- *   worker threads, chunk by chunk ahead of the copies, so an eighth / a quarter of the label bytes cross PCIe.  h_labels == NULL: h_scratch
- *   already holds the packed labels (lc2is_pack_labels_host / _begin + _end, or a loader that writes them itself).
+ *   worker threads, chunk by chunk ahead of the copies, so an eighth / a quarter of the label bytes cross PCIe.
+ * n_raw: the LAST n_raw images' labels cross as int64 anyway and are packed on the device, concurrently with the host
+ *   threads narrowing the first B - n_raw (0 = all on the host; for hosts whose cores read 8 bytes per label more
+ *   slowly than PCIe moves them - HostStep calibrates the split).  Ignored without h_scratch.
+ * flags: LC2IS_STEP_LABELS_PREPACKED - h_scratch already holds the host-form labels of the first B - n_raw images
+ *   (lc2is_pack_labels_host / _begin + _end, or a loader that writes them itself); also implied by h_labels == NULL
+ *   (then n_raw must be 0).
  */
+#define LC2IS_STEP_LABELS_PREPACKED 1
 int64_t lc2is_head_step_workspace(int B, int hw, int D, int C, int H, int W);
 int lc2is_head_step_host(const void* h_v, const float* h_t, const int64_t* h_labels,
                          int B, int h, int w, int D, int C, int H, int W,
                          int64_t ignore_index, float logit_scale, int do_backward,
                          float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                          void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                         void* h_scratch);
+                         void* h_scratch, int n_raw, int flags);
 
 /* The same step without the final synchronisation: everything (host-side label packing, H2D, kernels, D2H
  * of the results) is enqueued and *done_event receives a handle; lc2is_head_step_host_wait blocks until that
@@ -300,7 +306,7 @@ int lc2is_head_step_host_submit(const void* h_v, const float* h_t, const int64_t
                                 int64_t ignore_index, float logit_scale, int do_backward,
                                 float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                                 void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                                void* h_scratch, void** done_event);
+                                void* h_scratch, int n_raw, int flags, void** done_event);
 int lc2is_head_step_host_wait(void* done_event);
 
 #ifdef __cplusplus

@@ -65,9 +65,9 @@ SIGNATURES = {
     "lc2is_pack_labels": (c_int, [_p, c_int64, c_int, c_int64, _p, _p, _p]),
     "lc2is_head_step_workspace": (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     "lc2is_head_step_host": (c_int, [_p, _p, _p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
-                                     c_float, c_int, _p, _p, _p, _p, _p, _p, _p]),
+                                     c_float, c_int, _p, _p, _p, _p, _p, _p, _p, c_int, c_int]),
     "lc2is_head_step_host_submit": (c_int, [_p, _p, _p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
-                                            c_float, c_int, _p, _p, _p, _p, _p, _p, _p, POINTER(c_void_p)]),
+                                            c_float, c_int, _p, _p, _p, _p, _p, _p, _p, c_int, c_int, POINTER(c_void_p)]),
     "lc2is_head_step_host_wait": (c_int, [_p]),
     "lc2is_ce_labels_prepass_packed": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p]),
     "lc2is_pack_threads": (c_int, []),

@@ -372,7 +372,7 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
                              int64_t ignore_index, float logit_scale, int do_backward,
                              float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                              void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                             void* h_scratch, int n_chunks, bool async) {
+                             void* h_scratch, int n_raw, int flags, int n_chunks, bool async) {
     if (int e = ensure_device()) return e;
     if (!h_v || !h_t || (!h_labels && !h_scratch) || !h_out_loss || !h_out_n_valid || !h_out_confmat || !d_ws)
         return fail(LC2IS_ERR_ARG, "null pointer%s");
@@ -411,7 +411,14 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
     // With a pinned scratch buffer the int64 labels are narrowed to the packed uint16 form on the host
     // (worker pool), chunk by chunk ahead of the copies: 2 bytes per pixel cross PCIe instead of 8.
     const bool hpack = split && h_scratch != nullptr && C < 0x7fff;
-    const bool prepacked = h_labels == nullptr;             // h_scratch already holds the packed labels
+    // h_scratch already holds the packed labels (of the first B - n_raw images)
+    const bool prepacked = h_labels == nullptr || (flags & LC2IS_STEP_LABELS_PREPACKED);
+    // The LAST n_raw images' labels cross as int64 and are packed on the device while the host threads narrow the
+    // others: on a host whose cores are slower at reading 8 bytes per label than PCIe is at moving them, the two
+    // routes share the work (HostStep calibrates the split).
+    if (n_raw < 0 || n_raw > B) return fail(LC2IS_ERR_ARG, "n_raw outside [0, B]%s");
+    if (n_raw > 0 && !h_labels) return fail(LC2IS_ERR_ARG, "n_raw > 0 needs h_labels%s");
+    const int Bp = hpack ? B - n_raw : 0;                   // images whose labels are packed on the host
     // host form of the packed labels: one byte per label for C <= 254 (expanded to uint16 on the device, next to the
     // copy: lc2is_expand_labels), else the uint16 form itself
     const int lb = hpack ? host_label_bytes(C) : 2;
@@ -437,9 +444,10 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
     if (hpack && !prepacked)
         for (int i = 0; i < nchunk; ++i) {
             const int b0 = i * bc, nb = (b0 + bc <= B ? bc : B - b0);
-            if (nb > 0)
+            const int np = nb <= 0 ? 0 : (Bp - b0 < 0 ? 0 : (Bp - b0 > nb ? nb : Bp - b0));
+            if (np > 0)
                 pack_submit(h_labels + (size_t)b0 * H * W, (char*)h_scratch + (size_t)b0 * H * W * lb,
-                            (size_t)nb * H * W, C, ignore_index, lb, &pack_pending[i]);
+                            (size_t)np * H * W, C, ignore_index, lb, &pack_pending[i]);
         }
     cudaEvent_t ev_start = nullptr, ev_copy[MAXCH] = {};
     auto cleanup = [&]() {
@@ -476,17 +484,20 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         const size_t lab_off = (size_t)b0 * H * W, v_off = (size_t)b0 * hw * D * 2;
         STEP_CUDA(cudaMemcpyAsync(d_v + v_off, (const uint8_t*)h_v + v_off, (size_t)nb * hw * D * 2,
                                   cudaMemcpyHostToDevice, cst));
-        if (hpack) {
+        // images [b0, b0 + np) of the chunk arrive packed from the host, the other nr as int64
+        const int np = hpack ? (Bp - b0 < 0 ? 0 : (Bp - b0 > nb ? nb : Bp - b0)) : 0, nr = nb - np;
+        const size_t raw_off = lab_off + (size_t)np * H * W;
+        if (nr > 0)                                          // (does not wait for the host threads: enqueued first)
+            STEP_CUDA(cudaMemcpyAsync(d_labels + raw_off, h_labels + raw_off, (size_t)nr * H * W * 8,
+                                      cudaMemcpyHostToDevice, cst));
+        if (np > 0) {
             pack_wait(&pack_pending[i]);
-            if (lb == 1)
-                STEP_CUDA(cudaMemcpyAsync(d_lab8 + lab_off, (const uint8_t*)h_scratch + lab_off, (size_t)nb * H * W,
+            if (lb == 1)                                     // staged in the head of the int64 area: byte b*HW < b*HW*8
+                STEP_CUDA(cudaMemcpyAsync(d_lab8 + lab_off, (const uint8_t*)h_scratch + lab_off, (size_t)np * H * W,
                                           cudaMemcpyHostToDevice, cst));
             else
                 STEP_CUDA(cudaMemcpyAsync(d_packed + lab_off, (const uint16_t*)h_scratch + lab_off,
-                                          (size_t)nb * H * W * 2, cudaMemcpyHostToDevice, cst));
-        } else {
-            STEP_CUDA(cudaMemcpyAsync(d_labels + lab_off, h_labels + lab_off, (size_t)nb * H * W * 8,
-                                      cudaMemcpyHostToDevice, cst));
+                                          (size_t)np * H * W * 2, cudaMemcpyHostToDevice, cst));
         }
         mark("h2d", cst);
         if (piped) {
@@ -498,17 +509,21 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
         float* gl = do_backward ? d_glow + (size_t)b0 * C * hw : nullptr;
         // labels: the fused K2+K3 kernel only needs them packed and counted (its argmax warps add the -onehot term);
         // the separate kernels need the label prepass (count, packing, -onehot)
-        // (one-byte host labels: widened to the packed form and counted here)
-        const bool counted8 = hpack && lb == 1;
-        if (counted8)
-            STEP_RC(lc2is_expand_labels(d_lab8 + lab_off, (int64_t)nb * H * W, C, ignore_index, d_packed + lab_off,
-                                        fused ? d_nvalid : nullptr, stream));
-        if (fused) {
-            if (!hpack)
-                STEP_RC(lc2is_pack_labels(d_labels + lab_off, (int64_t)nb * H * W, C, ignore_index, d_packed + lab_off,
-                                          d_nvalid, stream));
-        } else if (hpack)
-            STEP_RC(lc2is_ce_labels_prepass_packed(d_packed + lab_off, nb, C, h, w, H, W, d_nvalid, gl, stream));
+        if (hpack) {
+            // one-byte host labels are widened to the packed form here, int64 ones packed; both count the valid pixels
+            // when nothing downstream does (the fused kernel counts for two-byte host labels, the prepass otherwise)
+            int64_t* cnt = (fused && lb == 1) ? d_nvalid : nullptr;
+            if (lb == 1 && np > 0)
+                STEP_RC(lc2is_expand_labels(d_lab8 + lab_off, (int64_t)np * H * W, C, ignore_index, d_packed + lab_off,
+                                            cnt, stream));
+            if (nr > 0)
+                STEP_RC(lc2is_pack_labels(d_labels + raw_off, (int64_t)nr * H * W, C, ignore_index, d_packed + raw_off,
+                                          cnt, stream));
+            if (!fused)
+                STEP_RC(lc2is_ce_labels_prepass_packed(d_packed + lab_off, nb, C, h, w, H, W, d_nvalid, gl, stream));
+        } else if (fused)
+            STEP_RC(lc2is_pack_labels(d_labels + lab_off, (int64_t)nb * H * W, C, ignore_index, d_packed + lab_off,
+                                      d_nvalid, stream));
         else if (split)
             STEP_RC(lc2is_ce_labels_prepass(d_labels + lab_off, nb, C, h, w, H, W, ignore_index, d_packed + lab_off,
                                             d_nvalid, gl, stream));
@@ -520,9 +535,9 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
                                         d_vhat + v_off, d_invv + (size_t)b0 * hw, lg, stream));
         mark("k1", st);
         if (fused) {
-            // (labels packed on the host arrive un-counted: the CE warps count them)
+            // (two-byte labels packed on the host arrive un-counted: the CE warps count them)
             STEP_RC(lc2is_ce_argmax_fused_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, 1,
-                                                 (hpack && !counted8) ? d_nvalid : nullptr, d_cm, nullptr, nullptr, stream));
+                                                 (hpack && lb == 2) ? d_nvalid : nullptr, d_cm, nullptr, nullptr, stream));
         } else if (split) {
             STEP_RC(lc2is_upsample_ce_packed(lg, d_packed + lab_off, nb, C, h, w, H, W, d_loss_sum, gl, stream));
             STEP_RC(lc2is_argmax_confmat_lowres_packed(lg, nb, C, h, w, H, W, d_packed + lab_off, d_cm, nullptr,
@@ -569,9 +584,10 @@ extern "C" int lc2is_head_step_host(const void* h_v, const float* h_t, const int
                                     int64_t ignore_index, float logit_scale, int do_backward,
                                     float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                                     void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                                    void* h_scratch) {
+                                    void* h_scratch, int n_raw, int flags) {
     return head_step_enqueue(h_v, h_t, h_labels, B, h, w, D, C, H, W, ignore_index, logit_scale, do_backward,
-                             h_out_loss, h_out_n_valid, h_out_confmat, d_ws, stream, copy_stream, h_scratch, 0, false);
+                             h_out_loss, h_out_n_valid, h_out_confmat, d_ws, stream, copy_stream, h_scratch, n_raw,
+                             flags, 0, false);
 }
 
 extern "C" int lc2is_head_step_host_submit(const void* h_v, const float* h_t, const int64_t* h_labels,
@@ -579,11 +595,11 @@ extern "C" int lc2is_head_step_host_submit(const void* h_v, const float* h_t, co
                                            int64_t ignore_index, float logit_scale, int do_backward,
                                            float* h_out_loss, int64_t* h_out_n_valid, int64_t* h_out_confmat,
                                            void* d_ws, lc2is_stream_t stream, lc2is_stream_t copy_stream,
-                                           void* h_scratch, void** done_event) {
+                                           void* h_scratch, int n_raw, int flags, void** done_event) {
     if (!done_event) return fail(LC2IS_ERR_ARG, "done_event is NULL%s");
     if (!copy_stream || copy_stream == stream) return fail(LC2IS_ERR_ARG, "submit needs a separate copy stream%s");
     int e = head_step_enqueue(h_v, h_t, h_labels, B, h, w, D, C, H, W, ignore_index, logit_scale, do_backward,
-                              h_out_loss, h_out_n_valid, h_out_confmat, d_ws, stream, copy_stream, h_scratch, 0, true);
+                              h_out_loss, h_out_n_valid, h_out_confmat, d_ws, stream, copy_stream, h_scratch, n_raw, flags, 0, true);
     if (e) return e;
     cudaEvent_t ev;
     LC2IS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));

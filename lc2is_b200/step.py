@@ -213,48 +213,96 @@ class HostStep:
 
     def __init__(self, B: int, h: int, w: int, H: int, W: int, C: int, D: int = 512, ignore_index: int = 0,
                  logit_scale: float = 1.0, backward: bool = True, device: Optional[torch.device] = None,
-                 pipelined: bool = True, host_pack: bool = True, depth: int = 2) -> None:
+                 pipelined: bool = True, host_pack: bool = True, depth: int = 2,
+                 raw_images: Optional[int] = None) -> None:
         dev = device or torch.device("cuda", torch.cuda.current_device())
         self.args = (B, h, w, D, C, H, W)
         self.ignore_index, self.logit_scale, self.backward = ignore_index, logit_scale, backward
         nbytes = int(lib.lc2is_head_step_workspace(B, h * w, D, C, H, W))
         # pinned scratch for the host-side int64 -> 1- / 2-byte narrowing of the labels (split geometries)
-        # (needs a few host threads per rank: with fewer than 4 the 8-byte labels cross PCIe as they are)
-        self.host_pack = bool(host_pack and lib.lc2is_ce_split_supported(h, w, H, W) and C < 0x7fff
-                              and lib.lc2is_pack_threads() >= 4)
+        self.host_pack = bool(host_pack and lib.lc2is_ce_split_supported(h, w, H, W) and C < 0x7fff)
+        # raw_images: how many of the batch's LAST label maps cross PCIe as int64 (packed on the device) while the host
+        # threads narrow the others; None = measure this host's packing rate and H2D rate once and balance the two
+        # routes (0 on a host with enough cores; everything raw when the host threads are slower than the 8-byte copy)
+        self.label_bytes = int(lib.lc2is_host_label_bytes(C)) if self.host_pack else 8
+        self.calibration = None
+        if not self.host_pack:
+            self.n_raw = B
+        elif raw_images is not None:
+            self.n_raw = max(0, min(B, int(raw_images)))
+        else:
+            self.n_raw = self._calibrate_split(B, h * w, D, H, W, C, dev)
+        if self.n_raw >= B:
+            self.host_pack, self.label_bytes = False, 8
         self.slots = [HostStep._Slot(nbytes, B, H, W, C, dev, self.host_pack) for _ in range(max(1, depth))]
         # pinned scratch for the packed labels: one more than the steps in flight, so that the labels of the NEXT batch
         # can be packed (prefetch) while all slots are busy
         # (host form: 1 byte per label for C <= 254, else the packed uint16 form - lc2is_host_label_bytes)
-        self.label_bytes = int(lib.lc2is_host_label_bytes(C)) if self.host_pack else 8
         self._scratch = [torch.empty(B, H, W, self.label_bytes, dtype=torch.uint8).pin_memory()
                          for _ in range(len(self.slots) + 1)] if self.host_pack else []
         self._scr_next = 0
         self._prefetched = None                     # (labels data_ptr, scratch index, pack handle)
         self.copy_stream = torch.cuda.Stream(device=dev) if pipelined else None
-        self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + B * H * W * self.label_bytes
+        n_raw = self.n_raw if self.host_pack else B
+        self.h2d_bytes = B * h * w * D * 2 + C * D * 4 + (B - n_raw) * H * W * self.label_bytes + n_raw * H * W * 8
         self.d2h_bytes = 4 + 8 + C * C * 8
         self._next, self._inflight = 0, []
         self._set_outputs(self.slots[0])
+
+    def _calibrate_split(self, B, hw, D, H, W, C, dev) -> int:
+        """Time one host packing pass over a batch of labels and one pinned H2D copy, then pick the number of raw
+        images that minimises max(host packing time, copy time) of a step.  Ranks of a node calibrate together (each
+        sees its share of the cores / DRAM / PCIe)."""
+        import time
+        import torch.distributed as dist
+        lb = self.label_bytes
+        lab = torch.zeros(B, H, W, dtype=torch.int64).pin_memory()
+        src = torch.zeros(B * H * W, dtype=torch.int64).pin_memory()    # its own buffer: lines the cores have just
+        out = torch.empty(B * H * W * lb, dtype=torch.uint8).pin_memory()  # touched copy several times slower
+        d_buf = torch.empty(B * H * W, dtype=torch.int64, device=dev)
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
+        t_pack, t_copy = float("inf"), float("inf")
+        for _ in range(4):
+            t0 = time.perf_counter()
+            check(lib.lc2is_pack_labels_host(ptr(lab), lab.numel(), C, self.ignore_index, ptr(out)), "lc2is_pack_labels_host")
+            t_pack = min(t_pack, time.perf_counter() - t0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            d_buf.copy_(src, non_blocking=True)
+            e1.record()
+            e1.synchronize()
+            t_copy = min(t_copy, e0.elapsed_time(e1) * 1e-3)
+        pack_per_img = 1.1 * t_pack / B                               # (slower next to the copies than alone)
+        bw = B * H * W * 8 / t_copy                                   # bytes / s
+        v_bytes = B * hw * D * 2
+        best, best_t = 0, float("inf")
+        for r in range(0, B + 1):
+            copy_t = (v_bytes + (B - r) * H * W * lb + r * H * W * 8) / bw
+            t = max(pack_per_img * (B - r), copy_t)
+            if t < best_t * 0.97:                                     # prefer fewer raw images on a near-tie
+                best, best_t = r, t
+        self.calibration = {"pack_ms": t_pack * 1e3, "h2d_gbs": bw / 1e9, "n_raw": best, "threads": int(lib.lc2is_pack_threads())}
+        return best
 
     def _set_outputs(self, s) -> None:
         self.out_loss, self.out_n_valid, self.out_confmat = s.out_loss, s.out_n_valid, s.out_confmat
 
     def _take_scratch(self, h_labels):
-        """-> (scratch tensor | None, labels pointer | None): the packed labels if `h_labels` were prefetched."""
+        """-> (scratch tensor | None, flags): LC2IS_STEP_LABELS_PREPACKED if `h_labels` were prefetched."""
         if not self.host_pack:
-            return None, ptr(h_labels)
+            return None, 0
         if self._prefetched is not None and self._prefetched[0] == h_labels.data_ptr():
             _, k, handle = self._prefetched
             self._prefetched = None
             check(lib.lc2is_pack_labels_host_end(handle), "lc2is_pack_labels_host_end")
-            return self._scratch[k], None                    # h_labels = NULL: h_scratch holds them
+            return self._scratch[k], 1                       # h_scratch holds the first B - n_raw label maps
         if self._prefetched is not None:                      # a prefetch for other labels: let it finish, drop it
             check(lib.lc2is_pack_labels_host_end(self._prefetched[2]), "lc2is_pack_labels_host_end")
             self._prefetched = None
         k = self._scr_next
         self._scr_next = (k + 1) % len(self._scratch)
-        return self._scratch[k], ptr(h_labels)
+        return self._scratch[k], 0
 
     def prefetch(self, h_labels: torch.Tensor) -> None:
         """Start packing the labels of the NEXT batch on the library's host threads (returns at once); the following
@@ -266,7 +314,7 @@ class HostStep:
         k = self._scr_next
         self._scr_next = (k + 1) % len(self._scratch)
         handle = ctypes.c_void_p()
-        check(lib.lc2is_pack_labels_host_begin(ptr(h_labels), h_labels.numel(), C, self.ignore_index,
+        check(lib.lc2is_pack_labels_host_begin(ptr(h_labels), (B - self.n_raw) * H * W, C, self.ignore_index,
                                                ptr(self._scratch[k]), ctypes.byref(handle)), "lc2is_pack_labels_host_begin")
         self._prefetched = (h_labels.data_ptr(), k, handle)
         self._prefetch_keep = h_labels
@@ -279,12 +327,12 @@ class HostStep:
         self._check_inputs(h_v, h_labels)
         assert not self._inflight, "wait() for the submitted steps first"
         s = self.slots[0]
-        scratch, lab_ptr = self._take_scratch(h_labels)
-        check(lib.lc2is_head_step_host(ptr(h_v), ptr(h_t), lab_ptr, B, h, w, D, C, H, W, self.ignore_index,
+        scratch, flags = self._take_scratch(h_labels)
+        check(lib.lc2is_head_step_host(ptr(h_v), ptr(h_t), ptr(h_labels), B, h, w, D, C, H, W, self.ignore_index,
                                        self.logit_scale, int(self.backward), ptr(s.out_loss),
                                        ptr(s.out_n_valid), ptr(s.out_confmat), ptr(s.ws), stream_ptr(),
                                        self.copy_stream.cuda_stream if self.copy_stream is not None else None,
-                                       ptr(scratch)),
+                                       ptr(scratch), self.n_raw if self.host_pack else 0, flags),
               "lc2is_head_step_host")
         self._set_outputs(s)
 
@@ -297,11 +345,12 @@ class HostStep:
         s = self.slots[self._next]
         self._next = (self._next + 1) % len(self.slots)
         ev = ctypes.c_void_p()
-        scratch, lab_ptr = self._take_scratch(h_labels)
-        check(lib.lc2is_head_step_host_submit(ptr(h_v), ptr(h_t), lab_ptr, B, h, w, D, C, H, W, self.ignore_index,
+        scratch, flags = self._take_scratch(h_labels)
+        check(lib.lc2is_head_step_host_submit(ptr(h_v), ptr(h_t), ptr(h_labels), B, h, w, D, C, H, W, self.ignore_index,
                                               self.logit_scale, int(self.backward), ptr(s.out_loss),
                                               ptr(s.out_n_valid), ptr(s.out_confmat), ptr(s.ws), stream_ptr(),
-                                              self.copy_stream.cuda_stream, ptr(scratch), ctypes.byref(ev)),
+                                              self.copy_stream.cuda_stream, ptr(scratch),
+                                              self.n_raw if self.host_pack else 0, flags, ctypes.byref(ev)),
               "lc2is_head_step_host_submit")
         s.event, s.keep = ev, (h_v, h_t, h_labels)          # host buffers must outlive the step
         self._inflight.append(s)

@@ -19,11 +19,14 @@ def _inputs(B, h, H, C):
 
 
 @pytest.mark.parametrize("pipelined", [False, True])
-@pytest.mark.parametrize("B,h,H,C", [(5, 8, 128, 151), (4, 32, 128, 150), (1, 8, 32, 19)])
-def test_host_step_matches_oracle(pipelined, B, h, H, C):
+@pytest.mark.parametrize("B,h,H,C,raw", [(5, 8, 128, 151, 0), (5, 8, 128, 151, 2), (5, 8, 128, 151, 5), (4, 32, 128, 150, 0),
+                                         (1, 8, 32, 19, 0), (4, 16, 128, 151, 1), (3, 8, 128, 300, 1)])
+def test_host_step_matches_oracle(pipelined, B, h, H, C, raw):
+    """x16 (fused kernel), x8 (separate split kernels), x4 (generic) geometries; `raw` of the label maps cross PCIe
+    as int64 and are packed on the device, the others are narrowed on the host (1 byte per label, 2 for C = 300)."""
     v, t, labels = _inputs(B, h, H, C)
     ref = O.head_step(v.float(), t, labels, ignore_index=0, n_cls=C)
-    hs = HostStep(B, h, h, H, H, C, ignore_index=0, pipelined=pipelined)
+    hs = HostStep(B, h, h, H, H, C, ignore_index=0, pipelined=pipelined, raw_images=raw)
     for _ in range(2):                                    # twice: workspace reuse across calls
         hs(v.pin_memory(), t.pin_memory(), labels.pin_memory())
     assert int(hs.out_n_valid) == int((labels != 0).sum())
@@ -56,7 +59,8 @@ def test_head_step_device_matches_oracle_and_host_step():
     assert abs(float(metrics.miou_from_confmat(step.confmat, 0)) - float(O.jaccard_macro(step.confmat.cpu(), 0))) < 1e-7
 
 
-def test_submit_wait_pipeline_matches_blocking_call():
+@pytest.mark.parametrize("raw", [0, 1, 3])
+def test_submit_wait_pipeline_matches_blocking_call(raw):
     """Two steps in flight (lc2is_head_step_host_submit / _wait) over alternating batches give, step by step,
     exactly the results of the blocking call; host-side label packing on and off agree bit for bit."""
     B, h, H, C = 4, 8, 128, 151
@@ -72,8 +76,8 @@ def test_submit_wait_pipeline_matches_blocking_call():
     for v, lab in batches:
         blocking(v, t, lab)
         ref.append((float(blocking.out_loss), int(blocking.out_n_valid), blocking.out_confmat.clone()))
-    hs = HostStep(B, h, h, H, H, C, ignore_index=0, depth=2)
-    assert hs.host_pack
+    hs = HostStep(B, h, h, H, H, C, ignore_index=0, depth=2, raw_images=raw)
+    assert hs.host_pack and hs.n_raw == raw
     got = []
     seq = [0, 1, 2, 0, 1, 2, 1]
     hs.submit(batches[seq[0]][0], t, batches[seq[0]][1])
@@ -172,3 +176,17 @@ def test_one_byte_host_labels_expand_to_the_device_packing(C, ign):
     want, nv_ref = ops.pack_labels(lab.to(DEV), C, ign)
     assert torch.equal(got.cpu().view(torch.int16), want.cpu().view(torch.int16))
     assert int(nv) == int(nv_ref) == int(((lab >= 0) & (lab < C) & (lab != ign)).sum())
+
+
+def test_default_host_step_calibrates_the_label_split():
+    """Without `raw_images` the step measures the host's packing rate and the H2D rate and picks how many label maps
+    cross as int64; whatever it picks, the results are those of the all-raw step."""
+    B, h, H, C = 4, 8, 128, 151
+    v, t, labels = _inputs(B, h, H, C)
+    hs = HostStep(B, h, h, H, H, C, ignore_index=0)
+    assert 0 <= hs.n_raw <= B and hs.calibration["pack_ms"] > 0 and hs.calibration["h2d_gbs"] > 1
+    ref = HostStep(B, h, h, H, H, C, ignore_index=0, host_pack=False)
+    for s_ in (hs, ref):
+        s_(v.pin_memory(), t.pin_memory(), labels.pin_memory())
+    assert torch.equal(hs.out_confmat, ref.out_confmat) and int(hs.out_n_valid) == int(ref.out_n_valid)
+    assert abs(float(hs.out_loss) - float(ref.out_loss)) <= 2e-6 * float(ref.out_loss)
