@@ -328,6 +328,8 @@ def run_b200(a):
                "api": "lc2is_head_step_host_submit / _wait, 2 steps in flight, labels of the next batch packed in the "
                       "background (lc2is_pack_labels_host_begin/_end); pinned host buffers in: bf16 V, fp32 T, int64 labels "
                       "narrowed to 1 byte (C <= 254) by the library's host threads and widened on the device; loss/n_valid/confmat out",
+               "label_route": {"host_label_bytes": hstep.label_bytes, "n_raw_int64_images": hstep.n_raw if hstep.host_pack else B,
+                               "calibration": hstep.calibration},
                "blocking_call": {"api": "lc2is_head_step_host", "ms_per_step": ms_block / e_steps,
                                  "value": world * B * e_steps / (ms_block * 1e-3)}}
 
