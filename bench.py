@@ -261,7 +261,7 @@ def run_b200(a):
     if not a.no_e2e:
         hstep = HostStep(B, h, w, H, W, C, D, ignore_index=0, backward=backward, device=dev, depth=2)
         cm_dev = torch.zeros(C, C, dtype=torch.int64, device=dev)
-        e_steps = max(3, min(steps, 50))
+        e_steps = max(3, min(steps, 200))
 
         cm_host = torch.zeros(C, C, dtype=torch.int64)
 
