@@ -121,10 +121,96 @@ struct K1Params {
     float scale;
 };
 
+// Row-major epilogue staging.  In TMEM a thread owns a ROW, so storing straight from registers makes every warp store
+// touch 32 rows (32 half-written sectors: the projection GEMM spent 8.9 us per tile in its epilogue against 3.3 us of
+// MMA).  Instead each warp passes 128 bytes per row (64 bf16 / 32 fp32 channels) through a swizzled 4 KB scratch and
+// writes them back as 8 stores of 4 rows x 128 contiguous bytes; two warps per TMEM lane quarter share the columns.
+constexpr int K1_EPI_WARPS_RM = 8;                 // row-major epilogue: two warps per TMEM lane quarter
+constexpr int K1_EPI_SCRATCH = K1_EPI_WARPS_RM * 4096;
+__device__ __forceinline__ void epi_put(uint8_t* scr, int lane, int chunk, uint4 v) {
+    *reinterpret_cast<uint4*>(scr + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
+}
+__device__ __forceinline__ void epi_flush(const uint8_t* scr, int lane, uint8_t* grow0, size_t row_stride_bytes,
+                                          int rows_valid, int chunks_valid) {
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3);
+        const uint4 v = *reinterpret_cast<const uint4*>(scr + row * 128 + ((c ^ (row & 7)) << 4));
+        if (row < rows_valid && c < chunks_valid)
+            *reinterpret_cast<uint4*>(grow0 + (size_t)row * row_stride_bytes + (c << 4)) = v;
+    }
+}
+// one warp: rows [m0, m0 + 32) x columns [n0, n0 + ncols) of the row-major output from TMEM address `taddr`
+__device__ __forceinline__ void epi_rowmajor(const K1Params& P, uint8_t* scr, int lane, uint32_t taddr, size_t m0,
+                                             int rows_valid, int n0, int ncols);
+
+__device__ __forceinline__ void epi_rowmajor(const K1Params& P, uint8_t* scr, int lane, uint32_t taddr, size_t m0,
+                                             int rows_valid, int n0, int ncols) {
+    const int esize = P.out_f32 ? 4 : 2;
+    const int G = 128 / esize;                                  // channels per 128-byte group
+    uint8_t* out = reinterpret_cast<uint8_t*>(P.out_rm);
+    for (int cg = 0; cg < ncols; cg += G) {
+        for (int sub = 0; sub < G && cg + sub < ncols; sub += 32) {
+            uint32_t r[32];
+            if (cg + sub + 32 <= ncols) {
+                tc::tmem_ld32(taddr + cg + sub, r);
+            } else {                                            // ragged tail: 16 columns
+                uint32_t r16[16];
+                tc::tmem_ld16(taddr + cg + sub, r16);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { r[j] = r16[j]; r[16 + j] = 0u; }
+            }
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int hq = 0; hq < 2; ++hq) {
+                if (cg + sub + 16 * hq >= ncols) break;
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(r[16 * hq + j]) * P.scale;
+                if (P.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(P.bias + n0 + cg + sub + 16 * hq);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 bv = __ldg(bp + j);
+                        o[4 * j] += bv.x; o[4 * j + 1] += bv.y; o[4 * j + 2] += bv.z; o[4 * j + 3] += bv.w;
+                    }
+                }
+                const int c16 = sub + 16 * hq;                  // channel offset inside the group
+                if (P.out_f32) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        epi_put(scr, lane, (c16 >> 2) + j,
+                                make_uint4(__float_as_uint(o[4 * j]), __float_as_uint(o[4 * j + 1]),
+                                           __float_as_uint(o[4 * j + 2]), __float_as_uint(o[4 * j + 3])));
+                } else {
+                    __nv_bfloat162 pk[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) pk[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+                    epi_put(scr, lane, (c16 >> 3), *reinterpret_cast<uint4*>(&pk[0]));
+                    epi_put(scr, lane, (c16 >> 3) + 1, *reinterpret_cast<uint4*>(&pk[4]));
+                }
+            }
+        }
+        __syncwarp();
+        const int cols_here = ncols - cg < G ? ncols - cg : G;
+        epi_flush(scr, lane, out + (m0 * (size_t)P.C + n0 + cg) * esize, (size_t)P.C * esize, rows_valid,
+                  cols_here * esize / 16);
+        __syncwarp();
+    }
+}
+// how the epilogue warps of one TMEM lane quarter split the tile's columns (whole 128-byte groups each)
+__device__ __forceinline__ void epi_split(int ncols, int esize, int part, int nparts, int* c0, int* c1) {
+    const int G = 128 / esize, groups = (ncols + G - 1) / G;
+    const int g0 = groups * part / nparts, g1 = groups * (part + 1) / nparts;
+    *c0 = g0 * G;
+    *c1 = g1 * G < ncols ? g1 * G : ncols;
+}
+
 // EPI 0: the cosine-logits epilogue (class-plane major fp32).  EPI 1: the linear-projection epilogue of
 // TextToPatch.visual (model/text_patch.py:12,17): row-major out[m, n] = acc + bias[n], bf16 or fp32.
 template <int EPI>
-__global__ void __launch_bounds__(K1_THREADS, 1)
+__global__ void __launch_bounds__(64 + 32 * K1_EPI_WARPS_RM, 1)
 k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const K1Params P) {
     extern __shared__ uint8_t smem_raw[];
@@ -136,6 +222,7 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull = empty + K1_MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint8_t* epi_scr = reinterpret_cast<uint8_t*>(full) + 256;   // EPI 1 only: 4 warps x 4 KB (16-byte aligned)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = P.B * P.tiles_per_img * P.n_ntiles;
@@ -144,7 +231,7 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc::prefetch_tmap(&tmA);
         tc::prefetch_tmap(&tmB);
         for (int i = 0; i < P.stages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, EPI == 0 ? 4 : K1_EPI_WARPS_RM); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
@@ -215,37 +302,27 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
             const int n0 = nt * P.NB;
-            for (int col = 0; col < P.NB; col += 16) {
-                if (n0 + col >= P.C) break;                     // warp-uniform
-                uint32_t r[16];
-                tc::tmem_ld16(taddr + col, r);
-                tc::tmem_ld_wait();
-                if constexpr (EPI == 0) {
+            if constexpr (EPI == 0) {
+                for (int col = 0; col < P.NB; col += 16) {
+                    if (n0 + col >= P.C) break;                 // warp-uniform
+                    uint32_t r[16];
+                    tc::tmem_ld16(taddr + col, r);
+                    tc::tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int c = n0 + col + j;
                         if (rvalid && c < P.C) __stcs(orow + (size_t)c * P.hw, __uint_as_float(r[j]) * P.scale);
                     }
-                } else if (rvalid) {
-                    // row-major: lane = row, 16 consecutive output channels (C % 16 == 0 for this epilogue)
-                    const size_t m = (size_t)b * P.hw + p;
-                    float o[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        o[j] = __uint_as_float(r[j]) * P.scale + (P.bias ? __ldg(P.bias + n0 + col + j) : 0.f);
-                    if (P.out_f32) {
-                        float4* op = reinterpret_cast<float4*>((float*)P.out_rm + m * P.C + n0 + col);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                    } else {
-                        __nv_bfloat162 pk[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) pk[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
-                        uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)P.out_rm + m * P.C + n0 + col);
-                        op[0] = *reinterpret_cast<uint4*>(&pk[0]);
-                        op[1] = *reinterpret_cast<uint4*>(&pk[4]);
-                    }
                 }
+            } else {
+                // row-major (C % 16 == 0 for this epilogue): this warp's 32 rows, staged for coalesced stores
+                const int pw = ti * K1_BM + q * 32;             // first row of the warp inside the image
+                const int ncols = P.C - n0 < P.NB ? P.C - n0 : P.NB;
+                int c0 = 0, c1 = 0;
+                epi_split(ncols > 0 ? ncols : 0, P.out_f32 ? 4 : 2, (warp - 2) >> 2, K1_EPI_WARPS_RM / 4, &c0, &c1);
+                if (pw < P.hw && c1 > c0)
+                    epi_rowmajor(P, epi_scr + (warp - 2) * 4096, lane, taddr + c0, (size_t)b * P.hw + pw,
+                                 P.hw - pw < 32 ? P.hw - pw : 32, n0 + c0, c1 - c0);
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -257,6 +334,185 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 1) {
         tc::tc_fence_after();
         tc::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2-SM form of the projection GEMM (cta_group::2): a CTA pair owns a 256 x 256 output tile.  Each CTA stages its own
+// 128 rows of x and HALF of the W tile (128 of the 256 output channels) - 32 KB per k-block instead of 48 KB, so six
+// stages fit where the 1-SM kernel has four and the pipeline tolerates ~1.4 us of load latency instead of ~0.8 us (the
+// 1-SM kernel is latency-bound at 43 % tensor-pipe activity, profiles/r01_linear_gemm.md).  Only the leader CTA
+// (cluster rank 0) issues tcgen05.mma; both CTAs' TMA loads complete on the LEADER's full barrier; tcgen05.commit
+// multicasts the "slot free" / "accumulator ready" arrivals to both CTAs; each CTA's epilogue drains its own 128 TMEM
+// lanes and the peer's epilogue warps arrive remotely on the leader's "accumulator drained" barrier.
+constexpr int K2SM_NB = 256;                                   // output channels per tile (128 staged per CTA)
+constexpr int K2SM_STAGE = K1_A_BYTES + (K2SM_NB / 2) * 128;   // 32 KB
+constexpr int K2SM_STAGES = 6;
+
+namespace tc2 {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(tc::smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int x,
+                                                int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(tc::smem_u32(smem_dst)), "l"(m), "r"(bar_cluster_addr), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {   // one full warp in EACH CTA
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(smem_result)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs when the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            tc::smem_u32(bar)),
+        "h"((uint16_t)3)
+        : "memory");
+}
+}  // namespace tc2
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * K1_EPI_WARPS_RM, 1)
+k1_linear_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                     const K1Params P) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base_u32 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base_u32 - tc::smem_u32(smem_raw));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)K2SM_STAGES * K2SM_STAGE);
+    uint64_t* empty = full + K1_MAX_STAGES;
+    uint64_t* tfull = empty + K1_MAX_STAGES;
+    uint64_t* tempty = tfull + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint8_t* epi_scr = reinterpret_cast<uint8_t*>(full) + 256;   // 4 warps x 4 KB
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = tc2::cluster_ctarank();
+    const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+    // pair tiles: 256 rows x 256 channels; the N tile runs fastest so that the two channel halves of the same rows
+    // are in flight together (x is read from HBM once)
+    const int n_ntiles = P.C / K2SM_NB;
+    const int total_tiles = (P.hw / (2 * K1_BM)) * n_ntiles;
+
+    if (warp == 0 && lane == 0) {
+        tc::prefetch_tmap(&tmA);
+        tc::prefetch_tmap(&tmB);
+        for (int i = 0; i < K2SM_STAGES; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 2 * K1_EPI_WARPS_RM); }   // both CTAs' warps
+        tc::fence_barrier_init();
+    }
+    tc2::cluster_sync();                                        // the peer's barriers exist before anything remote
+    if (warp == 1) tc2::tmem_alloc2(tmem_ptr, 512);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 rows of x, own half of the W tile; bytes land on the leader's barrier
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+                const int nt = tile % n_ntiles, mt = tile / n_ntiles;
+                const int arow = mt * 2 * K1_BM + (int)rank * K1_BM;
+                const int brow = nt * K2SM_NB + (int)rank * (K2SM_NB / 2);
+                for (int kb = 0; kb < P.num_kb; ++kb) {
+                    tc::mbar_wait(empty + stage, phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * K2SM_STAGE;
+                    if (rank == 0) tc::mbar_arrive_expect_tx(full + stage, 2u * K2SM_STAGE);
+                    const uint32_t bar = tc2::mapa(full + stage, 0);
+                    tc2::tma_load_2d_2sm(sa, &tmA, bar, kb * K1_BK, arow);
+                    tc2::tma_load_2d_2sm(sa + K1_A_BYTES, &tmB, bar, kb * K1_BK, brow);
+                    if (++stage == K2SM_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader CTA only =====
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = tc::make_idesc_bf16(2 * K1_BM, K2SM_NB, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+                const int buf = it & 1;
+                const uint32_t bphase = (it >> 1) & 1;
+                tc::mbar_wait(tempty + buf, bphase ^ 1);       // both CTAs' epilogues drained this buffer
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 256;
+                for (int kb = 0; kb < P.num_kb; ++kb) {
+                    tc::mbar_wait(full + stage, phase);
+                    tc::tc_fence_after();
+                    const uint32_t sa = base_u32 + stage * K2SM_STAGE;
+                    const uint64_t adesc = tc::make_smem_desc(sa, 16, 1024);
+                    const uint64_t bdesc = tc::make_smem_desc(sa + K1_A_BYTES, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < K1_BK / 16; ++k)
+                        tc2::umma_bf16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    tc2::umma_commit_2sm(empty + stage);        // frees the slot in both CTAs
+                    if (++stage == K2SM_STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc2::umma_commit_2sm(tfull + buf);              // accumulator ready in both CTAs
+            }
+        }
+    } else {
+        // ===== epilogue (both CTAs): own 128 TMEM lanes -> registers -> row-major global =====
+        const int q = warp & 3;
+        const uint32_t tempty_leader0 = tc2::mapa(tempty, 0), tempty_leader1 = tc2::mapa(tempty + 1, 0);
+        int it = 0;
+        for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
+            const int buf = it & 1;
+            const uint32_t bphase = (it >> 1) & 1;
+            const int nt = tile % n_ntiles, mt = tile / n_ntiles;
+            const size_t m0w = (size_t)mt * 2 * K1_BM + rank * K1_BM + q * 32;       // first row of this warp
+            tc::mbar_wait(tfull + buf, bphase);
+            tc::tc_fence_after();
+            const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
+            const int n0 = nt * K2SM_NB;
+            int c0 = 0, c1 = 0;
+            epi_split(K2SM_NB, P.out_f32 ? 4 : 2, (warp - 2) >> 2, K1_EPI_WARPS_RM / 4, &c0, &c1);
+            epi_rowmajor(P, epi_scr + (warp - 2) * 4096, lane, taddr + c0, m0w, 32, n0 + c0, c1 - c0);
+            tc::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) tc2::mbar_arrive_cluster(buf ? tempty_leader1 : tempty_leader0);
+        }
+    }
+    tc::tc_fence_before();
+    tc2::cluster_sync();                                        // nobody leaves while the peer may still touch it
+    if (warp == 1) {
+        tc::tc_fence_after();
+        tc2::tmem_dealloc2(tmem_base, 512);
     }
 }
 
@@ -402,6 +658,24 @@ extern "C" int lc2is_linear_fwd(const void* d_x_bf16, const void* d_w_bf16, cons
     K1Params P;
     P.out = nullptr; P.out_rm = d_y; P.bias = d_bias; P.out_f32 = y_dtype == LC2IS_F32;
     P.B = 1; P.hw = (int)M; P.C = N; P.C_pad = N; P.n_sets = 1;
+    // 2-SM form (CTA pairs, 256 x 256 tiles) for shapes it tiles exactly and that fill the GPU more than once;
+    // LC2IS_LINEAR_2SM=0 / 1 forces the choice
+    static const int force_2sm = [] { const char* e = getenv("LC2IS_LINEAR_2SM"); return e ? atoi(e) : -1; }();
+    const bool fits_2sm = M % (2 * K1_BM) == 0 && N % K2SM_NB == 0;
+    const long long pair_tiles = (M / (2 * K1_BM)) * (N / K2SM_NB);
+    if (fits_2sm && (force_2sm == 1 || (force_2sm != 0 && pair_tiles >= 2LL * (sm_count() / 2)))) {
+        P.num_kb = K / K1_BK; P.scale = 1.f; P.NB = K2SM_NB; P.n_ntiles = N / K2SM_NB; P.tiles_per_img = 0; P.stages = K2SM_STAGES;
+        const size_t smem2 = (size_t)K2SM_STAGES * K2SM_STAGE + 1024 + 256 + K1_EPI_SCRATCH;
+        CUtensorMap tmA2, tmB2;
+        if (int e = make_tmap_2d_bf16(&tmA2, d_x_bf16, (uint64_t)M, (uint64_t)K, K1_BM, K1_BK)) return e;
+        if (int e = make_tmap_2d_bf16(&tmB2, d_w_bf16, (uint64_t)N, (uint64_t)K, K2SM_NB / 2, K1_BK)) return e;
+        LC2IS_CUDA(cudaFuncSetAttribute(k1_linear_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        long long grid2 = 2 * (long long)(sm_count() / 2);
+        if (grid2 > 2 * pair_tiles) grid2 = 2 * pair_tiles;
+        k1_linear_2sm_kernel<<<(unsigned)grid2, 64 + 32 * K1_EPI_WARPS_RM, smem2, (cudaStream_t)stream>>>(tmA2, tmB2, P);
+        LC2IS_CHECK_LAUNCH("k1_linear_2sm_kernel");
+        return 0;
+    }
     const int n_ntiles0 = (N + 255) / 256;
     P.NB = ((N + n_ntiles0 - 1) / n_ntiles0 + 15) / 16 * 16;
     P.n_ntiles = (N + P.NB - 1) / P.NB;
@@ -409,12 +683,12 @@ extern "C" int lc2is_linear_fwd(const void* d_x_bf16, const void* d_w_bf16, cons
     P.num_kb = K / K1_BK;
     P.scale = 1.f;
     const int stage_bytes = K1_A_BYTES + P.NB * 128;
-    int stages = (200 * 1024) / stage_bytes;
+    int stages = (232448 - 1024 - 256 - K1_EPI_SCRATCH) / stage_bytes;   // 227 KB of dynamic shared memory
     if (stages > K1_MAX_STAGES) stages = K1_MAX_STAGES;
     if (stages > P.num_kb * 2) stages = P.num_kb * 2;
     if (stages < 2) stages = 2;
     P.stages = stages;
-    size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + K1_EPI_SCRATCH;
     if (smem < 120 * 1024) smem = 120 * 1024;
     CUtensorMap tmA, tmB;
     if (int e = make_tmap_2d_bf16(&tmA, d_x_bf16, (uint64_t)M, (uint64_t)K, K1_BM, K1_BK)) return e;
@@ -423,7 +697,7 @@ extern "C" int lc2is_linear_fwd(const void* d_x_bf16, const void* d_w_bf16, cons
     const int total_tiles = P.tiles_per_img * P.n_ntiles;
     int grid = sm_count();
     if (grid > total_tiles) grid = total_tiles;
-    k1_logits_kernel<1><<<grid, K1_THREADS, smem, (cudaStream_t)stream>>>(tmA, tmB, P);
+    k1_logits_kernel<1><<<grid, 64 + 32 * K1_EPI_WARPS_RM, smem, (cudaStream_t)stream>>>(tmA, tmB, P);
     LC2IS_CHECK_LAUNCH("k1_logits_kernel<linear>");
     return 0;
 }

@@ -130,7 +130,9 @@ def test_fused_head_loss_matches_oracle():
 
 
 @pytest.mark.parametrize("M,K,N,out_dtype", [(300, 768, 512, torch.bfloat16), (1024, 768, 512, torch.float32),
-                                              (129, 64, 16, torch.float32), (5000, 384, 272, torch.bfloat16)])
+                                              (129, 64, 16, torch.float32), (5000, 384, 272, torch.bfloat16),
+                                              (777, 128, 192, torch.float32), (2049, 192, 384, torch.bfloat16),
+                                              (64, 64, 48, torch.bfloat16)])
 def test_linear_projection_gemm(M, K, N, out_dtype):
     """lc2is_linear_fwd (TextToPatch.visual forward on the tcgen05 pipeline): against an fp32 matmul of the same
     bf16-rounded operands (accumulation order only) and against the fp32 nn.Linear (bf16 operand rounding)."""
@@ -145,6 +147,31 @@ def test_linear_projection_gemm(M, K, N, out_dtype):
     tol = 2e-5 if out_dtype == torch.float32 else 1.0 / 128          # bf16 output rounding
     assert float((y - ref_same).abs().max()) <= tol * float(ref_same.abs().max())
     assert float((y - ref_fp32).abs().max()) <= 2e-2 * float(ref_fp32.abs().max())
+
+
+@pytest.mark.parametrize("M,K,N,out_dtype", [(32768, 768, 512, torch.bfloat16), (20480, 128, 256, torch.float32),
+                                              (38912, 768, 512, torch.float32)])
+def test_linear_projection_gemm_two_sm_form(M, K, N, out_dtype):
+    """Shapes that take the cta_group::2 kernel (M % 256 == 0, N % 256 == 0, at least two waves of CTA pairs): same
+    checks as above, on the device (the fp32 reference of a 32768 x 768 x 512 product is computed by torch there)."""
+    g = torch.Generator(device=DEV).manual_seed(13)
+    x = torch.randn(M, K, generator=g, device=DEV)
+    w = torch.randn(N, K, generator=g, device=DEV) * K ** -0.5
+    b = torch.randn(N, generator=g, device=DEV)
+    xb, wb = x.to(torch.bfloat16), w.to(torch.bfloat16)
+    y = ops.linear_fwd(xb, wb, b, out_dtype).float()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref_same = xb.float() @ wb.float().t() + b
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    tol = 2e-5 if out_dtype == torch.float32 else 1.0 / 128
+    err = (y - ref_same).abs()
+    assert float(err.max()) <= tol * float(ref_same.abs().max()), (float(err.max()), int(err.argmax()) // N, int(err.argmax()) % N)
+    # every row block and channel block written (no tile skipped): per-block error maxima are all small
+    blk = err.view(M // 128, 128, N // 128, 128).amax(dim=(1, 3))
+    assert float(blk.max()) <= tol * float(ref_same.abs().max())
 
 
 def test_text_to_patch_module_matches_reference_module(golden_dir):
