@@ -366,7 +366,10 @@ __device__ __forceinline__ uint32_t mapa(const void* p, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (release at CTA scope): the arrival orders this thread's TMEM reads, which tcgen05.wait::ld +
+    // tcgen05.fence::before_thread_sync have already completed; a cluster-scope release would also wait for the
+    // epilogue's global stores (measured as membar stalls)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int x,
                                                 int y) {
