@@ -127,20 +127,6 @@ struct K1Params {
 // writes them back as 8 stores of 4 rows x 128 contiguous bytes; two warps per TMEM lane quarter share the columns.
 constexpr int K1_EPI_WARPS_RM = 8;                 // row-major epilogue: two warps per TMEM lane quarter
 constexpr int K1_EPI_SCRATCH = K1_EPI_WARPS_RM * 4096;
-__device__ __forceinline__ void epi_put(uint8_t* scr, int lane, int chunk, uint4 v) {
-    *reinterpret_cast<uint4*>(scr + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
-}
-__device__ __forceinline__ void epi_flush(const uint8_t* scr, int lane, uint8_t* grow0, size_t row_stride_bytes,
-                                          int rows_valid, int chunks_valid) {
-    const int c = lane & 7;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = i * 4 + (lane >> 3);
-        const uint4 v = *reinterpret_cast<const uint4*>(scr + row * 128 + ((c ^ (row & 7)) << 4));
-        if (row < rows_valid && c < chunks_valid)
-            *reinterpret_cast<uint4*>(grow0 + (size_t)row * row_stride_bytes + (c << 4)) = v;
-    }
-}
 // one warp: rows [m0, m0 + 32) x columns [n0, n0 + ncols) of the row-major output from TMEM address `taddr`
 __device__ __forceinline__ void epi_rowmajor(const K1Params& P, uint8_t* scr, int lane, uint32_t taddr, size_t m0,
                                              int rows_valid, int n0, int ncols);

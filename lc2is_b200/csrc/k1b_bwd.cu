@@ -159,7 +159,9 @@ constexpr int DV_B_BYTES = (DV_BN / 64) * DV_KB * 128; // 4 boxes [16 k][64 d]
 constexpr int DV_STAGE = DV_A_BYTES + DV_B_BYTES;      // 12 KB
 constexpr int DV_MAX_STAGES = 12;
 
-__global__ void __launch_bounds__(KB_THREADS, 1)
+constexpr int DV_EPI_WARPS = 8;                        // two epilogue warps per TMEM lane quarter
+constexpr int DV_THREADS = 64 + 32 * DV_EPI_WARPS;
+__global__ void __launch_bounds__(DV_THREADS, 1)
 k1b_dv_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmT, const DvParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -169,6 +171,7 @@ k1b_dv_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ C
     uint64_t* tfull = empty + DV_MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint8_t* epi_scr = reinterpret_cast<uint8_t*>(full) + 512;  // 8 warps x (4 KB v_hat in + 4 KB gradient out)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = P.B * P.tiles_per_img * P.n_ntiles;
 
@@ -176,7 +179,7 @@ k1b_dv_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ C
         tc::prefetch_tmap(&tmG);
         tc::prefetch_tmap(&tmT);
         for (int i = 0; i < P.stages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, 4); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, DV_EPI_WARPS); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
@@ -247,60 +250,91 @@ k1b_dv_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ C
             const size_t m = (size_t)b * P.hw + (rvalid ? p : 0);
             const float inv = rvalid ? __ldg(P.inv_v + m) : 0.f;
             const float rr = (rvalid && P.normalize) ? __ldg(P.r + m) * gs : 0.f;
+            // 64 channels = 128 bytes of v_hat per row at a time.  The two warps of a lane quarter take alternate groups.
+            // v_hat is fetched coalesced (4 rows x 128 bytes per load) one group AHEAD into registers - the first group
+            // before the accumulator is even ready - parked in the warp's swizzled scratch and read back by the thread that
+            // owns the row; the gradient leaves the same way (a thread owns a ROW in TMEM: direct accesses touch 32 rows).
+            const int part = (warp - 2) >> 2;
+            uint8_t* scr_in = epi_scr + (warp - 2) * 8192;
+            uint8_t* scr_out = scr_in + 4096;
+            const int pw = ti * DV_BM + q * 32;
+            const int rows_valid = P.hw - pw < 0 ? 0 : (P.hw - pw < 32 ? P.hw - pw : 32);
+            const size_t m0 = (size_t)b * P.hw + pw;
+            const int d0 = nt * DV_BN;
+            const int n_groups = (P.D - d0 < DV_BN ? P.D - d0 : DV_BN) / 64;      // D % 64 == 0
+            uint4 pf[8];
+            auto ldg_group = [&](int g) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(P.v_hat + m0 * P.D + d0 + g * 64);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = i * 4 + (lane >> 3);
+                    pf[i] = row < rows_valid
+                                ? __ldg(reinterpret_cast<const uint4*>(src + (size_t)row * P.D * 2 + ((lane & 7) << 4)))
+                                : make_uint4(0u, 0u, 0u, 0u);
+                }
+            };
+            if (P.normalize && part < n_groups) ldg_group(part);
             tc::mbar_wait(tfull + buf, bphase);
             tc::tc_fence_after();
             const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
-            const int d0 = nt * DV_BN;
-            // v_hat of four 16-channel chunks is fetched ahead of the TMEM reads: one global-memory round trip per 64
-            // channels instead of one per 16 on the critical path of the tile
-            for (int col0 = 0; col0 < DV_BN; col0 += 64) {
-                if (d0 + col0 >= P.D) break;
-                uint4 vh[4][2];
-                if (rvalid && P.normalize) {
+            for (int g = part; g < n_groups; g += DV_EPI_WARPS / 4) {
+                const int col0 = g * 64;
+                if (P.normalize) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (d0 + col0 + 16 * k < P.D) {
-                            const uint4* vp = reinterpret_cast<const uint4*>(P.v_hat + m * P.D + d0 + col0 + 16 * k);
-                            vh[k][0] = __ldg(vp); vh[k][1] = __ldg(vp + 1);
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = i * 4 + (lane >> 3);
+                        *reinterpret_cast<uint4*>(scr_in + row * 128 + (((lane & 7) ^ (row & 7)) << 4)) = pf[i];
                     }
+                    __syncwarp();
+                    if (g + DV_EPI_WARPS / 4 < n_groups) ldg_group(g + DV_EPI_WARPS / 4);
                 }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int col = col0 + 16 * k;
-                    if (d0 + col >= P.D) break;
                     uint32_t acc[16];
                     tc::tmem_ld16(taddr + col, acc);
                     tc::tmem_ld_wait();
-                    if (rvalid) {
-                        float o[16];
-                        if (P.normalize) {
-                            const uint4 v0 = vh[k][0], v1 = vh[k][1];
-                            unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    float o[16];
+                    if (P.normalize) {
+                        const uint4 v0 = epi_get(scr_in, lane, 2 * k), v1 = epi_get(scr_in, lane, 2 * k + 1);
+                        unsigned w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float va = __uint_as_float(w[j] << 16), vb = __uint_as_float(w[j] & 0xffff0000u);
-                                o[2 * j] = (__uint_as_float(acc[2 * j]) * sg - va * rr) * inv;
-                                o[2 * j + 1] = (__uint_as_float(acc[2 * j + 1]) * sg - vb * rr) * inv;
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(acc[j]) * sg;
+                        for (int j = 0; j < 8; ++j) {
+                            const float va = __uint_as_float(w[j] << 16), vb = __uint_as_float(w[j] & 0xffff0000u);
+                            o[2 * j] = (__uint_as_float(acc[2 * j]) * sg - va * rr) * inv;
+                            o[2 * j + 1] = (__uint_as_float(acc[2 * j + 1]) * sg - vb * rr) * inv;
                         }
-                        if (P.out_f32) {
-                            float4* op = reinterpret_cast<float4*>((float*)P.grad_v + m * P.D + d0 + col);
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) op[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                        } else {
-                            __nv_bfloat162 pk[8];
+                        for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(acc[j]) * sg;
+                    }
+                    if (P.out_f32) {                            // 32 fp32 channels per 128-byte group: flush after two chunks
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) pk[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
-                            uint4* op = reinterpret_cast<uint4*>((__nv_bfloat16*)P.grad_v + m * P.D + d0 + col);
-                            op[0] = *reinterpret_cast<uint4*>(&pk[0]);
-                            op[1] = *reinterpret_cast<uint4*>(&pk[4]);
+                        for (int j = 0; j < 4; ++j)
+                            epi_put(scr_out, lane, (k & 1) * 4 + j,
+                                    make_uint4(__float_as_uint(o[4 * j]), __float_as_uint(o[4 * j + 1]),
+                                               __float_as_uint(o[4 * j + 2]), __float_as_uint(o[4 * j + 3])));
+                        if (k & 1) {
+                            __syncwarp();
+                            epi_flush(scr_out, lane,
+                                      reinterpret_cast<uint8_t*>(P.grad_v) + (m0 * P.D + d0 + col - 16) * 4,
+                                      (size_t)P.D * 4, rows_valid, 8);
+                            __syncwarp();
                         }
+                    } else {
+                        __nv_bfloat162 pk[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) pk[j] = __floats2bfloat162_rn(o[2 * j], o[2 * j + 1]);
+                        epi_put(scr_out, lane, 2 * k, *reinterpret_cast<uint4*>(&pk[0]));
+                        epi_put(scr_out, lane, 2 * k + 1, *reinterpret_cast<uint4*>(&pk[4]));
                     }
                 }
+                if (!P.out_f32) {
+                    __syncwarp();
+                    epi_flush(scr_out, lane, reinterpret_cast<uint8_t*>(P.grad_v) + (m0 * P.D + d0 + col0) * 2,
+                              (size_t)P.D * 2, rows_valid, 8);
+                }
+                __syncwarp();                                   // scr_in / scr_out are rewritten by the next group
             }
             tc::tc_fence_before();
             __syncwarp();
@@ -531,18 +565,18 @@ extern "C" int lc2is_cosine_logits_bwd_ex(const void* d_grad_logits, int g_dtype
         P.tiles_per_img = (hw + DV_BM - 1) / DV_BM;
         P.n_ntiles = (D + DV_BN - 1) / DV_BN;
         P.num_kb = C_pad / DV_KB;
-        P.stages = P.num_kb * 2 < DV_MAX_STAGES ? P.num_kb * 2 : DV_MAX_STAGES;
+        P.stages = P.num_kb * 2 < 8 ? P.num_kb * 2 : 8;       // the K loop is short: 8 x 12 KB leaves room for the epilogue scratch
         if (P.stages < 2) P.stages = 2;
         P.normalize = normalize; P.out_f32 = gv_dtype == LC2IS_F32; P.scale = logit_scale;
         CUtensorMap tmG, tmT;
         if (int e = make_tmap_3d_bf16(&tmG, d_grad_logits_bf16, B, C_pad, hw, DV_KB, 64)) return e;
         if (int e = make_tmap_2d_bf16(&tmT, d_t_hat, (uint64_t)n_sets * C_pad, D, DV_KB, 64)) return e;
-        size_t smem = (size_t)P.stages * DV_STAGE + 1024 + 256;
+        size_t smem = (size_t)P.stages * DV_STAGE + 1024 + 512 + DV_EPI_WARPS * 8192;
         if (smem < 120 * 1024) smem = 120 * 1024;
         LC2IS_CUDA(cudaFuncSetAttribute(k1b_dv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int total_tiles = B * P.tiles_per_img * P.n_ntiles;
         int grid = sm_count() < total_tiles ? sm_count() : total_tiles;
-        k1b_dv_kernel<<<grid, KB_THREADS, smem, st>>>(tmG, tmT, P);
+        k1b_dv_kernel<<<grid, DV_THREADS, smem, st>>>(tmG, tmT, P);
         LC2IS_CHECK_LAUNCH("k1b_dv_kernel");
     }
     // ---- dT ----------------------------------------------------------------------------------------

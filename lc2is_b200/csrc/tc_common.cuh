@@ -137,6 +137,38 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
 
 }  // namespace tc
 
+// ---- row-major epilogue staging: 32 rows x 128 bytes per warp through a swizzled 4 KB scratch -----------------------
+// (in TMEM a thread owns a ROW; direct stores / loads would touch 32 rows per warp instruction)
+__device__ __forceinline__ void epi_put(uint8_t* scr, int lane, int chunk, uint4 v) {
+    *reinterpret_cast<uint4*>(scr + lane * 128 + ((chunk ^ (lane & 7)) << 4)) = v;
+}
+__device__ __forceinline__ void epi_flush(const uint8_t* scr, int lane, uint8_t* grow0, size_t row_stride_bytes,
+                                          int rows_valid, int chunks_valid) {
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3);
+        const uint4 v = *reinterpret_cast<const uint4*>(scr + row * 128 + ((c ^ (row & 7)) << 4));
+        if (row < rows_valid && c < chunks_valid)
+            *reinterpret_cast<uint4*>(grow0 + (size_t)row * row_stride_bytes + (c << 4)) = v;
+    }
+}
+// coalesced load of 32 rows x 128 bytes into the scratch (rows past rows_valid read as zero)
+__device__ __forceinline__ void epi_fetch(uint8_t* scr, int lane, const uint8_t* grow0, size_t row_stride_bytes,
+                                          int rows_valid) {
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = i * 4 + (lane >> 3);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (row < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(grow0 + (size_t)row * row_stride_bytes + (c << 4)));
+        *reinterpret_cast<uint4*>(scr + row * 128 + ((c ^ (row & 7)) << 4)) = v;
+    }
+}
+__device__ __forceinline__ uint4 epi_get(const uint8_t* scr, int lane, int chunk) {
+    return *reinterpret_cast<const uint4*>(scr + lane * 128 + ((chunk ^ (lane & 7)) << 4));
+}
+
 // ---- host: tensor-map encode through the runtime's driver entry point (no -lcuda) ---------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
