@@ -55,12 +55,13 @@ rownorm_kernel(const T* __restrict__ x, long long n_sets, int rows_per_set, int 
                 }
             }
         };
-        auto store8 = [&](int d, const float (&v)[8], float denom) {
+        // x * (1 / denom) with a correctly rounded reciprocal: against F.normalize's x / denom the fp32 product can be
+        // one ulp off, which survives the rounding to bf16 for about one element in 2^15 (by one bf16 ulp) - and a
+        // true division per element is ten instructions where this is one (the kernel is issue-bound: 64 KB rows/us)
+        auto store8 = [&](int d, const float (&v)[8], float rden) {
             __nv_bfloat162 p[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                p[i] = __floats2bfloat162_rn(normalize ? v[2 * i] / denom : v[2 * i],
-                                             normalize ? v[2 * i + 1] / denom : v[2 * i + 1]);
+            for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(v[2 * i] * rden, v[2 * i + 1] * rden);
             *reinterpret_cast<uint4*>(o + d) = *reinterpret_cast<uint4*>(p);
         };
         float ss = 0.f;
@@ -79,11 +80,12 @@ rownorm_kernel(const T* __restrict__ x, long long n_sets, int rows_per_set, int 
             }
             ss = warp_sum(ss);
             const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-            if (lane == 0 && inv_norm) inv_norm[(size_t)set * rows_per_set + row] = 1.f / denom;
+            const float rden = __frcp_rn(denom);
+            if (lane == 0 && inv_norm) inv_norm[(size_t)set * rows_per_set + row] = rden;
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
                 const int d = lane * 8 + it * 256;
-                if (d < D) store8(d, v[it], denom);
+                if (d < D) store8(d, v[it], rden);
             }
             continue;
         }
@@ -95,11 +97,12 @@ rownorm_kernel(const T* __restrict__ x, long long n_sets, int rows_per_set, int 
         }
         ss = warp_sum(ss);
         const float denom = normalize ? fmaxf(sqrtf(ss), 1e-12f) : 1.f;
-        if (lane == 0 && inv_norm) inv_norm[(size_t)set * rows_per_set + row] = 1.f / denom;
+        const float rden = __frcp_rn(denom);
+        if (lane == 0 && inv_norm) inv_norm[(size_t)set * rows_per_set + row] = rden;
         for (int d = lane * 8; d < D; d += 256) {
             float v[8];
             load8(d, v);
-            store8(d, v, denom);
+            store8(d, v, rden);
         }
     }
 }
