@@ -131,3 +131,27 @@ def test_host_label_packing_matches_device_encoding():
         _lib.check(_lib.lib.lc2is_pack_labels_host_begin(lab.data_ptr(), n, C, ign, out2.data_ptr(), ctypes.byref(hd)), "begin")
         _lib.check(_lib.lib.lc2is_pack_labels_host_end(hd), "end")
         assert torch.equal(out, out2)
+
+
+def test_host_label_packing_avx2_path_in_a_subprocess():
+    """The AVX-512 / AVX2 choice is made once per process: run the same encoding check with AVX-512 switched off."""
+    import os, subprocess, sys
+    code = (
+        "import torch\n"
+        "from lc2is_b200 import _lib\n"
+        "g = torch.Generator().manual_seed(3)\n"
+        "for n, C, ign in ((100003, 150, 0), (65536, 847, 3), (33, 254, 253)):\n"
+        "    lab = torch.randint(-3, C + 4, (n,), generator=g); lab[::5] = ign\n"
+        "    nb = _lib.lib.lc2is_host_label_bytes(C)\n"
+        "    inr = (lab >= 0) & (lab < C)\n"
+        "    if nb == 2:\n"
+        "        out = torch.zeros(n, dtype=torch.uint16); ref = torch.where(inr, torch.where(lab == ign, lab | 0x8000, lab), torch.full_like(lab, 0xFFFF))\n"
+        "    else:\n"
+        "        out = torch.zeros(n, dtype=torch.uint8); ref = torch.where(inr, torch.where(lab == ign, torch.full_like(lab, 0xFE), lab), torch.full_like(lab, 0xFF))\n"
+        "    _lib.check(_lib.lib.lc2is_pack_labels_host(lab.data_ptr(), n, C, ign, out.data_ptr()), 'pack')\n"
+        "    assert torch.equal(out.to(torch.int64), ref), (n, C)\n"
+        "print('ok')\n")
+    env = dict(os.environ, LC2IS_NO_AVX512="1", LC2IS_PACK_THREADS="3")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
