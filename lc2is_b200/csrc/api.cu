@@ -408,8 +408,8 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
     // kernels of chunk i run on `stream` (engine.py:75 / :145 copy the whole batch up front).
     // Gradients are produced un-normalised (g = 1) per chunk; the 1/N_valid of the 'mean' reduction is
     // only known after the last chunk and is applied by K1b through its device-side grad_scale.
-    // With a pinned scratch buffer the int64 labels are narrowed to the packed uint16 form on the host
-    // (worker pool), chunk by chunk ahead of the copies: 2 bytes per pixel cross PCIe instead of 8.
+    // With a pinned scratch buffer the int64 labels are narrowed on the host (worker pool), chunk by chunk ahead of
+    // the copies: 1 byte per pixel (2 for C > 254) crosses PCIe instead of 8.
     const bool hpack = split && h_scratch != nullptr && C < 0x7fff;
     // h_scratch already holds the packed labels (of the first B - n_raw images)
     const bool prepacked = h_labels == nullptr || (flags & LC2IS_STEP_LABELS_PREPACKED);
