@@ -27,7 +27,8 @@ if ROOT not in sys.path:
 
 METRIC = "ADE20K-shape 512^2 images/sec (logits+loss+mIoU)"
 UNIT = "images/s"
-GEOM = {"A": (32, 32), "B": (128, 128)}          # low-res grid; SURVEY 8: G-A aux head x16, G-B main head x4
+GEOM = {"A": (32, 32, 512), "B": (128, 128, 512), "5": (64, 64, 1024)}   # (h, w, H = W): SURVEY 8 G-A aux head x16,
+#                                   G-B main head x4; "5" = BASELINE config 5 (1024^2, use --classes 847 --batch 8)
 L2_BYTES = 126 * 1024 * 1024
 
 
@@ -48,8 +49,9 @@ def parse():
 
 
 def workload_name(a, h, w):
-    return (f"cfg2: text_patch logits + fused upsample/softmax-CE fwd/bwd + argmax/confmat mIoU, "
-            f"B={a.batch}/GPU, {h}x{w}->512x512 (x{512 // h}), D=512, C={a.classes}, ignore_index=0")
+    H = GEOM[a.geometry][2]
+    return (f"cfg{'5' if a.geometry == '5' else '2'}: text_patch logits + fused upsample/softmax-CE fwd/bwd + argmax/confmat mIoU, "
+            f"B={a.batch}/GPU, {h}x{w}->{H}x{H} (x{H // h}), D=512, C={a.classes}, ignore_index=0")
 
 
 # --------------------------------------------------------------------------------------------
@@ -139,7 +141,7 @@ def run_reference(a):
     if rank != 0:
         return
     import torch
-    h, w = GEOM[a.geometry]
+    h, w, HW_ = GEOM[a.geometry]
     steps = a.steps if a.steps is not None else 5
     warmup = a.warmup if a.warmup is not None else 1
     cores = os.cpu_count() or 1
@@ -178,8 +180,8 @@ def run_b200(a):
     steps = a.steps if a.steps is not None else 200
     warmup = a.warmup if a.warmup is not None else 20
     warmup = max(warmup, 3)
-    h, w = GEOM[a.geometry]
-    B, C, D, H, W = a.batch, a.classes, 512, 512, 512
+    h, w, HW_ = GEOM[a.geometry]
+    B, C, D, H, W = a.batch, a.classes, 512, HW_, HW_
     backward = not a.no_backward
 
     # ---- inputs: rotate over enough distinct sets that a step's inputs never sit in the 126 MB L2
