@@ -106,8 +106,27 @@ struct K2SParams {
     unsigned long long* n_valid;  // SPLIT: += number of counted pixels (null = the caller counted them already)
 };
 
-template <int S, bool SPLIT>
-__device__ __noinline__ float k2_strip_slow(const float* st, int cs, int gl, unsigned vm, int n, int y0, int x0,
+// Where a group's four taps (a b / c d) of class c come from.  TapsSmem: the staged tile, one LDS.128.  TapsGlobal: the
+// class-plane-major map itself (L1 / L2) - for class counts whose staged tile would leave a handful of warps per SM
+// (C = 847: 54 KB per warp); look-aheads past the last class re-read it.
+constexpr size_t K2_GTAPS_SMEM = 28 * 1024;              // staged bytes per warp above which the taps stay in global memory
+struct TapsSmem {
+    const float4* p;                                        // quad of class 0
+    int cs4;                                                // float4 per class
+    __device__ __forceinline__ float4 get(int c) const { return p[(size_t)c * cs4]; }
+};
+struct TapsGlobal {
+    const float* b;                                         // class 0 of the image
+    size_t plane;
+    int oA, oB, oC, oD, C;
+    __device__ __forceinline__ float4 get(int c) const {
+        const float* q = b + (size_t)(c < C ? c : C - 1) * plane;
+        return make_float4(__ldg(q + oA), __ldg(q + oB), __ldg(q + oC), __ldg(q + oD));
+    }
+};
+
+template <int S, bool SPLIT, class TQ>
+__device__ __noinline__ float k2_strip_slow(const TQ tq, unsigned vm, int n, int y0, int x0,
                                             int u, const K2SParams& P, float gs, float* gA, float* gB,
                                             float* gC, float* gD) {
     const int C = P.C;
@@ -121,13 +140,13 @@ __device__ __noinline__ float k2_strip_slow(const float* st, int cs, int gl, uns
             const float ly = ((float)(2 * u + r) + 0.5f) * (1.f / S), lx = ((float)j + 0.5f) * (1.f / S);
             float m = -INFINITY;
             for (int c = 0; c < C; ++c) {
-                const float4 q = *reinterpret_cast<const float4*>(st + (size_t)c * cs + gl * 4);
+                const float4 q = tq.get(c);
                 const float L = fmaf(ly, q.z - q.x, q.x), R = fmaf(ly, q.w - q.y, q.y);
                 m = fmaxf(m, fmaf(lx, R - L, L));
             }
             float sum = 0.f, lt = 0.f;
             for (int c = 0; c < C; ++c) {
-                const float4 q = *reinterpret_cast<const float4*>(st + (size_t)c * cs + gl * 4);
+                const float4 q = tq.get(c);
                 const float L = fmaf(ly, q.z - q.x, q.x), R = fmaf(ly, q.w - q.y, q.y);
                 const float l = fmaf(lx, R - L, L);
                 sum += ex2f((l - m) * LOG2E);
@@ -138,7 +157,7 @@ __device__ __noinline__ float k2_strip_slow(const float* st, int cs, int gl, uns
                 const float uu = gs / sum;
                 const float wa = (1.f - ly) * (1.f - lx), wb = (1.f - ly) * lx, wc = ly * (1.f - lx), wd = ly * lx;
                 for (int c = 0; c < C; ++c) {
-                    const float4 q = *reinterpret_cast<const float4*>(st + (size_t)c * cs + gl * 4);
+                    const float4 q = tq.get(c);
                     const float L = fmaf(ly, q.z - q.x, q.x), R = fmaf(ly, q.w - q.y, q.y);
                     const float gg = ex2f((fmaf(lx, R - L, L) - m) * LOG2E) * uu - (c == t ? gs : 0.f);
                     atomicAdd(gA + (size_t)c * plane, gg * wa); atomicAdd(gB + (size_t)c * plane, gg * wb);
@@ -152,7 +171,7 @@ __device__ __noinline__ float k2_strip_slow(const float* st, int cs, int gl, uns
 // CSF = floats per class of the tile the warp's quads live in (16 for the stand-alone kernel's per-warp tile, 64 for
 // the 16-group CTA tile of the fused K2+K3 kernel); st = the warp's first tap quad of class 0.
 // CTA_SYNC: the taps were staged by the whole CTA (barrier instead of a warp sync).
-template <int S, bool SPLIT, int CSF, bool CTA_SYNC, int UNR = 2>
+template <int S, bool SPLIT, int CSF, bool CTA_SYNC, int UNR = 2, bool GTAPS = false>
 __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, bool active, int n, int GY0,
                                               int GX0, int lane) {
     constexpr int TPG = S / 2;                              // threads (lanes) per group
@@ -237,12 +256,19 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, boo
     float* gb = P.grad_low ? P.grad_low + (size_t)n * C * plane : nullptr;
     float* gA = gb ? gb + (size_t)Ya * P.w + Xa : nullptr; float* gB = gb ? gb + (size_t)Ya * P.w + Xb : nullptr;
     float* gC = gb ? gb + (size_t)Yb * P.w + Xa : nullptr; float* gD = gb ? gb + (size_t)Yb * P.w + Xb : nullptr;
-    const float4* st4 = reinterpret_cast<const float4*>(st) + gl;      // + c * CS4
+    using TQ = typename std::conditional<GTAPS, TapsGlobal, TapsSmem>::type;
+    TQ tq;
+    if constexpr (GTAPS) {
+        tq.b = P.low + (size_t)n * C * plane; tq.plane = plane; tq.C = C;
+        tq.oA = Ya * P.w + Xa; tq.oB = Ya * P.w + Xb; tq.oC = Yb * P.w + Xa; tq.oD = Yb * P.w + Xb;
+    } else {
+        tq.p = reinterpret_cast<const float4*>(st) + gl; tq.cs4 = CS4;
+    }
 
     // ---- softmax shift: M = max over classes of the group's taps --------------------------------------------
     float mx = -INFINITY, mn = INFINITY;
     for (int c = u; c < C; c += TPG) {
-        const float4 q = st4[c * CS4];
+        const float4 q = tq.get(c);
         mx = fmaxf(mx, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
         mn = fminf(mn, fminf(fminf(q.x, q.y), fminf(q.z, q.w)));
     }
@@ -282,7 +308,7 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, boo
                 for (int j = 0; j < S; ++j) {
                     if (!((vm >> (r * 16 + j)) & 1u)) continue;
                     const unsigned t = (lw[r * (S / 2) + (j >> 1)] >> (16 * (j & 1))) & 0xffffu;
-                    const float4 q = st4[t * CS4];
+                    const float4 q = tq.get(t);
                     const float L = fmaf(lyr, q.z - q.x, q.x), R = fmaf(lyr, q.w - q.y, q.y);
                     loss -= fmaf(((float)j + 0.5f) * RS, R - L, L);
                 }
@@ -297,17 +323,15 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, boo
         {
             // software pipeline: taps two classes ahead, exponentials one class ahead (the tile has two
             // padding class slots, so the look-ahead needs no bounds check)
-            const float4* qp = st4 + CS4;
             float2 eN, rN;
-            row_exp(st4[0], eN, rN);
-            float4 qn = *qp;
+            row_exp(tq.get(0), eN, rN);
+            float4 qn = tq.get(1);
 #pragma unroll UNR
             for (int c = 0; c < C; ++c) {
                 float2 e2 = eN;
                 const float2 r2 = rN;
                 row_exp(qn, eN, rN);
-                qp += CS4;
-                qn = *qp;
+                qn = tq.get(c + 2);
 #pragma unroll
                 for (int j = 0; j < S; ++j) {
                     U2[j] = fadd2(U2[j], e2);
@@ -355,7 +379,7 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, boo
                         const int j = 2 * jj + e;
                         if (!((vm >> (r * 16 + j)) & 1u)) continue;
                         const int t = (int)(e ? t2.y : t2.x);
-                        const float4 q = st4[t * CS4];
+                        const float4 q = tq.get(t);
                         const float L = fmaf(lyr, q.z - q.x, q.x), R = fmaf(lyr, q.w - q.y, q.y);
                         loss -= fmaf(((float)j + 0.5f) * RS, R - L, L);
                         if (t != cur) { flush(); cur = t; sw0 = 0; sw1 = 0; }
@@ -388,16 +412,14 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, boo
             float* dst = (holder && uy <= P.h && ux <= P.w)
                              ? gb + (size_t)clampi2(uy, 0, P.h - 1) * P.w + clampi2(ux, 0, P.w - 1) : nullptr;
             const float2 omy = make_float2(1.f - ly2.x, 1.f - ly2.y);
-            const float4* qp = st4 + CS4;
             float2 eN, rN;
-            row_exp(st4[0], eN, rN);
-            float4 qn = *qp;
+            row_exp(tq.get(0), eN, rN);
+            float4 qn = tq.get(1);
 #pragma unroll UNR
             for (int c = 0; c < C; ++c) {
                 const float2 e2 = eN, r2 = rN;
                 row_exp(qn, eN, rN);                         // class c+1
-                qp += CS4;
-                qn = *qp;                                    // class c+2
+                qn = tq.get(c + 2);                          // class c+2
                 float2 h2 = U2[S - 1], d2 = h2;
                 h2 = ffma2(h2, r2, U2[S - 2]);
 #pragma unroll
@@ -421,7 +443,7 @@ __device__ __forceinline__ void k2_strip_warp(const K2SParams& P, float* st, boo
             }
         }
     } else if (warp_any) {
-        loss += k2_strip_slow<S, SPLIT>(st, CS, gl, vm, n, y0, x0, u, P, gs, gA, gB, gC, gD);
+        loss += k2_strip_slow<S, SPLIT, TQ>(tq, vm, n, y0, x0, u, P, gs, gA, gB, gC, gD);
     }
     loss = warp_sum(loss);
     if (lane == 0 && loss != 0.f) atomicAdd(P.loss_sum, (double)loss);

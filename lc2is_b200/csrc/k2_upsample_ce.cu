@@ -449,6 +449,22 @@ k2_strip_kernel(const K2SParams P) {
     k2_strip_warp<S, SPLIT, CS, false>(P, st, true, n, GY0, GX0, lane);
 }
 
+// The same strips with the taps read from the class-plane-major map itself (no staged tile): for class counts whose
+// tile would not leave enough warps per SM (BASELINE config 5: C = 847 -> 54 KB per warp, four warps per SM).
+template <int S, bool SPLIT>
+__global__ void __launch_bounds__(128)
+k2_strip_gtaps_kernel(const K2SParams P) {
+    constexpr int TPG = S / 2, GPW = 32 / TPG, WGX = GPW / 2, CS = GPW * 4;
+    const int lane = threadIdx.x & 31;
+    const long long wt = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int tiles_per_img = P.nty * P.ntx;
+    if (wt >= (long long)P.B * tiles_per_img) return;       // whole warp; there is no CTA barrier below
+    const int n = (int)(wt / tiles_per_img);
+    const int trem = (int)(wt - (long long)n * tiles_per_img);
+    const int tyi = trem / P.ntx, txi = trem - tyi * P.ntx;
+    k2_strip_warp<S, SPLIT, CS, false, 2, true>(P, nullptr, true, n, tyi * 2, txi * WGX, lane);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Label prepass of the split path (power-of-two scale S): everything of the cross-entropy that depends on
 // the labels only, in one pass over the int64 label map:
@@ -764,7 +780,8 @@ extern "C" int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_la
         int wpc = 4;
         while (wpc > 1 && smem_warp * wpc > 56 * 1024) wpc /= 2;
         const size_t smem = smem_warp * wpc;
-        if (smem <= 200 * 1024) {
+        const bool gtaps = smem_warp > K2_GTAPS_SMEM;        // staged tile too large for a decent occupancy
+        if (smem <= 200 * 1024 || gtaps) {
             const int wgx = (64 / s) / 2;
             P.nty = (h + 1 + 1) / 2;
             P.ntx = (w + 1 + wgx - 1) / wgx;
@@ -775,7 +792,12 @@ extern "C" int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_la
                 kernel<<<grid, wpc * 32, smem, st>>>(P);
                 return 0;
             };
-            int e = s == 8 ? launch(k2_strip_kernel<8, false>) : launch(k2_strip_kernel<16, false>);
+            auto launch_g = [&](auto kernel) -> int {
+                kernel<<<(unsigned)((tiles + 3) / 4), 128, 0, st>>>(P);
+                return 0;
+            };
+            int e = gtaps ? (s == 8 ? launch_g(k2_strip_gtaps_kernel<8, false>) : launch_g(k2_strip_gtaps_kernel<16, false>))
+                          : (s == 8 ? launch(k2_strip_kernel<8, false>) : launch(k2_strip_kernel<16, false>));
             if (e) return e;
             LC2IS_CHECK_LAUNCH("k2_strip_kernel");
             if (d_grad_low_bf16) return lc2is_grad_to_bf16(d_grad_low, B, C, h * w, d_grad_low_bf16, stream);
@@ -980,7 +1002,7 @@ extern "C" int lc2is_upsample_ce_packed(const float* d_low, const uint16_t* d_la
     int wpc = 4;
     while (wpc > 1 && smem_warp * wpc > 56 * 1024) wpc /= 2;
     const size_t smem = smem_warp * wpc;
-    if (smem > 200 * 1024) return fail(LC2IS_ERR_UNSUPPORTED, "too many classes for the strip kernel%s");
+    const bool gtaps = smem_warp > K2_GTAPS_SMEM;            // staged tile too large for a decent occupancy
     const int wgx = (64 / s) / 2;
     P.nty = (h + 1 + 1) / 2;
     P.ntx = (w + 1 + wgx - 1) / wgx;
@@ -991,7 +1013,12 @@ extern "C" int lc2is_upsample_ce_packed(const float* d_low, const uint16_t* d_la
         kernel<<<grid, wpc * 32, smem, (cudaStream_t)stream>>>(P);
         return 0;
     };
-    int e = s == 8 ? launch(k2_strip_kernel<8, true>) : launch(k2_strip_kernel<16, true>);
+    auto launch_g = [&](auto kernel) -> int {
+        kernel<<<(unsigned)((tiles + 3) / 4), 128, 0, (cudaStream_t)stream>>>(P);
+        return 0;
+    };
+    int e = gtaps ? (s == 8 ? launch_g(k2_strip_gtaps_kernel<8, true>) : launch_g(k2_strip_gtaps_kernel<16, true>))
+                  : (s == 8 ? launch(k2_strip_kernel<8, true>) : launch(k2_strip_kernel<16, true>));
     if (e) return e;
     LC2IS_CHECK_LAUNCH("k2_strip_kernel(split)");
     return 0;
