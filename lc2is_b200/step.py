@@ -277,18 +277,24 @@ class HostStep:
             e1.record()
             e1.synchronize()
             t_copy = min(t_copy, e0.elapsed_time(e1) * 1e-3)
-        pack_per_img = 1.1 * t_pack / B                               # (slower next to the copies than alone)
         bw = B * H * W * 8 / t_copy                                   # bytes / s
-        v_bytes = B * hw * D * 2
-        def step_time(r):
-            copy_t = (v_bytes + (B - r) * H * W * lb + r * H * W * 8) / bw
-            return max(pack_per_img * (B - r), copy_t)
-        t_opt = min(step_time(r) for r in range(B + 1))
-        # the model ignores the contention between the two routes: stay all-packed unless the gain is clear, and take
-        # the smallest split within 5 % of the optimum
-        best = 0 if step_time(0) <= 1.1 * t_opt else min(r for r in range(B + 1) if step_time(r) <= 1.05 * t_opt)
+        best = self.pick_raw_images(B, B * hw * D * 2, H * W * lb, H * W * 8, 1.1 * t_pack / B, bw)
         self.calibration = {"pack_ms": t_pack * 1e3, "h2d_gbs": bw / 1e9, "n_raw": best, "threads": int(lib.lc2is_pack_threads())}
         return best
+
+    @staticmethod
+    def pick_raw_images(B: int, v_bytes: int, packed_img_bytes: int, raw_img_bytes: int, pack_s_per_img: float,
+                        h2d_bytes_per_s: float) -> int:
+        """How many of the B label maps should cross PCIe as int64: a step lasts max(host packing of the others, H2D copy
+        of everything).  The model ignores the contention between the two routes, so stay all-packed (0) unless the
+        gain is clear (> 10 %), and take the smallest split within 5 % of the optimum."""
+        def step_time(r):
+            copy_t = (v_bytes + (B - r) * packed_img_bytes + r * raw_img_bytes) / h2d_bytes_per_s
+            return max(pack_s_per_img * (B - r), copy_t)
+        t_opt = min(step_time(r) for r in range(B + 1))
+        if step_time(0) <= 1.1 * t_opt:
+            return 0
+        return min(r for r in range(B + 1) if step_time(r) <= 1.05 * t_opt)
 
     def _set_outputs(self, s) -> None:
         self.out_loss, self.out_n_valid, self.out_confmat = s.out_loss, s.out_n_valid, s.out_confmat

@@ -155,3 +155,19 @@ def test_host_label_packing_avx2_path_in_a_subprocess():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_label_route_selection_rule():
+    """HostStep.pick_raw_images: all label maps packed on a fast host, a growing share sent as int64 as the host gets
+    slower, everything raw when packing is hopeless (numbers of the bench shape: B=16, 512^2 labels, 16.8 MB of V)."""
+    from lc2is_b200.step import HostStep
+    B, HW, v = 16, 512 * 512, 16 * 1024 * 512 * 2
+    pick = lambda pack_ms, gbs: HostStep.pick_raw_images(B, v, HW, HW * 8, pack_ms * 1e-3 / B, gbs * 1e9)
+    assert pick(0.30, 55) == 0 and pick(0.42, 55) == 0             # packing at or below the copy time: stay all-packed
+    picks = [pick(ms, 55) for ms in (0.6, 1.0, 2.0, 5.0, 50.0)]
+    assert picks == sorted(picks) and picks[0] >= 1 and picks[-1] >= 15
+    assert pick(1.0, 10) <= pick(1.0, 55)                           # a slow link keeps more of the packing on the host
+    for ms, gbs in ((0.6, 55), (2.2, 52), (1.0, 20)):
+        r = pick(ms, gbs)
+        t = lambda k: max(ms * 1e-3 / B * (B - k), (v + (B - k) * HW + k * HW * 8) / (gbs * 1e9))
+        assert t(r) <= 1.05 * min(t(k) for k in range(B + 1)) + 1e-12
