@@ -171,3 +171,31 @@ def test_label_route_selection_rule():
         r = pick(ms, gbs)
         t = lambda k: max(ms * 1e-3 / B * (B - k), (v + (B - k) * HW + k * HW * 8) / (gbs * 1e9))
         assert t(r) <= 1.05 * min(t(k) for k in range(B + 1)) + 1e-12
+
+
+def test_host_label_packing_property():
+    """Property test (hypothesis): any int64 label vector, class count and ignore_index pack to the documented codes,
+    for the one-byte and the two-byte host form alike, whatever the length / alignment of the slice."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+    from lc2is_b200 import _lib
+    special = [0, 1, -1, 253, 254, 255, 256, 32766, 32767, 65535, 65536, 2 ** 31, -2 ** 31, 2 ** 62, -2 ** 62]
+
+    @hyp.settings(max_examples=150, deadline=None)
+    @hyp.given(st.integers(1, 600), st.integers(1, 300), st.sampled_from([-100, -1, 0, 3, 253, 299]),
+               st.integers(0, 7), st.randoms(use_true_random=False))
+    def check(C, n, ign, off, rnd):
+        vals = [rnd.choice(special) if rnd.random() < 0.2 else rnd.randrange(-2, C + 2) for _ in range(n)]
+        lab = torch.tensor([0] * off + vals, dtype=torch.int64)[off:]          # misaligned view of the source
+        nb = _lib.lib.lc2is_host_label_bytes(C)
+        out = torch.full((n + 16,), 9, dtype=torch.uint8 if nb == 1 else torch.uint16)
+        _lib.check(_lib.lib.lc2is_pack_labels_host(lab.data_ptr(), n, C, ign, out.data_ptr()), "pack")
+        inr = (lab >= 0) & (lab < C)
+        if nb == 1:
+            ref = torch.where(inr, torch.where(lab == ign, torch.full_like(lab, 0xFE), lab), torch.full_like(lab, 0xFF))
+        else:
+            ref = torch.where(inr, torch.where(lab == ign, lab | 0x8000, lab), torch.full_like(lab, 0xFFFF))
+        assert torch.equal(out[:n].to(torch.int64), ref)
+        assert bool((out[n:] == 9).all())
+
+    check()
