@@ -78,7 +78,8 @@ int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int hw, int D,
 
 /* TextToPatch.visual / .textual forward (model/text_patch.py:11-12,16-17): y[M,N] = x[M,K] W[N,K]^T + b[N] on the
  * logits GEMM's tcgen05 / TMEM / TMA pipeline.  x, W bf16 (W in nn.Linear's own [out,in] layout), b fp32 or NULL,
- * y bf16 or fp32 row major.  K % 64 == 0, N % 16 == 0. */
+ * y bf16 or fp32 row major.  K % 64 == 0, N % 16 == 0.  Shapes with M % 256 == 0, N % 256 == 0 and at least two
+ * waves of 256 x 256 tiles run the 2-SM (cta_group::2) form of the kernel, everything else the 1-SM form. */
 int lc2is_linear_fwd(const void* d_x_bf16, const void* d_w_bf16, const float* d_bias,
                      long long M, int N, int K, void* d_y, int y_dtype, lc2is_stream_t stream);
 
