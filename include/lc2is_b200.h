@@ -128,7 +128,8 @@ int lc2is_grad_to_bf16(const float* d_grad, int B, int C, int hw, void* d_grad_b
  *       input = F.interpolate(input, mode="bilinear", size=H); CrossEntropyLoss(input,target)
  *       model/loss.py:19-20 (AuxiliaryLoss)  and  final.py:44 + engine.py:94 (criterion),
  *       plus their autograd backward (engine.py:100).
- * lc2is_count_valid: n_valid += #{labels != ignore_index} (the 'mean' denominator).
+ * lc2is_count_valid: n_valid += #{labels in [0,C) and != ignore_index} (the 'mean' denominator; ids outside [0,C) are
+ *            skipped by every CE kernel - torch would device-assert on them - so they are not counted either).
  * d_low      [B, C, h, w] fp32 low-resolution logits.
  * d_labels   [B, H, W] int64, values in [0,C) or ignore_index.
  * d_grad_scale DEVICE fp32 scalar g: gradients are g * (softmax - onehot) scattered through
@@ -138,7 +139,7 @@ int lc2is_grad_to_bf16(const float* d_grad, int B, int C, int hw, void* d_grad_b
  * d_grad_low_bf16 [B, C_pad, h*w] bf16 out (overwritten, pad rows zeroed) or NULL.
  * The upsampled [B,C,H,W] tensor never exists in memory.
  */
-int lc2is_count_valid(const int64_t* d_labels, int64_t n, int64_t ignore_index,
+int lc2is_count_valid(const int64_t* d_labels, int64_t n, int C, int64_t ignore_index,
                       int64_t* d_n_valid, lc2is_stream_t stream);
 /* *d_scale = mult / *d_n_valid (0 if no valid pixel): the 'mean' gradient scale, no host sync. */
 int lc2is_mean_scale(const int64_t* d_n_valid, float mult, float* d_scale, lc2is_stream_t stream);

@@ -48,7 +48,7 @@ SIGNATURES = {
     "lc2is_cosine_logits_bwd_ex": (c_int, [_p, c_int, _p, _p, _p, _p, _p, c_int, c_int, c_int, c_int, c_int, c_int,
                                            c_float, _p, _p, c_int, _p, _p, _p, c_int]),
     "lc2is_grad_to_bf16": (c_int, [_p, c_int, c_int, c_int, _p, _p]),
-    "lc2is_count_valid": (c_int, [_p, c_int64, c_int64, _p, _p]),
+    "lc2is_count_valid": (c_int, [_p, c_int64, c_int, c_int64, _p, _p]),
     "lc2is_mean_scale": (c_int, [_p, c_float, _p, _p]),
     "lc2is_finalize_loss": (c_int, [_p, _p, _p, _p]),
     "lc2is_upsample_ce_fwd_bwd": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, _p, _p,

@@ -56,7 +56,7 @@ __global__ void finalize_loss_kernel(const double* loss_sum, const long long* n_
 using namespace lc2is;
 
 extern "C" const char* lc2is_last_error(void) { return g_err; }
-extern "C" int lc2is_abi_version(void) { return 3; }
+extern "C" int lc2is_abi_version(void) { return 4; }
 extern "C" int64_t lc2is_launch_count(void) { return g_launches.load(); }
 
 extern "C" int lc2is_mean_scale(const int64_t* d_n_valid, float mult, float* d_scale, lc2is_stream_t stream) {
@@ -528,7 +528,7 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
             STEP_RC(lc2is_ce_labels_prepass(d_labels + lab_off, nb, C, h, w, H, W, ignore_index, d_packed + lab_off,
                                             d_nvalid, gl, stream));
         else
-            STEP_RC(lc2is_count_valid(d_labels + lab_off, (int64_t)nb * H * W, ignore_index, d_nvalid, stream));
+            STEP_RC(lc2is_count_valid(d_labels + lab_off, (int64_t)nb * H * W, C, ignore_index, d_nvalid, stream));
         mark("prepass", st);
         if (i == 0) STEP_RC(lc2is_proto_normalize(d_t, 1, C, D, 1, d_that, d_invt, stream));
         STEP_RC(lc2is_cosine_logits_fwd(d_v + v_off, LC2IS_BF16, nb, hw, D, d_that, 1, C, 1, logit_scale,

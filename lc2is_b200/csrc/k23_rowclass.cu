@@ -1,0 +1,660 @@
+// k23_rc: bilinear x16 upsample + softmax cross-entropy (forward + backward) + argmax / confusion matrix in ONE
+// persistent kernel of independent warps - the dominant kernel of the head step at the aux-head geometry.
+//
+// Replaces  F.interpolate(bilinear, size=H) + CrossEntropyLoss fwd/bwd   (reference model/loss.py:17-21, engine.py:94-100)
+//      and  F.interpolate + Softmax2d + JaccardIndex's argmax / bincount (reference metrics.py:84-92, :127-134)
+// on the same low-resolution class-plane-major logits [B,C,h,w]; the upsampled [B,C,H,W] tensor never exists.
+//
+// Geometry (as in k2_strip.cuh): a GROUP (ky,kx), ky = -1..h-1, kx = -1..w-1, is the 16 x 16 pixel region that interpolates
+// between source cells (ky,kx)..(ky+1,kx+1) (index-clamped).  A JOB is two horizontally adjacent groups; a warp owns a
+// job from start to end (no CTA barrier anywhere), jobs are dealt round-robin to the warps of a persistent grid.
+//
+//   stage     the job's source cells of every class land in the warp's private shared-memory tile by ONE TMA box
+//             (4-D tensor map [B][C][h][w], box 1 x C x 2 x 8 starting on a 16-byte boundary; out-of-bounds cells are
+//             zero-filled and never used); the box of the warp's NEXT job is issued as soon as this one has been
+//             converted, so it lands behind the whole job.
+//   convert   lane = class: the cells become per-group quads (a, b, c-a, d-b), and the same sweep finds the softmax shift
+//             M = max tap of the group, the tap range and non-finite taps.
+//   row phase lane = one pixel row of one group (2 groups x 16 rows), one sweep over the classes does BOTH
+//             pass A of the cross-entropy - S(j) = sum_c E_c rho_c^j: the upsampled logit is linear along the row, so the
+//               16 exponentials of a (class,row) are a geometric progression: 2 ex2, then FADD2 / FMUL2 over column pairs
+//             and the running maximum of the argmax - v(j) = fma(j, delta, v0) as 8 FFMA2, one FMNMX3 per pixel and class
+//               PAIR, chunks of 6 classes: "if (cm > best) { best = cm; chunk = k }", then the winning chunk is rescanned
+//               per pixel for the FIRST class that reaches the maximum (torch.argmax's tie rule).
+//             The row then has its log-sum-exp, U(j) = valid / S(j) (to shared memory), target logits, the exact integer
+//             -onehot tap weights (run-length reductions) and its confusion-matrix counts.
+//   class phase lane = CLASS: for a (class, group) the 16 x 16 terms are E(y) rho(y)^j with E(y+1) = E(y) sigma and
+//             rho(y+1) = rho(y) tau - four ex2 per (class, group) - and  h = sum_j U(j) rho^j,  d = dh/drho  by one Horner
+//             sweep per row pair (two FFMA2 per pixel pair, U broadcast from shared memory) give the four tap gradients
+//             in registers: no cross-lane reduction; the six source cells of the job leave as one float reduction each.
+// Jobs whose taps are not finite or span more than K2_FAST_RANGE take exact per-pixel paths (warp-uniform; ATen's taps, so
+// 0 * inf poisons the same pixels as argmax(softmax(interpolate(x)))).
+#include "common.cuh"
+#include "k2_strip.cuh"
+#include "tc_common.cuh"
+#include <mutex>
+#include <unordered_map>
+
+namespace lc2is {
+
+constexpr int RC_S = 16;                 // scale
+constexpr int RC_CH = 6;                 // classes per argmax chunk (even)
+constexpr int RC_USTRIDE = 16 * 16 + 16; // floats per group in the U tile (+16: the two groups land in different banks)
+constexpr float RC_PAD = -1.0e30f;       // padding classes: exp -> 0, never the argmax
+
+struct RCParams {
+    const float* low;                // [B,C,h,w]
+    const unsigned short* labels;    // packed [B,H,W]: class id, bit 15 = ignore flag, 0xFFFF = not a class id
+    float* grad;                     // [B,C,h,w] accumulates the un-scaled gradient (or null: forward only)
+    double* loss_sum;
+    unsigned long long* n_valid;     // += counted pixels (or null)
+    unsigned long long* confmat;     // [C,C]
+    unsigned long long* per_image;   // [B,3,C] or null
+    long long* pred;                 // [B,H,W] or null
+    int onehot;                      // add the -onehot term to grad
+    int B, C, h, w, H, W;
+    int CP;                          // classes incl. padding (multiple of RC_CH)
+    int jpr;                         // jobs per group row = ceil((w + 1) / 2)
+    int use_tma;
+    long long njobs;
+    unsigned warp_bytes;             // shared memory per warp
+};
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y, int z,
+                                            int u) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(tc::smem_u32(smem_dst)), "l"(m), "r"(tc::smem_u32(bar)), "r"(x), "r"(y), "r"(z), "r"(u)
+        : "memory");
+}
+
+struct RCJob {
+    int n, ky, kx0;                  // image, group row (-1..h-1), first group column (2*jx - 1)
+};
+__device__ __forceinline__ RCJob rc_decode(const RCParams& P, long long job) {
+    RCJob J;
+    const int per_img = (P.h + 1) * P.jpr;
+    J.n = (int)(job / per_img);
+    const int rem = (int)(job - (long long)J.n * per_img);
+    const int gy = rem / P.jpr;
+    J.ky = gy - 1;
+    J.kx0 = 2 * (rem - gy * P.jpr) - 1;
+    return J;
+}
+
+// The cell tile of a job: rows ys, ys+1 and columns xs..xs+7 of every class, [c][2][8], out of bounds = 0 (never used).
+// The box starts on a 16-byte boundary (the TMA unit rejects other start addresses: xs is a multiple of 4 cells) at the
+// first cell the job's index-clamped taps touch, so no coordinate is negative.
+__device__ __forceinline__ int rc_xs(const RCJob& J) { return max(J.kx0, 0) & ~3; }
+__device__ __forceinline__ int rc_ys(const RCJob& J) { return max(J.ky, 0); }
+__device__ __forceinline__ void rc_stage(const RCParams& P, const CUtensorMap* tm, float* cells, uint64_t* bar,
+                                         const RCJob& J, int lane) {
+    const int xs = rc_xs(J), ys = rc_ys(J);
+    if (P.use_tma) {
+        if (lane == 0) {
+            tc::mbar_arrive_expect_tx(bar, (uint32_t)P.C * 64u);
+            tma_load_4d(cells, tm, bar, xs, ys, 0, J.n);
+        }
+    } else {
+        const float* base = P.low + (size_t)J.n * P.C * P.h * P.w;
+        for (int idx = lane; idx < P.C * 16; idx += 32) {
+            const int c = idx >> 4, r = (idx >> 3) & 1, cx = idx & 7;
+            const int y = ys + r, x = xs + cx;
+            float v = 0.f;
+            if (y < P.h && x < P.w) v = __ldg(base + ((size_t)c * P.h + y) * P.w + x);
+            cells[idx] = v;
+        }
+    }
+}
+
+// exact per-pixel argmax of one row with ATen's taps on the global map (non-finite logits; rare)
+// (results go through the warp's idle U tile: out[j] - a pointer to registers would put the caller's array on the stack)
+__device__ __noinline__ void rc_argmax_slow(const RCParams& P, int n, int ky, int kx, int i, bool row_in, int* out) {
+    const float ly = ((float)i + 0.5f) * (1.f / RC_S);
+    const int ya = ky < 0 ? 0 : ky, xa = kx < 0 ? 0 : kx;
+    const int yb = min(ya + 1, P.h - 1), xb = min(xa + 1, P.w - 1);
+    const float tyy = ky < 0 ? 0.f : ly;
+    const float* base = P.low + (size_t)n * P.C * P.h * P.w;
+#pragma unroll 1
+    for (int j = 0; j < RC_S; ++j) {
+        const float tx = kx < 0 ? 0.f : ((float)j + 0.5f) * (1.f / RC_S);
+        float best = -INFINITY;
+        int idx = 0;
+        bool bad = false;
+        for (int c = 0; c < P.C && row_in; ++c) {
+            const float* pc = base + (size_t)c * P.h * P.w;
+            const float qx = __ldg(pc + ya * P.w + xa), qy = __ldg(pc + ya * P.w + xb);
+            const float qz = __ldg(pc + yb * P.w + xa), qw = __ldg(pc + yb * P.w + xb);
+            const float r0 = fmaf(qy, tx, qx * (1.f - tx)), r1 = fmaf(qw, tx, qz * (1.f - tx));
+            const float v = fmaf(r1, tyy, r0 * (1.f - tyy));
+            bad |= !(v < INFINITY);
+            if (v > best) { best = v; idx = c; }
+        }
+        out[j] = bad ? 0 : idx;
+    }
+}
+
+// exact per-pixel cross-entropy of one row (index-clamped taps on the global map): returns sum(lse) of the valid pixels
+// and adds the softmax term of the gradient with float reductions
+__device__ __noinline__ float rc_ce_slow(const RCParams& P, int n, int ky, int kx, int i, unsigned vm) {
+    const int C = P.C;
+    const size_t plane = (size_t)P.h * P.w;
+    const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
+    const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);
+    const float* b = P.low + (size_t)n * C * plane;
+    const int oA = Ya * P.w + Xa, oB = Ya * P.w + Xb, oC = Yb * P.w + Xa, oD = Yb * P.w + Xb;
+    float* gb = P.grad ? P.grad + (size_t)n * C * plane : nullptr;
+    const float ly = ((float)i + 0.5f) * (1.f / RC_S);
+    float loss = 0.f;
+    for (int j = 0; j < RC_S; ++j) {
+        if (!((vm >> j) & 1u)) continue;
+        const float lx = ((float)j + 0.5f) * (1.f / RC_S);
+        float m = -INFINITY;
+        for (int c = 0; c < C; ++c) {
+            const float* q = b + (size_t)c * plane;
+            const float qa = __ldg(q + oA), qb = __ldg(q + oB), qc = __ldg(q + oC), qd = __ldg(q + oD);
+            const float L = fmaf(ly, qc - qa, qa), R = fmaf(ly, qd - qb, qb);
+            m = fmaxf(m, fmaf(lx, R - L, L));
+        }
+        float sum = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float* q = b + (size_t)c * plane;
+            const float qa = __ldg(q + oA), qb = __ldg(q + oB), qc = __ldg(q + oC), qd = __ldg(q + oD);
+            const float L = fmaf(ly, qc - qa, qa), R = fmaf(ly, qd - qb, qb);
+            sum += ex2f((fmaf(lx, R - L, L) - m) * LOG2E);
+        }
+        loss += logf(sum) + m;
+        if (gb) {
+            const float uu = 1.f / sum;
+            const float wa = (1.f - ly) * (1.f - lx), wb = (1.f - ly) * lx, wc = ly * (1.f - lx), wd = ly * lx;
+            for (int c = 0; c < C; ++c) {
+                const float* q = b + (size_t)c * plane;
+                const float qa = __ldg(q + oA), qb = __ldg(q + oB), qc = __ldg(q + oC), qd = __ldg(q + oD);
+                const float L = fmaf(ly, qc - qa, qa), R = fmaf(ly, qd - qb, qb);
+                const float gg = ex2f((fmaf(lx, R - L, L) - m) * LOG2E) * uu;
+                float* g = gb + (size_t)c * plane;
+                atomicAdd(g + oA, gg * wa); atomicAdd(g + oB, gg * wb);
+                atomicAdd(g + oC, gg * wc); atomicAdd(g + oD, gg * wd);
+            }
+        }
+    }
+    return loss;
+}
+
+__device__ __forceinline__ float fmax3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+template <int S>
+__global__ void __launch_bounds__(512, 1)
+k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RCParams P) {
+    static_assert(S == 16, "x16 geometry");
+    constexpr float RS = 1.f / S, LX0 = 0.5f / S;
+    constexpr int CH = RC_CH;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const long long gw = (long long)blockIdx.x * nwarps + warp;
+    const long long gstride = (long long)gridDim.x * nwarps;
+    if (gw >= P.njobs) return;                              // whole warp; there is no CTA barrier below
+
+    const int C = P.C, CP = P.CP;
+    unsigned char* wb = smem_raw + (size_t)warp * P.warp_bytes;
+    float* cells = reinterpret_cast<float*>(wb);                        // [C][2][8]    TMA landing zone
+    float* quads = cells + (size_t)CP * 16;                             // [CP][2 groups][4] = (a, b, c-a, d-b)
+    float* Usm = quads + (size_t)CP * 8;                                // [2][RC_USTRIDE]: U[g][j][row]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(Usm + 2 * RC_USTRIDE);
+    const size_t plane = (size_t)P.h * P.w;
+
+    if (lane == 0) {
+        tc::mbar_init(bar, 1);
+        tc::fence_barrier_init();
+        tc::prefetch_tmap(&tm);
+    }
+    __syncwarp();
+    unsigned parity = 0;
+    {
+        const RCJob J0 = rc_decode(P, gw);
+        rc_stage(P, &tm, cells, bar, J0, lane);
+    }
+
+    // row-phase lane mapping
+    const int gi = lane >> 4, i = lane & 15;
+    const float ly = ((float)i + 0.5f) * RS;
+    float2 J2[S / 2];
+#pragma unroll
+    for (int k = 0; k < S / 2; ++k) J2[k] = make_float2((float)(2 * k), (float)(2 * k + 1));
+
+#pragma unroll 1
+    for (long long job = gw; job < P.njobs; job += gstride) {
+        const RCJob J = rc_decode(P, job);
+        const int n = J.n, ky = J.ky, kx0 = J.kx0;
+        // ---- wait for the taps -----------------------------------------------------------------------------
+        if (P.use_tma) { tc::mbar_wait(bar, parity); parity ^= 1u; }
+        else __syncwarp();
+
+        // ---- convert (lane = class): quads, shift, range, non-finite ----------------------------------------
+        const bool gin0 = ky < P.h && kx0 < P.w;            // kx0 <= w-1 always; ky <= h-1 always
+        const bool gin1 = ky < P.h && kx0 + 1 < P.w;
+        float mx0 = -INFINITY, mn0 = INFINITY, mx1 = -INFINITY, mn1 = INFINITY;
+        bool bad = false;
+        {
+            const int xs = rc_xs(J), ys = rc_ys(J);
+            const int ya = (clampi2(ky, 0, P.h - 1) - ys) * 8, yb = (clampi2(ky + 1, 0, P.h - 1) - ys) * 8;
+            int xa[2], xb[2];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int kx = kx0 + g;
+                xa[g] = clampi2(kx, 0, P.w - 1) - xs;                 // 0..6 (phantom group: column w-1)
+                xb[g] = clampi2(kx + 1, 0, P.w - 1) - xs;
+            }
+            for (int k = lane; k < CP; k += 32) {
+                const float* cp = cells + k * 16;
+                float4 q0, q1;
+                if (k < C) {
+                    const float a0 = cp[ya + xa[0]], b0 = cp[ya + xb[0]], c0 = cp[yb + xa[0]], d0 = cp[yb + xb[0]];
+                    const float a1 = cp[ya + xa[1]], b1 = cp[ya + xb[1]], c1 = cp[yb + xa[1]], d1 = cp[yb + xb[1]];
+                    mx0 = fmaxf(mx0, fmaxf(fmaxf(a0, b0), fmaxf(c0, d0)));
+                    mn0 = fminf(mn0, fminf(fminf(a0, b0), fminf(c0, d0)));
+                    mx1 = fmaxf(mx1, fmaxf(fmaxf(a1, b1), fmaxf(c1, d1)));
+                    mn1 = fminf(mn1, fminf(fminf(a1, b1), fminf(c1, d1)));
+                    bad |= !(fabsf(a0) < INFINITY) | !(fabsf(b0) < INFINITY) | !(fabsf(c0) < INFINITY) | !(fabsf(d0) < INFINITY);
+                    if (gin1)
+                        bad |= !(fabsf(a1) < INFINITY) | !(fabsf(b1) < INFINITY) | !(fabsf(c1) < INFINITY) | !(fabsf(d1) < INFINITY);
+                    q0 = make_float4(a0, b0, c0 - a0, d0 - b0);
+                    q1 = make_float4(a1, b1, c1 - a1, d1 - b1);
+                } else {
+                    q0 = make_float4(RC_PAD, RC_PAD, 0.f, 0.f);
+                    q1 = q0;
+                }
+                reinterpret_cast<float4*>(quads)[k * 2] = q0;
+                reinterpret_cast<float4*>(quads)[k * 2 + 1] = q1;
+            }
+            // clamped staging hides ATen's second tap of the top / left border groups (row / column 1, weight 0):
+            // 0 * inf = NaN poisons those pixels in the reference - look at it on the global map
+            if (ky < 0 || kx0 < 0) {
+                const float* base = P.low + (size_t)n * C * plane;
+                for (int g = 0; g < 2; ++g) {
+                    const int kx = kx0 + g;
+                    if (!(ky < 0 || kx < 0) || kx >= P.w) continue;
+                    const int Ya = ky < 0 ? 0 : ky, Xa = kx < 0 ? 0 : kx;
+                    const int Yb = min(Ya + 1, P.h - 1), Xb = min(Xa + 1, P.w - 1);
+                    for (int k = lane; k < C; k += 32) {
+                        const float* pc = base + (size_t)k * plane;
+                        const float t1 = __ldg(pc + Ya * P.w + Xb), t2 = __ldg(pc + Yb * P.w + Xa), t3 = __ldg(pc + Yb * P.w + Xb);
+                        bad |= !(fabsf(t1) < INFINITY) | !(fabsf(t2) < INFINITY) | !(fabsf(t3) < INFINITY);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
+            mn0 = fminf(mn0, __shfl_xor_sync(0xffffffffu, mn0, o));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o));
+            mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
+        }
+        const bool nonfinite = __any_sync(0xffffffffu, bad);
+        __syncwarp();                                       // quads complete, cells free
+        // ---- the box of the next job lands behind this one ----------------------------------------------------
+        if (job + gstride < P.njobs) {
+            const RCJob Jn = rc_decode(P, job + gstride);
+            rc_stage(P, &tm, cells, bar, Jn, lane);
+        }
+
+        // ---- this lane's row: labels ---------------------------------------------------------------------------
+        const int kx = kx0 + gi;
+        const bool group_in = gi ? gin1 : gin0;
+        const int y = S * ky + S / 2 + i, x0 = S * kx + S / 2;
+        const bool row_in = group_in && y >= 0 && y < P.H;
+        unsigned lw16[S / 2];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int x = x0 + hh * (S / 2);
+            const bool in = row_in && x >= 0 && x < P.W;
+            uint4 t = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            if (in) t = __ldg(reinterpret_cast<const uint4*>(P.labels + ((size_t)n * P.H + y) * P.W + x));
+            lw16[hh * 4 + 0] = t.x; lw16[hh * 4 + 1] = t.y; lw16[hh * 4 + 2] = t.z; lw16[hh * 4 + 3] = t.w;
+        }
+        unsigned vm = 0;                                    // pixels counted by the CE (class id without the ignore flag)
+#pragma unroll
+        for (int k = 0; k < S / 2; ++k) {
+            if ((lw16[k] & 0xffffu) < (unsigned)C) vm |= 1u << (2 * k);
+            if ((lw16[k] >> 16) < (unsigned)C) vm |= 1u << (2 * k + 1);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, vm != 0);
+        const bool any0 = (bal & 0xffffu) != 0, any1 = (bal >> 16) != 0;
+        const float M = gi ? mx1 : mx0;
+        const bool wide = (any0 && !((mx0 - mn0) < K2_FAST_RANGE)) || (any1 && !((mx1 - mn1) < K2_FAST_RANGE));
+        const bool slow = nonfinite || wide;
+        const float4* Q = reinterpret_cast<const float4*>(quads) + gi;
+        float loss = 0.f;
+        int bidx[S];
+
+        if (!slow) {
+            // ================= row phase: pass A + running maximum, one sweep over the classes ======================
+            const float Mk = M * LOG2E;
+            float2 S2[S / 2];
+            float best[S];
+            int bch[S];
+#pragma unroll
+            for (int k = 0; k < S / 2; ++k) S2[k] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < S; ++j) { best[j] = -INFINITY; bch[j] = 0; }
+            const int nch = CP / CH;
+            const float4* qp = Q;
+#pragma unroll 1
+            for (int k = 0; k < nch; ++k) {
+                float cm[S];
+#pragma unroll
+                for (int p = 0; p < CH / 2; ++p) {
+                    const float4 qa = qp[0], qb = qp[2];
+                    qp += 4;
+                    const float La = fmaf(ly, qa.z, qa.x), Ra = fmaf(ly, qa.w, qa.y);
+                    const float Lb = fmaf(ly, qb.z, qb.x), Rb = fmaf(ly, qb.w, qb.y);
+                    const float rla = Ra - La, rlb = Rb - Lb;
+                    const float v0a = fmaf(rla, LX0, La), da = rla * RS;
+                    const float v0b = fmaf(rlb, LX0, Lb), db = rlb * RS;
+                    const float Ea = ex2f(fmaf(v0a, LOG2E, -Mk)), ra = ex2f(da * LOG2E);
+                    const float Eb = ex2f(fmaf(v0b, LOG2E, -Mk)), rb = ex2f(db * LOG2E);
+                    float2 e2a = make_float2(Ea, Ea * ra), e2b = make_float2(Eb, Eb * rb);
+                    const float2 r2a = bc2(ra * ra), r2b = bc2(rb * rb);
+                    const float2 da2 = bc2(da), db2 = bc2(db), va0 = bc2(v0a), vb0 = bc2(v0b);
+#pragma unroll
+                    for (int jj = 0; jj < S / 2; ++jj) {
+                        S2[jj] = fadd2(S2[jj], fadd2(e2a, e2b));
+                        if (jj < S / 2 - 1) { e2a = fmul2(e2a, r2a); e2b = fmul2(e2b, r2b); }
+                        const float2 va = ffma2(J2[jj], da2, va0), vb = ffma2(J2[jj], db2, vb0);
+                        if (p == 0) {
+                            cm[2 * jj] = fmaxf(va.x, vb.x);
+                            cm[2 * jj + 1] = fmaxf(va.y, vb.y);
+                        } else {
+                            cm[2 * jj] = fmax3f(va.x, vb.x, cm[2 * jj]);
+                            cm[2 * jj + 1] = fmax3f(va.y, vb.y, cm[2 * jj + 1]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    if (cm[j] > best[j]) { best[j] = cm[j]; bch[j] = k; }
+            }
+            // ---- log-sum-exp, U = valid / S -> shared memory ------------------------------------------------------
+            {
+                float lg = 0.f;
+                float* up = Usm + gi * RC_USTRIDE + i;
+#pragma unroll
+                for (int jj = 0; jj < S / 2; ++jj) {
+                    const bool va = (vm >> (2 * jj)) & 1u, vb = (vm >> (2 * jj + 1)) & 1u;
+                    const float sa = va ? S2[jj].x : 1.f, sb = vb ? S2[jj].y : 1.f;
+                    lg += lg2f(sa) + lg2f(sb);
+                    up[(2 * jj) * 16] = va ? rcpf(sa) : 0.f;
+                    up[(2 * jj + 1) * 16] = vb ? rcpf(sb) : 0.f;
+                }
+                loss = fmaf((float)__popc(vm), M, lg * LN2);
+            }
+            // ---- argmax phase 2: the FIRST class of the winning chunk that reaches the maximum ----------------------
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const int c0 = bch[j] * CH;
+                int bi = c0;
+#pragma unroll
+                for (int cc = CH - 1; cc >= 0; --cc) {
+                    const float4 q = Q[(c0 + cc) * 2];
+                    const float L = fmaf(ly, q.z, q.x), R = fmaf(ly, q.w, q.y);
+                    const float rl = R - L;
+                    const float v = fmaf((float)j, rl * RS, fmaf(rl, LX0, L));
+                    if (v == best[j]) bi = c0 + cc;
+                }
+                bidx[j] = bi;
+            }
+        } else {
+            int* tmp = reinterpret_cast<int*>(Usm) + lane * S;
+            rc_argmax_slow(P, n, ky, kx, i, row_in, tmp);
+#pragma unroll
+            for (int j = 0; j < S; ++j) bidx[j] = tmp[j];
+            if (vm) loss = rc_ce_slow(P, n, ky, kx, i, vm);
+        }
+
+        // ---- target logits, -onehot term (exact integer tap weights, run-length along the row) --------------------
+        if (vm) {
+            const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
+            const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);
+            const size_t oA = (size_t)Ya * P.w + Xa, oB = (size_t)Ya * P.w + Xb, oC = (size_t)Yb * P.w + Xa, oD = (size_t)Yb * P.w + Xb;
+            const float* lbase = P.low + (size_t)n * C * plane;
+            float* gbase = (P.grad && P.onehot) ? P.grad + (size_t)n * C * plane : nullptr;
+            constexpr float WSC = 1.f / (float)(4 * S * S);
+            const int lyi = 2 * i + 1;
+            int cur = -1, sw0 = 0, sw1 = 0;
+            float tv0 = 0.f, tdl = 0.f;
+            auto flush = [&]() {
+                if (cur < 0 || !gbase) return;
+                float* gp = gbase + (size_t)cur * plane;
+                atomicAdd(gp + oA, -(float)((2 * S - lyi) * sw0) * WSC); atomicAdd(gp + oB, -(float)((2 * S - lyi) * sw1) * WSC);
+                atomicAdd(gp + oC, -(float)(lyi * sw0) * WSC);           atomicAdd(gp + oD, -(float)(lyi * sw1) * WSC);
+            };
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                if (!((vm >> j) & 1u)) continue;
+                const int lab = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0xffffu);
+                if (lab != cur) {
+                    flush();
+                    cur = lab; sw0 = 0; sw1 = 0;
+                    float qa, qb, qc, qd;
+                    if (!slow) { const float4 q = Q[lab * 2]; qa = q.x; qb = q.y; qc = q.z; qd = q.w; }
+                    else {
+                        const float* q = lbase + (size_t)lab * plane;
+                        qa = __ldg(q + oA); qb = __ldg(q + oB); qc = __ldg(q + oC) - qa; qd = __ldg(q + oD) - qb;
+                    }
+                    const float L = fmaf(ly, qc, qa), R = fmaf(ly, qd, qb);
+                    const float rl = R - L;
+                    tv0 = fmaf(rl, LX0, L); tdl = rl * RS;
+                }
+                loss -= fmaf((float)j, tdl, tv0);
+                sw0 += 2 * S - (2 * j + 1);
+                sw1 += 2 * j + 1;
+            }
+            flush();
+        }
+
+        // ---- predictions, counts --------------------------------------------------------------------------------
+        {
+            unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                const int x = x0 + j;
+                bool valid = row_in && x >= 0 && x < P.W;
+                int t = 0;
+                const int pr = bidx[j];
+                if (valid) {
+                    if (P.pred) P.pred[((size_t)n * P.H + y) * P.W + x] = pr;
+                    t = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0x7fffu);   // bit 15: ignore flag of the CE
+                    valid = t < C;
+                }
+                const unsigned act = __ballot_sync(0xffffffffu, valid);
+                if (valid) {
+                    const int key = t * C + pr;
+                    const unsigned m = __match_any_sync(act, key);
+                    if (lane == __ffs(m) - 1) {
+                        const unsigned long long cnt = (unsigned long long)__popc(m);
+                        atomicAdd(&P.confmat[key], cnt);
+                        if (pimg) {
+                            if (t == pr) atomicAdd(&pimg[t], cnt);
+                            atomicAdd(&pimg[C + t], cnt);
+                            atomicAdd(&pimg[2 * C + pr], cnt);
+                        }
+                    }
+                }
+            }
+        }
+        {
+            int cnt = __popc(vm);
+            loss = warp_sum(loss);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+            if (lane == 0) {
+                if (loss != 0.f) atomicAdd(P.loss_sum, (double)loss);
+                if (P.n_valid && cnt) atomicAdd(P.n_valid, (unsigned long long)cnt);
+            }
+        }
+        __syncwarp();                                       // U tile complete
+
+        // ================= class phase (lane = class): tap gradients by Horner sweeps ==============================
+        if (!slow && P.grad != nullptr && (any0 || any1)) {
+            float* gimg = P.grad + (size_t)n * C * plane;
+            const int cy0 = clampi2(ky, 0, P.h - 1), cy1 = clampi2(ky + 1, 0, P.h - 1);
+            int cxs[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) cxs[c] = clampi2(kx0 + c, 0, P.w - 1);
+            const float Mk0 = mx0 * LOG2E, Mk1 = mx1 * LOG2E;
+#pragma unroll 1
+            for (int kb = 0; kb < C; kb += 32) {
+                const int k = kb + lane;
+                const int kk = k < CP ? k : CP - 1;
+                float cell[6];
+#pragma unroll
+                for (int c = 0; c < 6; ++c) cell[c] = 0.f;
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    if (!(g ? any1 : any0)) continue;
+                    const float4 q = reinterpret_cast<const float4*>(quads)[kk * 2 + g];     // a, b, c-a, d-b
+                    const float b0 = q.y - q.x, gm = q.w - q.z;
+                    const float L0 = fmaf(0.5f * RS, q.z, q.x), rl0 = fmaf(0.5f * RS, gm, b0);
+                    const float aE0 = fmaf(fmaf(rl0, LX0, L0), LOG2E, -(g ? Mk1 : Mk0));
+                    const float aS = fmaf(gm, LX0, q.z) * (RS * LOG2E);
+                    const float E0 = ex2f(aE0), sg = ex2f(aS), r0 = ex2f(rl0 * (RS * LOG2E)), ta = ex2f(gm * (RS * RS * LOG2E));
+                    const float sg2 = sg * sg, ta2 = ta * ta;
+                    float2 e2a = make_float2(E0, E0 * sg), r2a = make_float2(r0, r0 * ta);
+                    float2 e2b = fmul2(e2a, bc2(sg2)), r2b = fmul2(r2a, bc2(ta2));
+                    const float2 sg4 = bc2(sg2 * sg2), ta4 = bc2(ta2 * ta2);
+                    float2 aG = make_float2(0.f, 0.f), aX = aG, aYG = aG, aYX = aG;
+                    const float4* U4 = reinterpret_cast<const float4*>(Usm + g * RC_USTRIDE);
+#pragma unroll
+                    for (int up = 0; up < 4; ++up) {
+                        // rows 4up..4up+3: chain a = rows (4up, 4up+1), chain b = rows (4up+2, 4up+3)
+                        float4 u = U4[(S - 1) * 4 + up];
+                        float2 ha = make_float2(u.x, u.y), hb = make_float2(u.z, u.w);
+                        float2 dA = ha, dB = hb;
+                        u = U4[(S - 2) * 4 + up];
+                        ha = ffma2(ha, r2a, make_float2(u.x, u.y));
+                        hb = ffma2(hb, r2b, make_float2(u.z, u.w));
+#pragma unroll
+                        for (int j = S - 3; j >= 0; --j) {
+                            u = U4[j * 4 + up];
+                            dA = ffma2(dA, r2a, ha);
+                            dB = ffma2(dB, r2b, hb);
+                            ha = ffma2(ha, r2a, make_float2(u.x, u.y));
+                            hb = ffma2(hb, r2b, make_float2(u.z, u.w));
+                        }
+                        const float2 Ga = fmul2(e2a, ha), Gb = fmul2(e2b, hb);                       // sum_j g
+                        const float2 Xa = fmul2(fmul2(e2a, r2a), dA), Xb = fmul2(fmul2(e2b, r2b), dB);   // sum_j j g
+                        const float2 lya = make_float2((4 * up + 0.5f) * RS, (4 * up + 1.5f) * RS);
+                        const float2 lyb = make_float2((4 * up + 2.5f) * RS, (4 * up + 3.5f) * RS);
+                        aG = fadd2(aG, fadd2(Ga, Gb));
+                        aX = fadd2(aX, fadd2(Xa, Xb));
+                        aYG = ffma2(lya, Ga, ffma2(lyb, Gb, aYG));
+                        aYX = ffma2(lya, Xa, ffma2(lyb, Xb, aYX));
+                        if (up < 3) {
+                            e2a = fmul2(e2a, sg4); e2b = fmul2(e2b, sg4);
+                            r2a = fmul2(r2a, ta4); r2b = fmul2(r2b, ta4);
+                        }
+                    }
+                    const float G = aG.x + aG.y, X = aX.x + aX.y, YG = aYG.x + aYG.y, YX = aYX.x + aYX.y;
+                    const float SX = fmaf(X, RS, G * LX0);              // sum lambda_x g
+                    const float SYX = fmaf(YX, RS, YG * LX0);           // sum lambda_y lambda_x g
+                    const float gD = SYX, gB = SX - SYX, gC = YG - SYX, gA = (G - SX) - gC;
+                    cell[g] += gA; cell[g + 1] += gB; cell[3 + g] += gC; cell[3 + g + 1] += gD;
+                }
+                if (k < C) {
+                    float* gk = gimg + (size_t)k * plane;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        if (cell[c] != 0.f) atomicAdd(gk + (size_t)cy0 * P.w + cxs[c], cell[c]);
+                        if (cell[3 + c] != 0.f) atomicAdd(gk + (size_t)cy1 * P.w + cxs[c], cell[3 + c]);
+                    }
+                }
+            }
+        }
+        __syncwarp();                                       // quads / U free for the next job
+    }
+}
+
+// ---- host: 4-D fp32 tensor map of the low-resolution logits, cached per (pointer, shape) ---------------------------
+struct RCMapKey {
+    const void* p; int B, C, h, w;
+    bool operator==(const RCMapKey& o) const { return p == o.p && B == o.B && C == o.C && h == o.h && w == o.w; }
+};
+struct RCMapHash {
+    size_t operator()(const RCMapKey& k) const {
+        size_t x = (size_t)k.p;
+        x ^= ((size_t)k.B * 1000003u) ^ ((size_t)k.C << 20) ^ ((size_t)k.h << 40) ^ ((size_t)k.w << 52);
+        return x * 0x9E3779B97F4A7C15ull;
+    }
+};
+static int rc_tensor_map(const float* low, int B, int C, int h, int w, CUtensorMap* out) {
+    static std::mutex mu;
+    static std::unordered_map<RCMapKey, CUtensorMap, RCMapHash> cache;
+    const RCMapKey key{low, B, C, h, w};
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return 0; }
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return fail(LC2IS_ERR_ARG, "cuTensorMapEncodeTiled entry point not found%s");
+    cuuint64_t dims[4] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)w * 4, (cuuint64_t)w * h * 4, (cuuint64_t)w * h * C * 4};
+    cuuint32_t box[4] = {8, 2, (cuuint32_t)C, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)low, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(LC2IS_ERR_ARG, "cuTensorMapEncodeTiled(low) failed (%s%lld)", "", (long long)r);
+    if (cache.size() >= 256) cache.clear();
+    cache.emplace(key, *out);
+    return 0;
+}
+
+static size_t rc_warp_bytes(int C) {
+    const int CP = (C + RC_CH - 1) / RC_CH * RC_CH;
+    size_t b = (size_t)CP * (16 + 8) * 4 + (size_t)2 * RC_USTRIDE * 4 + 16;
+    return (b + 127) / 128 * 128;
+}
+
+// warps per CTA (one CTA per SM) for C classes; 0 = does not fit
+int rc_warps_for(int C) {
+    const size_t wb = rc_warp_bytes(C);
+    int nw = (int)((size_t)220 * 1024 / wb);
+    if (nw > 16) nw = 16;
+    return nw >= 8 ? nw : 0;
+}
+
+int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, int C, int h, int w, int H, int W,
+                  double* d_loss_sum, float* d_grad_low, int onehot, int64_t* d_n_valid, int64_t* d_confmat,
+                  int64_t* d_per_image, int64_t* d_pred, cudaStream_t st) {
+    const int nw = rc_warps_for(C);
+    if (!nw) return LC2IS_ERR_UNSUPPORTED;
+    RCParams P;
+    P.low = d_low; P.labels = d_labels_packed; P.grad = d_grad_low; P.loss_sum = d_loss_sum;
+    P.n_valid = (unsigned long long*)d_n_valid; P.confmat = (unsigned long long*)d_confmat;
+    P.per_image = (unsigned long long*)d_per_image; P.pred = (long long*)d_pred; P.onehot = onehot;
+    P.B = B; P.C = C; P.h = h; P.w = w; P.H = H; P.W = W;
+    P.CP = (C + RC_CH - 1) / RC_CH * RC_CH;
+    P.jpr = (w + 1 + 1) / 2;
+    P.njobs = (long long)B * (h + 1) * P.jpr;
+    P.warp_bytes = (unsigned)rc_warp_bytes(C);
+    P.use_tma = (C <= 256 && w % 4 == 0 && ((uintptr_t)d_low % 16) == 0 && !getenv("LC2IS_RC_NO_TMA")) ? 1 : 0;
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (P.use_tma)
+        if (int e = rc_tensor_map(d_low, B, C, h, w, &tm)) return e;
+    const size_t smem = (size_t)P.warp_bytes * nw;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        attr_err = cudaFuncSetAttribute(k23_rc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    });
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(k23_rc_kernel)");
+    long long ctas = (P.njobs + nw - 1) / nw;
+    if (ctas > sm_count()) ctas = sm_count();
+    k23_rc_kernel<16><<<(unsigned)ctas, nw * 32, smem, st>>>(tm, P);
+    LC2IS_CHECK_LAUNCH("k23_rc_kernel");
+    return 0;
+}
+
+}  // namespace lc2is

@@ -28,8 +28,9 @@ namespace lc2is {
 
 // ---------------------------------------------------------------------------------------------
 // count valid labels (the 'mean' denominator)
-__global__ void k2_count_valid_kernel(const long long* __restrict__ labels, long long n, long long ignore,
+__global__ void k2_count_valid_kernel(const long long* __restrict__ labels, long long n, long long C, long long ignore,
                                       unsigned long long* __restrict__ out) {
+    auto counted = [&](long long v) { return (unsigned long long)v < (unsigned long long)C && v != ignore; };
     long long cnt = 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -38,9 +39,9 @@ __global__ void k2_count_valid_kernel(const long long* __restrict__ labels, long
     const longlong2* l2 = reinterpret_cast<const longlong2*>(labels);
     for (long long k = i; k < n2; k += stride) {
         longlong2 v = __ldg(l2 + k);
-        cnt += (v.x != ignore) + (v.y != ignore);
+        cnt += (int)counted(v.x) + (int)counted(v.y);
     }
-    if (i == 0 && (n & 1)) cnt += labels[n - 1] != ignore;
+    if (i == 0 && (n & 1)) cnt += counted(labels[n - 1]);
     int c = (int)cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -719,7 +720,7 @@ __global__ void k2_grad_to_bf16_kernel(const float* __restrict__ g, int C, int C
 
 using namespace lc2is;
 
-extern "C" int lc2is_count_valid(const int64_t* d_labels, int64_t n, int64_t ignore_index,
+extern "C" int lc2is_count_valid(const int64_t* d_labels, int64_t n, int C, int64_t ignore_index,
                                  int64_t* d_n_valid, lc2is_stream_t stream) {
     if (int e = ensure_device()) return e;
     if (n < 0) return fail(LC2IS_ERR_SHAPE, "negative n%s");
@@ -731,7 +732,7 @@ extern "C" int lc2is_count_valid(const int64_t* d_labels, int64_t n, int64_t ign
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     k2_count_valid_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        (const long long*)d_labels, n, ignore_index, (unsigned long long*)d_n_valid);
+        (const long long*)d_labels, n, (long long)C, ignore_index, (unsigned long long*)d_n_valid);
     LC2IS_CHECK_LAUNCH("k2_count_valid_kernel");
     return 0;
 }

@@ -2,9 +2,11 @@
 //
 // Replaces reference metrics.py:84-92 / :63-69 / :127-134 and utils.py:15-22:
 //   F.interpolate(bicubic|bilinear) -> Softmax2d -> JaccardIndex (argmax + bincount).
-// softmax is strictly monotone, so the argmax is taken on the logits (first index wins ties,
-// like torch.argmax); NaN / +inf anywhere in a pixel's class vector gives class 0, which is
-// what argmax(softmax(x)) returns for an all-NaN row.
+// The argmax is taken on the logits (first index wins ties, like torch.argmax).  The reference takes it on
+// softmax(logits) (metrics.py:92): in exact arithmetic the same pixel, in fp32 softmax can round a near-tie (top-2 gap
+// below ~2^-23 relative to the row sum's scale) onto one value and then the FIRST of the merged classes wins; the
+// parity tests bound that set (tests/test_gpu_k3.py::test_argmax_rule_vs_reference_softmax).  NaN / +inf anywhere in a
+// pixel's class vector gives class 0, which is what argmax(softmax(x)) returns for an all-NaN row.
 //
 // Three kernels:
 //   k3_full    - logits materialised at mask resolution.  HBM-bound stream: 128-bit loads,
@@ -21,7 +23,7 @@ namespace lc2is {
 
 constexpr int K3_THREADS = 256;
 constexpr int K3_SMEM_HIST_MAX_C = 300;   // 16-bit counters, two per word: 300*300*2 = 180,000 B
-constexpr int K3_FLUSH_ITEMS = 60;        // flush before a 16-bit counter can overflow (60 * 1024 px < 65536)
+constexpr int K3_FLUSH_PIXELS = 60 * 1024; // flush before a 16-bit counter can overflow (< 65536 pixels between flushes)
 
 struct ArgmaxState {
     float best;
@@ -143,7 +145,7 @@ k3_full_kernel(const T* __restrict__ logits, int N, int C, int H, int W,
     for (long long it = it0; it < it1; ++it) {
         const int n = (int)(it / chunks_per_img);
         const int k = (int)(it - (long long)n * chunks_per_img);
-        if (n != cur_img || since_flush >= K3_FLUSH_ITEMS) {
+        if (n != cur_img || since_flush >= K3_FLUSH_PIXELS / chunk) {   // an item is `chunk` pixels (1024 fp32 / 2048 bf16)
             if (hist && cur_img >= 0)
                 hist_flush(hist, confmat, per_image ? per_image + (size_t)cur_img * 3 * C : nullptr, C);
             cur_img = n;
@@ -942,11 +944,16 @@ using namespace lc2is;
 // un-scaled softmax term (or NULL) - and, with onehot != 0, the -onehot term as well (then the labels only need
 // lc2is_pack_labels, not the label prepass); d_n_valid (optional) += #counted pixels, for labels that were packed without
 // counting; d_confmat / d_per_image ACCUMULATE; d_pred optional.
+namespace lc2is {
+int rc_warps_for(int C);                                    // k23_rowclass.cu
+int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, int C, int h, int w, int H, int W,
+                  double* d_loss_sum, float* d_grad_low, int onehot, int64_t* d_n_valid, int64_t* d_confmat,
+                  int64_t* d_per_image, int64_t* d_pred, cudaStream_t st);
+}
 extern "C" int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W) {
     int s = 0;
     if (!fast_scale(h, w, H, W, &s) || s != 16) return 0;
-    const size_t smem = (size_t)(C + 8) * 64 * sizeof(float);
-    return smem <= 72 * 1024 ? 1 : 0;                       // three CTAs per SM
+    return rc_warps_for(C) > 0 ? 1 : 0;                     // the job tiles of >= 8 warps fit one SM
 }
 
 extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* d_labels_packed,
@@ -960,7 +967,10 @@ extern "C" int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* 
     if (!d_low || !d_labels_packed || !d_loss_sum || !d_confmat) return fail(LC2IS_ERR_ARG, "null pointer%s");
     if ((uintptr_t)d_labels_packed % 16) return fail(LC2IS_ERR_ARG, "packed labels must be 16-byte aligned%s");
     if (!lc2is_ce_argmax_fused_supported(C, h, w, H, W))
-        return fail(LC2IS_ERR_UNSUPPORTED, "fused K2+K3 needs scale 16 and a class count whose tap tile fits three CTAs per SM%s");
+        return fail(LC2IS_ERR_UNSUPPORTED, "fused K2+K3 needs scale 16 and a class count whose job tiles fit one SM%s");
+    if (!getenv("LC2IS_FUSED_V1") || (size_t)(C + 8) * 64 * sizeof(float) > 72 * 1024)
+        return launch_k23_rc(d_low, d_labels_packed, B, C, h, w, H, W, d_loss_sum, d_grad_low, onehot, d_n_valid,
+                             d_confmat, d_per_image, d_pred, (cudaStream_t)stream);
     K2SParams P2;
     P2.low = d_low; P2.labels = nullptr; P2.labels16 = d_labels_packed; P2.grad_low = d_grad_low;
     P2.n_valid = (unsigned long long*)d_n_valid;

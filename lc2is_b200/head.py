@@ -70,7 +70,7 @@ class _SegHeadLoss(torch.autograd.Function):
         C = t.shape[-2]
         logits, v_hat, inv_v = ops.cosine_logits_fwd(v, t_hat, C, hw_shape, normalize, logit_scale)
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
-        n_valid = ops.count_valid(labels, ignore_index)
+        n_valid = ops.count_valid(labels, C, ignore_index)
         gscale = ops.mean_scale(n_valid) if reduction == "mean" else None
         loss_sum, _, gbf = ops.upsample_ce(logits, labels, ignore_index, gscale, want_grad=need_grad,
                                            want_bf16=need_grad)

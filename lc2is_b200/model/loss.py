@@ -22,7 +22,7 @@ class _UpsampleCE(torch.autograd.Function):
     def forward(ctx, low: Tensor, target: Tensor, ignore_index: int, reduction: str):
         need_grad = ctx.needs_input_grad[0]
         low32 = low.float()
-        n_valid = ops.count_valid(target, ignore_index)
+        n_valid = ops.count_valid(target, low.shape[1], ignore_index)
         gscale = ops.mean_scale(n_valid) if reduction == "mean" else None
         loss_sum, grad, _ = ops.upsample_ce(low32, target, ignore_index, gscale, want_grad=need_grad)
         loss = ops.finalize_loss(loss_sum, n_valid) if reduction == "mean" else loss_sum.float()

@@ -113,11 +113,12 @@ def cosine_logits_bwd(grad: Tensor, logits: Tensor, v_hat: Tensor, inv_v: Tensor
 
 
 # ---- K2 -----------------------------------------------------------------------------------
-def count_valid(labels: Tensor, ignore_index: int, out: Optional[Tensor] = None) -> Tensor:
+def count_valid(labels: Tensor, n_classes: int, ignore_index: int, out: Optional[Tensor] = None) -> Tensor:
+    """#{labels in [0, n_classes) and != ignore_index}: the 'mean' denominator of every CE route."""
     labels = _req(labels, torch.int64, "labels")
     if out is None:
         out = torch.zeros(1, dtype=torch.int64, device=labels.device)
-    check(lib.lc2is_count_valid(ptr(labels), labels.numel(), int(ignore_index), ptr(out), stream_ptr()),
+    check(lib.lc2is_count_valid(ptr(labels), labels.numel(), int(n_classes), int(ignore_index), ptr(out), stream_ptr()),
           "lc2is_count_valid")
     return out
 

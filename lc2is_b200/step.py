@@ -2,10 +2,9 @@
 ``eval_loop`` do around the head, engine.py:75-101 and :145-163), chained through the C ABI on
 the current stream with no host synchronisation and no allocation inside the step:
 
-    count_valid -> [DP: all-reduce n_valid] -> mean_scale -> K0 proto_normalize ->
-    K1 cosine_logits_fwd -> K2 upsample+CE fwd/bwd -> K1b cosine_logits_bwd ->
-    K3 argmax/confusion matrix (fused bilinear, the 'outputs' map of final.py:44) ->
-    finalize_loss -> [DP: all-reduce gradient bucket + confusion matrix]
+    pack / count labels -> [DP: all-reduce n_valid] -> K0 proto_normalize -> K1 cosine_logits_fwd ->
+    K2 upsample+CE fwd/bwd + K3 argmax/confusion matrix (one kernel at x16; the 'outputs' map of final.py:44) ->
+    mean_scale -> K1b cosine_logits_bwd -> finalize_loss -> [DP: all-reduce gradient bucket, behind the next step]
 
 Used by bench.py and usable as the data-parallel engine shim.
 """
@@ -19,19 +18,54 @@ from . import _lib, dp
 from ._lib import BF16, BILINEAR, F32, check, lib, ptr, stream_ptr
 
 
+class _Block:
+    """Everything ONE step accumulates into, in one flat buffer that is zeroed with a single fill:
+        [ grad bucket: grad_t (C*D) | loss_sum as fp32 (1) | pad ] [ grad_low (B*C*h*w) ]
+        [ scalars: double loss_sum | int64 n_valid | float gscale | float loss ]
+    HeadStep keeps TWO of them and alternates, so that the gradient-bucket all-reduce of step i can stay in flight
+    while step i+1 zero-fills and fills the other one."""
+
+    def __init__(self, B, C, D, h, w, dev):
+        nb = C * D + 1
+        nb_pad = (nb + 3) // 4 * 4
+        ngl = B * C * h * w
+        ngl_pad = (ngl + 3) // 4 * 4
+        self.acc32 = torch.zeros(nb_pad + ngl_pad + 8, dtype=torch.float32, device=dev)   # zeroed as fp32: 16-byte stores
+        acc = self.acc32.view(torch.uint8)
+        f32 = self.acc32[: nb_pad + ngl_pad]
+        self.bucket = dp.GradBucket([(1, C, D), (1,)], dev, flat=f32[:nb])
+        self.grad_t = self.bucket.views[0]
+        self.grad_low = f32[nb_pad:nb_pad + ngl].view(B, C, h, w)
+        o = 4 * (nb_pad + ngl_pad)
+        # scalars: [0:8] double loss_sum | [8:16] int64 n_valid | [16:20] float gscale | [20:24] float loss
+        self.scalars = acc[o:o + 32]
+        self.loss_sum = self.scalars[0:8].view(torch.float64)
+        self.n_valid = self.scalars[8:16].view(torch.int64)
+        self.gscale = self.scalars[16:20].view(torch.float32)
+        self.loss = self.scalars[20:24].view(torch.float32)
+
+
 class HeadStep:
     """Pre-allocated device-resident step.  Per call: loss / n_valid / grad_v / grad_t of the batch; the confusion
     matrix ACCUMULATES over calls (``reset_metrics()`` clears it, ``global_confmat()`` returns it summed over the
     ranks - integer sums commute, so an evaluation pass needs ONE int64 all-reduce at its end).
 
     Data-parallel order of a call (weak scaling, one process per GPU):
-        zero-fill -> label prepass -> [n_valid all-reduce, async] -> K0 -> K1 -> K2 -> [wait n_valid] -> K1b ->
-        [gradient-bucket all-reduce, async] -> K3 -> [wait bucket] -> loss
-    so the valid-count all-reduce hides behind K0/K1/K2 and the gradient all-reduce behind K3."""
+        [bucket all-reduce of the PREVIOUS call, async] -> zero-fill -> pack labels -> [n_valid all-reduce, async] ->
+        K0 -> K1 -> K2+K3 -> [wait n_valid] -> K1b -> [wait the previous bucket; its loss]
+    The valid-count all-reduce hides behind K0 / K1 / K2+K3 and the gradient-bucket all-reduce of call i behind the whole
+    of call i+1 (two accumulator blocks alternate), so no collective is exposed inside a pass; ``flush()`` all-reduces the
+    last call's bucket.  ``loss`` / ``n_valid`` / ``grad_t`` / ``grad_low`` are those of the most recent call and - with a
+    process group - complete after ``flush()``.
+
+    ``capture(v, t, labels)`` records one call into a CUDA graph (static input addresses; one graph per input set and
+    accumulator block) and returns a callable that replays it: one cudaGraphLaunch instead of ~12 kernel launches and
+    two collectives enqueued from Python."""
 
     def __init__(self, B: int, h: int, w: int, H: int, W: int, C: int, D: int = 512, ignore_index: int = 0,
                  logit_scale: float = 1.0, normalize: bool = True, backward: bool = True,
-                 v_dtype=torch.bfloat16, device: Optional[torch.device] = None, distributed: bool = False) -> None:
+                 v_dtype=torch.bfloat16, device: Optional[torch.device] = None, distributed: bool = False,
+                 extra_bucket_floats: int = 0) -> None:
         dev = device or torch.device("cuda", torch.cuda.current_device())
         self.B, self.h, self.w, self.H, self.W, self.C, self.D = B, h, w, H, W, C, D
         self.hw = h * w
@@ -48,29 +82,16 @@ class HeadStep:
         self.logits = e(B, C, h, w)
         self.split = bool(lib.lc2is_ce_split_supported(h, w, H, W))     # label prepass + packed-label K2 / K3
         self.labels_packed = e(B, H, W, dt=torch.uint16) if self.split else None
-        # x16: K2 and K3 run as ONE warp-specialised kernel (complementary pipes share the SMs)
+        # x16: K2 and K3 run as ONE kernel (k23_rc_kernel)
         self.fused = bool(self.split and lib.lc2is_ce_argmax_fused_supported(C, h, w, H, W))
         self.grad_v = e(B, self.hw, D, dt=torch.bfloat16)
-        # Everything a step accumulates into lives in ONE flat buffer that is zeroed with a single fill:
-        #   [ grad bucket: grad_t (C*D) | loss_sum as fp32 (1) | pad ] [ grad_low (B*C*h*w) ]
-        #   [ scalars: double loss_sum | int64 n_valid | float gscale | float loss ]
-        nb = C * D + 1
-        nb_pad = (nb + 3) // 4 * 4
-        ngl = B * C * self.hw
-        ngl_pad = (ngl + 3) // 4 * 4
-        self._acc32 = torch.zeros(nb_pad + ngl_pad + 8, dtype=torch.float32, device=dev)   # zeroed as fp32: 16-byte stores
-        self._acc = self._acc32.view(torch.uint8)
-        f32 = self._acc32[: nb_pad + ngl_pad]
-        self.bucket = dp.GradBucket([(1, C, D), (1,)], dev, flat=f32[:nb])
-        self.grad_t = self.bucket.views[0]
-        self.grad_low = f32[nb_pad:nb_pad + ngl].view(B, C, h, w)
-        o = 4 * (nb_pad + ngl_pad)
-        # scalars: [0:8] double loss_sum | [8:16] int64 n_valid | [16:20] float gscale | [20:24] float loss
-        self.scalars = self._acc[o:o + 32]
-        self.loss_sum = self.scalars[0:8].view(torch.float64)
-        self.n_valid = self.scalars[8:16].view(torch.int64)
-        self.gscale = self.scalars[16:20].view(torch.float32)
-        self.loss = self.scalars[20:24].view(torch.float32)
+        self._blocks = [_Block(B, C, D, h, w, dev), _Block(B, C, D, h, w, dev)]
+        self._cur = 0
+        # gradients of upstream parameters that ride in the same all-reduce (TextToPatch: BASELINE config 4's 2.93 MB
+        # bucket): callers write them into `extra` before the next call / flush()
+        self.extra = [torch.zeros(extra_bucket_floats, dtype=torch.float32, device=dev) for _ in range(2)] \
+            if extra_bucket_floats else None
+        self._pending = None           # block whose bucket has not been all-reduced yet (distributed only)
         self.confmat = torch.zeros(C, C, dtype=torch.int64, device=dev)        # this rank's counts, accumulated
         self._confmat_global = torch.zeros(C, C, dtype=torch.int64, device=dev) if self.distributed else None
         nbytes = int(lib.lc2is_cosine_logits_bwd_workspace(B, self.hw, D, 1, C))
@@ -78,6 +99,18 @@ class HeadStep:
         self.k2_events = None          # optional (start, stop) CUDA events around the K2 call
         self._open = None
         self.timers = None             # optional {name: [(start, stop) CUDA events]} per section (bench --kernel-times)
+
+    # ---- the most recent call's results ---------------------------------------------------------------------
+    @property
+    def _blk(self) -> _Block:
+        return self._blocks[self._cur]
+
+    loss = property(lambda self: self._blk.loss)
+    n_valid = property(lambda self: self._blk.n_valid)
+    grad_t = property(lambda self: self._blk.grad_t)
+    grad_low = property(lambda self: self._blk.grad_low)
+    loss_sum = property(lambda self: self._blk.loss_sum)
+    bucket = property(lambda self: self._blk.bucket)
 
     def _mark(self, name: str) -> None:
         """Close the running timed section and open `name` (None = just close).  No-op unless self.timers is a dict."""
@@ -101,33 +134,86 @@ class HeadStep:
         dp.allreduce_confmat_(self._confmat_global)
         return self._confmat_global
 
-    def finish(self) -> None:
-        """Kept for callers of the earlier interface: a call leaves nothing outstanding any more."""
-        return None
+    # ---- data-parallel exchange of a finished block ------------------------------------------------------------
+    def _start_exchange(self, k: int):
+        """All-reduce block k's gradient bucket (+ the upstream gradients riding with it) asynchronously."""
+        works = [dp.allreduce_sum_async(self._blocks[k].bucket.flat)]
+        if self.extra is not None:
+            works.append(dp.allreduce_sum_async(self.extra[k]))
+        return works
+
+    def _finish_exchange(self, k: int, works) -> None:
+        for wk in works:
+            wk.wait()                                             # stream-level wait, no host sync
+        blk = self._blocks[k]
+        blk.loss.copy_(blk.bucket.views[1] / blk.n_valid)
+
+    def flush(self) -> None:
+        """Complete the most recent call: all-reduce its gradient bucket (distributed only; enqueued, no host sync)."""
+        if self._pending is not None:
+            k, self._pending = self._pending, None
+            self._finish_exchange(k, self._start_exchange(k))
+
+    def capture(self, v: torch.Tensor, t: torch.Tensor, labels: torch.Tensor):
+        """Record ``self(v, t, labels)`` for the NEXT accumulator block into a CUDA graph; returns ``replay()``.
+        The tensors' addresses are baked in (refill them in place).  Graphs alternate blocks like eager calls do, so
+        capture one per (input set, block) in the order they will be replayed and replay them in that order."""
+        assert self.timers is None and self.k2_events is None, "no event timers inside a captured step"
+        k = self._cur ^ 1
+        pending = self._pending
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                self._enqueue(v, t, labels, k, pending)
+        torch.cuda.current_stream().wait_stream(side)
+        # capturing does not execute: leave the bookkeeping as if the call had not happened
+        nxt_pending = k if self.distributed else None
+
+        def replay():
+            assert self._cur == (k ^ 1) and self._pending == pending, "replay graphs in the order they were captured"
+            g.replay()
+            self._cur, self._pending = k, nxt_pending
+        replay.graph = g
+        replay.block = k
+        # the graphs of a rotation are captured back to back: advance the bookkeeping so that the next capture
+        # records the other block (and this block's pending exchange)
+        self._cur, self._pending = k, nxt_pending
+        return replay
 
     def __call__(self, v: torch.Tensor, t: torch.Tensor, labels: torch.Tensor) -> None:
         """v [B,hw,D] (bf16/fp32), t [C,D] fp32, labels [B,H,W] int64 - all on the device.  Enqueues everything on
         the current stream; no host synchronisation."""
+        k = self._cur ^ 1
+        self._enqueue(v, t, labels, k, self._pending)
+        self._cur = k
+        self._pending = k if self.distributed else None
+
+    def _enqueue(self, v, t, labels, k: int, pending) -> None:
         st = stream_ptr()
         B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
         dist_on = self.distributed
+        blk = self._blocks[k]
+        # the previous call's bucket goes out first: its all-reduce runs on NCCL's stream next to this whole call
+        works_prev = self._start_exchange(pending) if pending is not None else None
         self._mark("zero-fill")
-        self._acc32.zero_()                                      # bucket, grad_low, scalars: one fill
-        glow = ptr(self.grad_low) if self.backward else None
+        blk.acc32.zero_()                                        # bucket, grad_low, scalars: one fill
+        glow = ptr(blk.grad_low) if self.backward else None
         self._mark("label prepass / count")
         if self.fused:
-            # the fused K2+K3 kernel only needs the labels packed and counted (its argmax warps add the -onehot term)
+            # the fused K2+K3 kernel only needs the labels packed and counted (its row phase adds the -onehot term)
             check(lib.lc2is_pack_labels(ptr(labels), labels.numel(), C, self.ignore_index, ptr(self.labels_packed),
-                                        ptr(self.n_valid), st), "pack_labels")
+                                        ptr(blk.n_valid), st), "pack_labels")
         elif self.split:
             # un-scaled gradients accumulate into grad_low (prepass: -onehot, K2: +softmax); 1/N_valid is applied
             # by K1b, so the valid-count all-reduce hides behind K0 / K1 / K2
             check(lib.lc2is_ce_labels_prepass(ptr(labels), B, C, h, w, H, W, self.ignore_index,
-                                              ptr(self.labels_packed), ptr(self.n_valid), glow, st), "ce_labels_prepass")
+                                              ptr(self.labels_packed), ptr(blk.n_valid), glow, st), "ce_labels_prepass")
         else:
-            check(lib.lc2is_count_valid(ptr(labels), labels.numel(), self.ignore_index, ptr(self.n_valid), st),
+            check(lib.lc2is_count_valid(ptr(labels), labels.numel(), C, self.ignore_index, ptr(blk.n_valid), st),
                   "count_valid")
-        w_valid = dp.allreduce_sum_async(self.n_valid) if dist_on else None
+        w_valid = dp.allreduce_sum_async(blk.n_valid) if dist_on else None
         self._mark("K0+K1 logits")
         check(lib.lc2is_proto_normalize(ptr(t), 1, C, D, int(self.normalize), ptr(self.t_hat), ptr(self.inv_t), st),
               "proto_normalize")
@@ -139,40 +225,26 @@ class HeadStep:
             self.k2_events[0].record()
         if self.fused:
             check(lib.lc2is_ce_argmax_fused_packed(ptr(self.logits), ptr(self.labels_packed), B, C, h, w, H, W,
-                                                   ptr(self.loss_sum), glow, 1, None, ptr(self.confmat), None, None, st),
+                                                   ptr(blk.loss_sum), glow, 1, None, ptr(self.confmat), None, None, st),
                   "ce_argmax_fused_packed")
         elif self.split:
             check(lib.lc2is_upsample_ce_packed(ptr(self.logits), ptr(self.labels_packed), B, C, h, w, H, W,
-                                               ptr(self.loss_sum), glow, st), "upsample_ce_packed")
+                                               ptr(blk.loss_sum), glow, st), "upsample_ce_packed")
         else:
             check(lib.lc2is_upsample_ce_fwd_bwd(ptr(self.logits), ptr(labels), B, C, h, w, H, W, self.ignore_index,
-                                                None, ptr(self.loss_sum), glow, None, st), "upsample_ce_fwd_bwd")
+                                                None, ptr(blk.loss_sum), glow, None, st), "upsample_ce_fwd_bwd")
         if self.k2_events is not None:
             self.k2_events[1].record()
         self._mark("K1b backward")
         if w_valid is not None:
             w_valid.wait()                                        # stream-level wait, no host sync
-        check(lib.lc2is_mean_scale(ptr(self.n_valid), 1.0, ptr(self.gscale), st), "mean_scale")
-        w_b = None
-        if self.backward and dist_on:
-            # data-parallel: prototype gradient first, its all-reduce hides behind the patch-gradient GEMM
-            args = (ptr(self.grad_low), F32, ptr(self.logits), ptr(self.v_hat), ptr(self.inv_v), ptr(self.t_hat),
-                    ptr(self.inv_t), B, hw, D, 1, C, int(self.normalize), self.logit_scale, ptr(self.gscale))
-            check(lib.lc2is_cosine_logits_bwd_ex(*args, None, BF16, ptr(self.grad_t), ptr(self.bwd_ws), st, 0),
-                  "cosine_logits_bwd(dT)")
-            self.bucket.views[1].copy_(self.loss_sum)            # fp32 copy of the loss sum rides in the bucket
-            w_b = dp.allreduce_sum_async(self.bucket.flat)
-            check(lib.lc2is_cosine_logits_bwd_ex(*args, ptr(self.grad_v), BF16, None, ptr(self.bwd_ws), st, 1),
-                  "cosine_logits_bwd(dV)")
-        elif self.backward:
-            check(lib.lc2is_cosine_logits_bwd(ptr(self.grad_low), F32, ptr(self.logits), ptr(self.v_hat),
+        check(lib.lc2is_mean_scale(ptr(blk.n_valid), 1.0, ptr(blk.gscale), st), "mean_scale")
+        if self.backward:
+            check(lib.lc2is_cosine_logits_bwd(ptr(blk.grad_low), F32, ptr(self.logits), ptr(self.v_hat),
                                               ptr(self.inv_v), ptr(self.t_hat), ptr(self.inv_t), B, hw, D, 1, C,
-                                              int(self.normalize), self.logit_scale, ptr(self.gscale),
-                                              ptr(self.grad_v), BF16, ptr(self.grad_t), ptr(self.bwd_ws), st),
+                                              int(self.normalize), self.logit_scale, ptr(blk.gscale),
+                                              ptr(self.grad_v), BF16, ptr(blk.grad_t), ptr(self.bwd_ws), st),
                   "cosine_logits_bwd")
-        elif dist_on:
-            self.bucket.views[1].copy_(self.loss_sum)
-            w_b = dp.allreduce_sum_async(self.bucket.flat)
         self._mark("K3 argmax+confmat")
         if self.fused:
             pass                                                  # done inside the fused kernel
@@ -184,10 +256,11 @@ class HeadStep:
                                                   ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
         self._mark("finalize")
         if dist_on:
-            w_b.wait()
-            self.loss.copy_(self.bucket.views[1] / self.n_valid)
+            blk.bucket.views[1].copy_(blk.loss_sum)              # fp32 copy of the loss sum rides in the bucket
+            if works_prev is not None:
+                self._finish_exchange(pending, works_prev)
         else:
-            check(lib.lc2is_finalize_loss(ptr(self.loss_sum), ptr(self.n_valid), ptr(self.loss), st), "finalize_loss")
+            check(lib.lc2is_finalize_loss(ptr(blk.loss_sum), ptr(blk.n_valid), ptr(blk.loss), st), "finalize_loss")
         self._mark(None)
 
 
@@ -365,6 +438,22 @@ class HostStep:
               "lc2is_head_step_host_submit")
         s.event, s.keep = ev, (h_v, h_t, h_labels)          # host buffers must outlive the step
         self._inflight.append(s)
+
+    def close(self) -> None:
+        """Drain the steps in flight and a label prefetch that was never consumed (its worker threads write into this
+        object's pinned scratch), so that the buffers can be freed."""
+        if getattr(self, "_prefetched", None) is not None:
+            handle = self._prefetched[2]
+            self._prefetched = None
+            check(lib.lc2is_pack_labels_host_end(handle), "lc2is_pack_labels_host_end")
+        while getattr(self, "_inflight", None):
+            self.wait()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
     def wait(self):
         s = self._inflight.pop(0)

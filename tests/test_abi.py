@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/lc2is_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES out of sync with the header"
-    assert lib.lc2is_abi_version() == 3
+    assert lib.lc2is_abi_version() == 4
 
 
 def test_class_pad():
@@ -36,10 +36,10 @@ def test_class_pad():
 def test_no_cpu_fallback():
     from lc2is_b200 import _lib, ops, metrics
     from lc2is_b200.model.loss import AuxiliaryLoss
-    assert _lib.lib.lc2is_count_valid(None, 0, 0, None, None) == -3
+    assert _lib.lib.lc2is_count_valid(None, 0, 5, 0, None, None) == -3
     assert "no CPU fallback" in _lib.last_error()
     with pytest.raises(_lib.Lc2isError):
-        ops.count_valid(torch.zeros(8, dtype=torch.int64), 0)
+        ops.count_valid(torch.zeros(8, dtype=torch.int64), 5, 0)
     with pytest.raises(_lib.Lc2isError):
         AuxiliaryLoss(ignore_index=0)(torch.zeros(1, 3, 2, 2), torch.zeros(1, 8, 8, dtype=torch.int64))
     with pytest.raises(_lib.Lc2isError):

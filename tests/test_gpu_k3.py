@@ -193,7 +193,8 @@ def test_strip_kernel_non_finite_taps_and_ties():
     assert torch.equal(cm.cpu(), O.confusion_matrix(pred_ref, labels, C))
 
 
-@pytest.mark.parametrize("N,C,h,ign,frac", [(3, 151, 6, 0, 0.1), (2, 150, 32, 0, 0.1), (1, 19, 3, 5, 0.3), (5, 37, 5, 0, 0.0)])
+@pytest.mark.parametrize("N,C,h,ign,frac", [(3, 151, 6, 0, 0.1), (2, 150, 32, 0, 0.1), (1, 19, 3, 5, 0.3), (5, 37, 5, 0, 0.0),
+                                               (3, 151, 8, 0, 0.1), (1, 19, 4, 5, 0.3), (2, 40, 12, 0, 0.2), (1, 200, 4, 0, 0.1)])
 def test_fused_ce_argmax_kernel_matches_separate_kernels_and_oracle(N, C, h, ign, frac):
     """k23_fused_kernel (x16): the warp-specialised K2+K3 kernel gives the loss / gradient of the split K2 path and
     the bit-exact confusion matrix / per-image counts / masks of K3 (dyadic logits)."""
@@ -240,3 +241,95 @@ def test_fused_kernel_non_finite_taps():
     cm, _, pred = ops.ce_argmax_fused(low.to(DEV), packed, (H, H), ls, None, want_pred=True)
     assert torch.equal(pred.cpu(), pred_ref)
     assert torch.equal(cm.cpu(), O.confusion_matrix(pred_ref, labels, C))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's rule on BASELINE-shaped data: metrics.py:92 takes argmax(Softmax2d(x)), the kernels argmax(x).  In
+# fp32 the softmax can round a near-tie onto one value and then the FIRST of the merged classes wins, so the two differ
+# on a handful of pixels (~2e-6 of them on cosine logits).  These tests state the bound and what a differing
+# pixel must look like: the kernel's class IS the argmax of the logits, the reference's class is an earlier class whose
+# softmax value the fp32 softmax made equal (materialised input) / whose logit is within fp32 evaluation-order noise
+# (fused resize, where ATen and the kernel round the interpolation differently).
+def _cosine_low(B, h, C, seed=11):
+    v = synthetic.make_patch_embeddings(B, h * h, 512, seed=seed)
+    t = synthetic.make_prototypes(C, 512)
+    return O.cosine_logits_bf16_operands(v, t, hw_shape=(h, h))
+
+
+def _check_rule(pred, up, max_frac, gap_tol):
+    """pred (kernel) vs argmax(softmax(up)) (reference): few differing pixels, each a near-tie."""
+    pred_ref = O.argmax_reference(up)
+    diff = (pred != pred_ref)
+    n_diff = int(diff.sum())
+    assert n_diff <= max_frac * pred.numel(), (n_diff, pred.numel())
+    if n_diff:
+        idx = diff.nonzero()
+        x = up[idx[:, 0], :, idx[:, 1], idx[:, 2]]                                   # [n_diff, C]
+        vk = x.gather(1, pred[diff].view(-1, 1)).squeeze(1)
+        vr = x.gather(1, pred_ref[diff].view(-1, 1)).squeeze(1)
+        top = x.max(1).values
+        assert float((top - vk).abs().max()) <= gap_tol and float((top - vr).abs().max()) <= gap_tol
+    return n_diff
+
+
+def test_argmax_rule_vs_reference_softmax_materialised():
+    """(i) materialised [2,150,512,512] bilinear-upsampled bf16-operand cosine logits: the kernel sees the SAME fp32
+    tensor as the reference, so a differing pixel can only be a softmax-merged near-tie and the kernel's class is the
+    exact argmax of the logits."""
+    B, C, h, H = 2, 150, 32, 512
+    up = F.interpolate(_cosine_low(B, h, C), mode="bilinear", scale_factor=H // h)
+    labels = synthetic.make_labels(B, H, H, C)
+    _, _, pred = ops.argmax_confmat(up.to(DEV), labels.to(DEV), want_pred=True)
+    pred = pred.cpu()
+    assert torch.equal(pred, O.argmax_logits(up))                                    # the kernel's own rule, bit-exact
+    n = _check_rule(pred, up, 2e-5, 2.0 ** -22)
+    ref = O.argmax_reference(up)
+    d = pred != ref
+    if n:                                                                            # the reference picked an EARLIER class
+        assert bool((ref[d] < pred[d]).all())
+
+
+@pytest.mark.parametrize("s,h", [(16, 32), (4, 128)])
+def test_argmax_rule_vs_reference_softmax_fused_bilinear(s, h):
+    """(ii) fused bilinear x16 / x4 from the low-resolution cosine logits against argmax(softmax(interpolate(x)))."""
+    B, C = 2, 150
+    H = s * h
+    low = _cosine_low(B, h, C, seed=12)
+    up = F.interpolate(low, mode="bilinear", scale_factor=s)
+    labels = synthetic.make_labels(B, H, H, C)
+    cm, _, pred = ops.argmax_confmat(low.to(DEV), labels.to(DEV), want_pred=True, size=(H, H), mode="bilinear")
+    _check_rule(pred.cpu(), up, 2e-5, 1e-6)
+    assert int(cm.sum()) == B * H * H
+    if s == 16:                                                                      # the fused K2+K3 kernel's argmax
+        packed, _ = ops.pack_labels(labels.to(DEV), C, 0)
+        ls = torch.zeros(1, dtype=torch.float64, device=DEV)
+        _, _, pred2 = ops.ce_argmax_fused(low.to(DEV), packed, (H, H), ls, None, want_pred=True)
+        _check_rule(pred2.cpu(), up, 2e-5, 1e-6)
+
+
+def test_argmax_rule_vs_reference_softmax_bicubic_compute_miou():
+    """(iii) the compute_mIOU path at size: bicubic x4, C=151, 128^2 -> 512^2 (metrics.py:89-92)."""
+    N, C, h, s = 2, 151, 128, 4
+    H = s * h
+    low = _cosine_low(N, h, C, seed=13)
+    labels = synthetic.make_labels(N, h, h, C, block=4)                              # labels at 128^2, nearest x4 (metrics.py:90)
+    up = F.interpolate(low, mode="bicubic", scale_factor=s)
+    lab_up = F.interpolate(labels[:, None].float(), mode="nearest", scale_factor=s)[:, 0].long()
+    _, _, pred = ops.argmax_confmat(low.to(DEV), lab_up.to(DEV), want_pred=True, size=(H, H), mode="bicubic")
+    n = _check_rule(pred.cpu(), up, 2e-5, 1e-6)
+    got = metrics.compute_mIOU(low, labels, C)["mIOU_label"]
+    ref = O.compute_mIOU(low, labels, C)["mIOU_label"]
+    assert abs(got - ref) <= 1e-5 + 4.0 * n / (H * H), (got, ref, n)                 # exact when no pixel differs
+
+
+def test_bf16_dominant_class_does_not_overflow_the_16bit_counters():
+    """One (target, prediction) pair takes every pixel and a CTA sees > 65535 of them between image boundaries: the
+    shared-memory counters are 16 bit and must be flushed on PIXELS (a bf16 item is 2048 pixels, an fp32 one 1024)."""
+    N, C, H = 1, 4, 4096                                                              # 16.7 M pixels in one image
+    logits = torch.zeros(N, C, H, H, dtype=torch.bfloat16, device=DEV)
+    logits[:, 2] = 1.0
+    labels = torch.full((N, H, H), 1, dtype=torch.int64, device=DEV)
+    cm, _, _ = ops.argmax_confmat(logits, labels)
+    ref = torch.zeros(C, C, dtype=torch.int64)
+    ref[1, 2] = N * H * H
+    assert torch.equal(cm.cpu(), ref)

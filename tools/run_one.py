@@ -10,7 +10,7 @@ L = synthetic.make_labels(B, H, H, C, ignore_frac=0.1).to(dev)
 t = synthetic.make_prototypes(C, D).to(dev)
 t_hat, inv_t = ops.proto_normalize(t)
 logits, v_hat, inv_v = ops.cosine_logits_fwd(V, t_hat, C, (h, h))
-nv = ops.count_valid(L, 0); gs = ops.mean_scale(nv)
+nv = ops.count_valid(L, C, 0); gs = ops.mean_scale(nv)
 for _ in range(3):
     if which == "k1": ops.cosine_logits_fwd(V, t_hat, C, (h, h))
     if which == "k2": ops.upsample_ce(logits, L, 0, gs)

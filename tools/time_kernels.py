@@ -31,9 +31,9 @@ def main():
     def want(k): return not a.only or k in a.only.split(",")
     if want("k1"):
         res["k1_fwd(prep+gemm)"] = timeit(lambda i: ops.cosine_logits_fwd(V[i % nset], t_hat, C, (h, h)))
-    nv = ops.count_valid(L[0], 0); gs = ops.mean_scale(nv)
+    nv = ops.count_valid(L[0], C, 0); gs = ops.mean_scale(nv)
     if want("count"):
-        res["count_valid"] = timeit(lambda i: ops.count_valid(L[i % nset], 0))
+        res["count_valid"] = timeit(lambda i: ops.count_valid(L[i % nset], C, 0))
     if want("k2"):
         res["k2(memset+fused)"] = timeit(lambda i: ops.upsample_ce(outs[i % nset][0], L[i % nset], 0, gs))
         if ops.ce_split_supported(h, h, H, H):
