@@ -11,8 +11,8 @@
 //
 //   stage     the job's source cells of every class land in the warp's private shared-memory tile by ONE TMA box
 //             (4-D tensor map [B][C][h][w], box 1 x C x 2 x 8 starting on a 16-byte boundary; out-of-bounds cells are
-//             zero-filled and never used); the box of the warp's NEXT job is issued as soon as this one has been
-//             converted, so it lands behind the whole job.
+//             zero-filled and never used).  The landing zone doubles as the U tile of the job, so the box of the warp's
+//             NEXT job is issued at the end of the job; its latency is covered by the other 15 warps of the SM.
 //   convert   lane = class: the cells become per-group quads (a, b, c-a, d-b), and the same sweep finds the softmax shift
 //             M = max tap of the group, the tap range and non-finite taps.
 //   row phase lane = one pixel row of one group (2 groups x 16 rows), one sweep over the classes does BOTH
@@ -38,9 +38,11 @@
 namespace lc2is {
 
 constexpr int RC_S = 16;                 // scale
-constexpr int RC_CH = 6;                 // classes per argmax chunk (even)
+constexpr int RC_CH = 8;                 // classes per argmax chunk (even)
 constexpr int RC_USTRIDE = 16 * 16 + 16; // floats per group in the U tile (+16: the two groups land in different banks)
 constexpr float RC_PAD = -1.0e30f;       // padding classes: exp -> 0, never the argmax
+// column indices of a pixel pair, (2k, 2k+1): constant-bank operands of the packed fma that evaluates the row
+__constant__ float2 RC_J2[RC_S / 2] = {{0.f, 1.f}, {2.f, 3.f}, {4.f, 5.f}, {6.f, 7.f}, {8.f, 9.f}, {10.f, 11.f}, {12.f, 13.f}, {14.f, 15.f}};
 
 struct RCParams {
     const float* low;                // [B,C,h,w]
@@ -57,7 +59,8 @@ struct RCParams {
     int jpr;                         // jobs per group row = ceil((w + 1) / 2)
     int use_tma;
     long long njobs;
-    unsigned warp_bytes;             // shared memory per warp
+    unsigned cells_bytes;            // shared memory per warp: TMA landing zone (later the U tile), multiple of 128
+    unsigned quads_bytes;            // shared memory per warp: quads + mbarrier
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y, int z,
@@ -68,10 +71,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// float reduction to GLOBAL memory (atomicAdd on a pointer of unknown state space expands to a generic-address sequence)
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 struct RCJob {
     int n, ky, kx0;                  // image, group row (-1..h-1), first group column (2*jx - 1)
 };
-__device__ __forceinline__ RCJob rc_decode(const RCParams& P, long long job) {
+__device__ __noinline__ RCJob rc_decode(const RCParams& P, long long job) {
     RCJob J;
     const int per_img = (P.h + 1) * P.jpr;
     J.n = (int)(job / per_img);
@@ -97,6 +105,7 @@ __device__ __forceinline__ void rc_stage(const RCParams& P, const CUtensorMap* t
         }
     } else {
         const float* base = P.low + (size_t)J.n * P.C * P.h * P.w;
+#pragma unroll 1
         for (int idx = lane; idx < P.C * 16; idx += 32) {
             const int c = idx >> 4, r = (idx >> 3) & 1, cx = idx & 7;
             const int y = ys + r, x = xs + cx;
@@ -173,8 +182,8 @@ __device__ __noinline__ float rc_ce_slow(const RCParams& P, int n, int ky, int k
                 const float L = fmaf(ly, qc - qa, qa), R = fmaf(ly, qd - qb, qb);
                 const float gg = ex2f((fmaf(lx, R - L, L) - m) * LOG2E) * uu;
                 float* g = gb + (size_t)c * plane;
-                atomicAdd(g + oA, gg * wa); atomicAdd(g + oB, gg * wb);
-                atomicAdd(g + oC, gg * wc); atomicAdd(g + oD, gg * wd);
+                red_add_f32(g + oA, gg * wa); red_add_f32(g + oB, gg * wb);
+                red_add_f32(g + oC, gg * wc); red_add_f32(g + oD, gg * wd);
             }
         }
     }
@@ -182,6 +191,15 @@ __device__ __noinline__ float rc_ce_slow(const RCParams& P, int n, int ky, int k
 }
 
 __device__ __forceinline__ float fmax3f(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// The group's taps (a b / c d) as two linear forms in lambda_y: the logit of pixel column j of the row at lambda_y is
+//   v(j) = v0 + j * delta,   v0 = p0 + lambda_y * p1 (column 0),   delta = q0 + lambda_y * q1 (column step)
+// (exact in fp32 on the dyadic exactness set).
+__device__ __forceinline__ float4 rc_quad(float a, float b, float c, float d) {
+    constexpr float RS = 1.f / RC_S, LX0 = 0.5f / RC_S;
+    const float ba = b - a, ca = c - a, gm = (d - b) - ca;
+    return make_float4(fmaf(ba, LX0, a), fmaf(gm, LX0, ca), ba * RS, gm * RS);
+}
 
 template <int S>
 __global__ void __launch_bounds__(512, 1)
@@ -197,11 +215,14 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
     if (gw >= P.njobs) return;                              // whole warp; there is no CTA barrier below
 
     const int C = P.C, CP = P.CP;
-    unsigned char* wb = smem_raw + (size_t)warp * P.warp_bytes;
-    float* cells = reinterpret_cast<float*>(wb);                        // [C][2][8]    TMA landing zone
-    float* quads = cells + (size_t)CP * 16;                             // [CP][2 groups][4] = (a, b, c-a, d-b)
-    float* Usm = quads + (size_t)CP * 8;                                // [2][RC_USTRIDE]: U[g][j][row]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(Usm + 2 * RC_USTRIDE);
+    // all landing zones first (each a multiple of 128 bytes, the alignment TMA wants), then the per-warp rest
+    float* cells = reinterpret_cast<float*>(smem_raw + (size_t)warp * P.cells_bytes);   // [C][2][8] TMA landing zone
+    float* quads = reinterpret_cast<float*>(smem_raw + (size_t)nwarps * P.cells_bytes + (size_t)warp * P.quads_bytes);
+    //                                                                     [CP][2 groups][4] = (p0, p1, q0, q1): rc_quad
+    // The U tile [2][RC_USTRIDE] (U[g][j][row], and the row records before it) lives in the landing zone: the cells are
+    // dead once they are converted, and the box of the NEXT job is only issued when this job's class phase has read U.
+    float* Usm = cells;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(quads + (size_t)CP * 8);
     const size_t plane = (size_t)P.h * P.w;
 
     if (lane == 0) {
@@ -219,9 +240,6 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
     // row-phase lane mapping
     const int gi = lane >> 4, i = lane & 15;
     const float ly = ((float)i + 0.5f) * RS;
-    float2 J2[S / 2];
-#pragma unroll
-    for (int k = 0; k < S / 2; ++k) J2[k] = make_float2((float)(2 * k), (float)(2 * k + 1));
 
 #pragma unroll 1
     for (long long job = gw; job < P.njobs; job += gstride) {
@@ -259,8 +277,8 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
                     bad |= !(fabsf(a0) < INFINITY) | !(fabsf(b0) < INFINITY) | !(fabsf(c0) < INFINITY) | !(fabsf(d0) < INFINITY);
                     if (gin1)
                         bad |= !(fabsf(a1) < INFINITY) | !(fabsf(b1) < INFINITY) | !(fabsf(c1) < INFINITY) | !(fabsf(d1) < INFINITY);
-                    q0 = make_float4(a0, b0, c0 - a0, d0 - b0);
-                    q1 = make_float4(a1, b1, c1 - a1, d1 - b1);
+                    q0 = rc_quad(a0, b0, c0, d0);
+                    q1 = rc_quad(a1, b1, c1, d1);
                 } else {
                     q0 = make_float4(RC_PAD, RC_PAD, 0.f, 0.f);
                     q1 = q0;
@@ -272,11 +290,13 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
             // 0 * inf = NaN poisons those pixels in the reference - look at it on the global map
             if (ky < 0 || kx0 < 0) {
                 const float* base = P.low + (size_t)n * C * plane;
+#pragma unroll 1
                 for (int g = 0; g < 2; ++g) {
                     const int kx = kx0 + g;
                     if (!(ky < 0 || kx < 0) || kx >= P.w) continue;
                     const int Ya = ky < 0 ? 0 : ky, Xa = kx < 0 ? 0 : kx;
                     const int Yb = min(Ya + 1, P.h - 1), Xb = min(Xa + 1, P.w - 1);
+#pragma unroll 1
                     for (int k = lane; k < C; k += 32) {
                         const float* pc = base + (size_t)k * plane;
                         const float t1 = __ldg(pc + Ya * P.w + Xb), t2 = __ldg(pc + Yb * P.w + Xa), t3 = __ldg(pc + Yb * P.w + Xb);
@@ -293,12 +313,7 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
             mn1 = fminf(mn1, __shfl_xor_sync(0xffffffffu, mn1, o));
         }
         const bool nonfinite = __any_sync(0xffffffffu, bad);
-        __syncwarp();                                       // quads complete, cells free
-        // ---- the box of the next job lands behind this one ----------------------------------------------------
-        if (job + gstride < P.njobs) {
-            const RCJob Jn = rc_decode(P, job + gstride);
-            rc_stage(P, &tm, cells, bar, Jn, lane);
-        }
+        __syncwarp();                                       // quads complete, cells free (they become the U tile)
 
         // ---- this lane's row: labels ---------------------------------------------------------------------------
         const int kx = kx0 + gi;
@@ -328,162 +343,177 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
         const float4* Q = reinterpret_cast<const float4*>(quads) + gi;
         float loss = 0.f;
         int bidx[S];
+        float2 S2[S / 2];                                   // fast path: S(j) of the row, column pairs
 
         if (!slow) {
             // ================= row phase: pass A + running maximum, one sweep over the classes ======================
             const float Mk = M * LOG2E;
-            float2 S2[S / 2];
-            float best[S];
+            // The loops of this kernel are kept ROLLED on purpose: the warps of an SM are at different places of the job
+            // at any time, and with the loop bodies unrolled the kernel ran out of instruction cache (ncu: no_instruction was
+            // the top stall reason of the 148 KB version).
+            float best[S], snap[S];                         // running maximum; its value at the last chunk boundary
             int bch[S];
 #pragma unroll
             for (int k = 0; k < S / 2; ++k) S2[k] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < S; ++j) { best[j] = -INFINITY; bch[j] = 0; }
+            for (int j = 0; j < S; ++j) { best[j] = -INFINITY; snap[j] = -INFINITY; bch[j] = 0; }
             const int nch = CP / CH;
             const float4* qp = Q;
 #pragma unroll 1
             for (int k = 0; k < nch; ++k) {
-                float cm[S];
-#pragma unroll
-                for (int p = 0; p < CH / 2; ++p) {
-                    const float4 qa = qp[0], qb = qp[2];
-                    qp += 4;
-                    const float La = fmaf(ly, qa.z, qa.x), Ra = fmaf(ly, qa.w, qa.y);
-                    const float Lb = fmaf(ly, qb.z, qb.x), Rb = fmaf(ly, qb.w, qb.y);
-                    const float rla = Ra - La, rlb = Rb - Lb;
-                    const float v0a = fmaf(rla, LX0, La), da = rla * RS;
-                    const float v0b = fmaf(rlb, LX0, Lb), db = rlb * RS;
-                    const float Ea = ex2f(fmaf(v0a, LOG2E, -Mk)), ra = ex2f(da * LOG2E);
-                    const float Eb = ex2f(fmaf(v0b, LOG2E, -Mk)), rb = ex2f(db * LOG2E);
-                    float2 e2a = make_float2(Ea, Ea * ra), e2b = make_float2(Eb, Eb * rb);
-                    const float2 r2a = bc2(ra * ra), r2b = bc2(rb * rb);
-                    const float2 da2 = bc2(da), db2 = bc2(db), va0 = bc2(v0a), vb0 = bc2(v0b);
-#pragma unroll
-                    for (int jj = 0; jj < S / 2; ++jj) {
-                        S2[jj] = fadd2(S2[jj], fadd2(e2a, e2b));
-                        if (jj < S / 2 - 1) { e2a = fmul2(e2a, r2a); e2b = fmul2(e2b, r2b); }
-                        const float2 va = ffma2(J2[jj], da2, va0), vb = ffma2(J2[jj], db2, vb0);
-                        if (p == 0) {
-                            cm[2 * jj] = fmaxf(va.x, vb.x);
-                            cm[2 * jj + 1] = fmaxf(va.y, vb.y);
-                        } else {
-                            cm[2 * jj] = fmax3f(va.x, vb.x, cm[2 * jj]);
-                            cm[2 * jj + 1] = fmax3f(va.y, vb.y, cm[2 * jj + 1]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < S; ++j)
-                    if (cm[j] > best[j]) { best[j] = cm[j]; bch[j] = k; }
-            }
-            // ---- log-sum-exp, U = valid / S -> shared memory ------------------------------------------------------
-            {
-                float lg = 0.f;
-                float* up = Usm + gi * RC_USTRIDE + i;
+#pragma unroll 1
+              for (int p = 0; p < CH / 2; ++p) {
+                const float4 qa = qp[0], qb = qp[2];
+                qp += 4;
+                const float v0a = fmaf(ly, qa.y, qa.x), da = fmaf(ly, qa.w, qa.z);
+                const float v0b = fmaf(ly, qb.y, qb.x), db = fmaf(ly, qb.w, qb.z);
+                const float Ea = ex2f(fmaf(v0a, LOG2E, -Mk)), ra = ex2f(da * LOG2E);
+                const float Eb = ex2f(fmaf(v0b, LOG2E, -Mk)), rb = ex2f(db * LOG2E);
+                float2 e2a = make_float2(Ea, Ea * ra), e2b = make_float2(Eb, Eb * rb);
+                const float2 r2a = bc2(ra * ra), r2b = bc2(rb * rb);
+                const float2 da2 = bc2(da), db2 = bc2(db), va0 = bc2(v0a), vb0 = bc2(v0b);
 #pragma unroll
                 for (int jj = 0; jj < S / 2; ++jj) {
-                    const bool va = (vm >> (2 * jj)) & 1u, vb = (vm >> (2 * jj + 1)) & 1u;
-                    const float sa = va ? S2[jj].x : 1.f, sb = vb ? S2[jj].y : 1.f;
-                    lg += lg2f(sa) + lg2f(sb);
-                    up[(2 * jj) * 16] = va ? rcpf(sa) : 0.f;
-                    up[(2 * jj + 1) * 16] = vb ? rcpf(sb) : 0.f;
+                    S2[jj] = fadd2(S2[jj], fadd2(e2a, e2b));
+                    if (jj < S / 2 - 1) { e2a = fmul2(e2a, r2a); e2b = fmul2(e2b, r2b); }
+                    const float2 va = ffma2(RC_J2[jj], da2, va0), vb = ffma2(RC_J2[jj], db2, vb0);
+                    best[2 * jj] = fmax3f(va.x, vb.x, best[2 * jj]);
+                    best[2 * jj + 1] = fmax3f(va.y, vb.y, best[2 * jj + 1]);
                 }
-                loss = fmaf((float)__popc(vm), M, lg * LN2);
+              }
+              // chunk boundary: pixels whose maximum moved inside this chunk (strictly up) remember the chunk
+#pragma unroll
+              for (int j = 0; j < S; ++j)
+                  if (best[j] != snap[j]) { snap[j] = best[j]; bch[j] = k; }
             }
             // ---- argmax phase 2: the FIRST class of the winning chunk that reaches the maximum ----------------------
 #pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const int c0 = bch[j] * CH;
-                int bi = c0;
+            for (int j = 0; j < S; ++j) { bch[j] *= CH; bidx[j] = bch[j]; }
+#pragma unroll 1
+            for (int cc = CH - 1; cc >= 0; --cc) {          // (downwards: the last match written is the first class)
+                const float4* qc = Q + cc * 2;
 #pragma unroll
-                for (int cc = CH - 1; cc >= 0; --cc) {
-                    const float4 q = Q[(c0 + cc) * 2];
-                    const float L = fmaf(ly, q.z, q.x), R = fmaf(ly, q.w, q.y);
-                    const float rl = R - L;
-                    const float v = fmaf((float)j, rl * RS, fmaf(rl, LX0, L));
-                    if (v == best[j]) bi = c0 + cc;
+                for (int j = 0; j < S; ++j) {
+                    const float4 q = qc[bch[j] * 2];
+                    const float v = fmaf((float)j, fmaf(ly, q.w, q.z), fmaf(ly, q.y, q.x));
+                    if (v == best[j]) bidx[j] = bch[j] + cc;
                 }
-                bidx[j] = bi;
             }
         } else {
             int* tmp = reinterpret_cast<int*>(Usm) + lane * S;
             rc_argmax_slow(P, n, ky, kx, i, row_in, tmp);
 #pragma unroll
             for (int j = 0; j < S; ++j) bidx[j] = tmp[j];
+            __syncwarp();
             if (vm) loss = rc_ce_slow(P, n, ky, kx, i, vm);
         }
 
-        // ---- target logits, -onehot term (exact integer tap weights, run-length along the row) --------------------
-        if (vm) {
-            const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
-            const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);
-            const size_t oA = (size_t)Ya * P.w + Xa, oB = (size_t)Ya * P.w + Xb, oC = (size_t)Yb * P.w + Xa, oD = (size_t)Yb * P.w + Xb;
-            const float* lbase = P.low + (size_t)n * C * plane;
-            float* gbase = (P.grad && P.onehot) ? P.grad + (size_t)n * C * plane : nullptr;
-            constexpr float WSC = 1.f / (float)(4 * S * S);
-            const int lyi = 2 * i + 1;
-            int cur = -1, sw0 = 0, sw1 = 0;
-            float tv0 = 0.f, tdl = 0.f;
-            auto flush = [&]() {
-                if (cur < 0 || !gbase) return;
-                float* gp = gbase + (size_t)cur * plane;
-                atomicAdd(gp + oA, -(float)((2 * S - lyi) * sw0) * WSC); atomicAdd(gp + oB, -(float)((2 * S - lyi) * sw1) * WSC);
-                atomicAdd(gp + oC, -(float)(lyi * sw0) * WSC);           atomicAdd(gp + oD, -(float)(lyi * sw1) * WSC);
-            };
+        // ---- the row's labels and predictions, by RUNS (labels are piecewise constant along a row) ------------------
+        //   * a run of equal counted labels: its target logits (closed form over the run's columns) and its -onehot term
+        //     of dL/dlogits as exact integer tap weights (lambda * 2S): four float reductions per run
+        //   * a run of equal (target, prediction) pairs: one 64-bit reduction into the confusion matrix
+        // Run starts are found with the labels still in registers; the loops over the runs index the row through
+        // (label, prediction) records in the still idle U tile.
+        {
+            const unsigned inmask = !row_in ? 0u : (x0 < 0 ? 0xff00u : (x0 + S > P.W ? 0x00ffu : 0xffffu));
+            unsigned* rec = reinterpret_cast<unsigned*>(Usm) + lane;
+            unsigned ce_start = 0, cm_start = 0, cmv = 0;
+            int prev_lab = -1, prev_key = -1;
 #pragma unroll
             for (int j = 0; j < S; ++j) {
-                if (!((vm >> j) & 1u)) continue;
-                const int lab = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0xffffu);
-                if (lab != cur) {
-                    flush();
-                    cur = lab; sw0 = 0; sw1 = 0;
-                    float qa, qb, qc, qd;
-                    if (!slow) { const float4 q = Q[lab * 2]; qa = q.x; qb = q.y; qc = q.z; qd = q.w; }
-                    else {
-                        const float* q = lbase + (size_t)lab * plane;
-                        qa = __ldg(q + oA); qb = __ldg(q + oB); qc = __ldg(q + oC) - qa; qd = __ldg(q + oD) - qb;
-                    }
-                    const float L = fmaf(ly, qc, qa), R = fmaf(ly, qd, qb);
-                    const float rl = R - L;
-                    tv0 = fmaf(rl, LX0, L); tdl = rl * RS;
-                }
-                loss -= fmaf((float)j, tdl, tv0);
-                sw0 += 2 * S - (2 * j + 1);
-                sw1 += 2 * j + 1;
+                const unsigned lab = (lw16[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                const int t = (int)(lab & 0x7fffu);                           // bit 15: ignore flag of the CE
+                const bool c = (vm >> j) & 1u, v = ((inmask >> j) & 1u) && t < C;
+                const int key = t * C + bidx[j];
+                if (c && (int)lab != prev_lab) ce_start |= 1u << j;
+                if (v && key != prev_key) cm_start |= 1u << j;
+                prev_lab = c ? (int)lab : -1;
+                prev_key = v ? key : -1;
+                cmv |= (v ? 1u : 0u) << j;
+                rec[j * 32] = lab | ((unsigned)bidx[j] << 16);
             }
-            flush();
+            if (P.pred != nullptr && inmask) {
+                long long* prow = P.pred + ((size_t)n * P.H + y) * P.W + x0;
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    if ((inmask >> j) & 1u) prow[j] = bidx[j];
+            }
+            // end of the run that starts at j0: the next column that starts a run or is not counted
+            auto run_end = [](unsigned starts, unsigned counted, int j0) {
+                const unsigned brk = ((starts | ~counted) & 0xffffu) >> (j0 + 1);
+                return brk ? j0 + __ffs(brk) : S;
+            };
+            // -- cross-entropy runs
+            {
+                const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
+                const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);
+                const int oA = Ya * P.w + Xa, oB = Ya * P.w + Xb, oC = Yb * P.w + Xa, oD = Yb * P.w + Xb;
+                const float* lbase = P.low + (size_t)n * C * plane;
+                float* gbase = (P.grad && P.onehot) ? P.grad + (size_t)n * C * plane : nullptr;
+                constexpr float WSC = 1.f / (float)(4 * S * S);
+                const float wt = -(float)(2 * S - (2 * i + 1)) * WSC, wb = -(float)(2 * i + 1) * WSC;   // top / bottom taps
+                float tsub = 0.f;
+                unsigned m = ce_start;
+#pragma unroll 1
+                while (m) {
+                    const int j0 = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int j1 = run_end(ce_start, vm, j0);
+                    const int lab = (int)(rec[j0 * 32] & 0xffffu);
+                    const int len = j1 - j0, sumj = (len * (j0 + j1 - 1)) >> 1;     // sum of the run's column indices
+                    const int sw1 = 2 * sumj + len, sw0 = 2 * S * len - sw1;          // sums of (2j+1), 2S - (2j+1)
+                    float4 q;
+                    if (!slow) q = Q[lab * 2];
+                    else {
+                        const float* t4 = lbase + (size_t)lab * plane;
+                        q = rc_quad(__ldg(t4 + oA), __ldg(t4 + oB), __ldg(t4 + oC), __ldg(t4 + oD));
+                    }
+                    // sum over the run of v(j) = v0 + j * delta
+                    tsub += fmaf((float)sumj, fmaf(ly, q.w, q.z), (float)len * fmaf(ly, q.y, q.x));
+                    if (gbase) {
+                        float* gp = gbase + (size_t)lab * plane;
+                        red_add_f32(gp + oA, wt * (float)sw0); red_add_f32(gp + oB, wt * (float)sw1);
+                        red_add_f32(gp + oC, wb * (float)sw0); red_add_f32(gp + oD, wb * (float)sw1);
+                    }
+                }
+                loss -= tsub;
+            }
+            // -- confusion-matrix runs
+            {
+                unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
+                unsigned m = cm_start;
+#pragma unroll 1
+                while (m) {
+                    const int j0 = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned long long cnt = (unsigned long long)(run_end(cm_start, cmv, j0) - j0);
+                    const unsigned r = rec[j0 * 32];
+                    const int t = (int)(r & 0x7fffu), pr = (int)(r >> 16);
+                    atomicAdd(&P.confmat[t * C + pr], cnt);
+                    if (pimg) {
+                        if (t == pr) atomicAdd(&pimg[t], cnt);
+                        atomicAdd(&pimg[C + t], cnt);
+                        atomicAdd(&pimg[2 * C + pr], cnt);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // ---- log-sum-exp of the row, U = valid / S -> shared memory (class phase) ---------------------------------
+        if (!slow) {
+            float lg = 0.f;
+            float* up = Usm + gi * RC_USTRIDE + i;
+#pragma unroll
+            for (int jj = 0; jj < S / 2; ++jj) {
+                const bool va = (vm >> (2 * jj)) & 1u, vb = (vm >> (2 * jj + 1)) & 1u;
+                const float sa = va ? S2[jj].x : 1.f, sb = vb ? S2[jj].y : 1.f;
+                lg += lg2f(sa) + lg2f(sb);
+                up[(2 * jj) * 16] = va ? rcpf(sa) : 0.f;
+                up[(2 * jj + 1) * 16] = vb ? rcpf(sb) : 0.f;
+            }
+            loss += fmaf((float)__popc(vm), M, lg * LN2);
         }
 
-        // ---- predictions, counts --------------------------------------------------------------------------------
-        {
-            unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const int x = x0 + j;
-                bool valid = row_in && x >= 0 && x < P.W;
-                int t = 0;
-                const int pr = bidx[j];
-                if (valid) {
-                    if (P.pred) P.pred[((size_t)n * P.H + y) * P.W + x] = pr;
-                    t = (int)((lw16[j >> 1] >> (16 * (j & 1))) & 0x7fffu);   // bit 15: ignore flag of the CE
-                    valid = t < C;
-                }
-                const unsigned act = __ballot_sync(0xffffffffu, valid);
-                if (valid) {
-                    const int key = t * C + pr;
-                    const unsigned m = __match_any_sync(act, key);
-                    if (lane == __ffs(m) - 1) {
-                        const unsigned long long cnt = (unsigned long long)__popc(m);
-                        atomicAdd(&P.confmat[key], cnt);
-                        if (pimg) {
-                            if (t == pr) atomicAdd(&pimg[t], cnt);
-                            atomicAdd(&pimg[C + t], cnt);
-                            atomicAdd(&pimg[2 * C + pr], cnt);
-                        }
-                    }
-                }
-            }
-        }
         {
             int cnt = __popc(vm);
             loss = warp_sum(loss);
@@ -514,30 +544,30 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     if (!(g ? any1 : any0)) continue;
-                    const float4 q = reinterpret_cast<const float4*>(quads)[kk * 2 + g];     // a, b, c-a, d-b
-                    const float b0 = q.y - q.x, gm = q.w - q.z;
-                    const float L0 = fmaf(0.5f * RS, q.z, q.x), rl0 = fmaf(0.5f * RS, gm, b0);
-                    const float aE0 = fmaf(fmaf(rl0, LX0, L0), LOG2E, -(g ? Mk1 : Mk0));
-                    const float aS = fmaf(gm, LX0, q.z) * (RS * LOG2E);
-                    const float E0 = ex2f(aE0), sg = ex2f(aS), r0 = ex2f(rl0 * (RS * LOG2E)), ta = ex2f(gm * (RS * RS * LOG2E));
+                    const float4 q = reinterpret_cast<const float4*>(quads)[kk * 2 + g];     // p0, p1, q0, q1
+                    // row y: v0 = p0 + ly p1, delta = q0 + ly q1, ly = (y + 0.5) / 16
+                    const float aE0 = fmaf(fmaf(0.5f * RS, q.y, q.x), LOG2E, -(g ? Mk1 : Mk0));
+                    const float E0 = ex2f(aE0), sg = ex2f(q.y * (RS * LOG2E));
+                    const float r0 = ex2f(fmaf(0.5f * RS, q.w, q.z) * LOG2E), ta = ex2f(q.w * (RS * LOG2E));
                     const float sg2 = sg * sg, ta2 = ta * ta;
                     float2 e2a = make_float2(E0, E0 * sg), r2a = make_float2(r0, r0 * ta);
                     float2 e2b = fmul2(e2a, bc2(sg2)), r2b = fmul2(r2a, bc2(ta2));
                     const float2 sg4 = bc2(sg2 * sg2), ta4 = bc2(ta2 * ta2);
                     float2 aG = make_float2(0.f, 0.f), aX = aG, aYG = aG, aYX = aG;
                     const float4* U4 = reinterpret_cast<const float4*>(Usm + g * RC_USTRIDE);
-#pragma unroll
+                    float2 lya = make_float2(0.5f * RS, 1.5f * RS), lyb = make_float2(2.5f * RS, 3.5f * RS);
+#pragma unroll 1
                     for (int up = 0; up < 4; ++up) {
                         // rows 4up..4up+3: chain a = rows (4up, 4up+1), chain b = rows (4up+2, 4up+3)
-                        float4 u = U4[(S - 1) * 4 + up];
+                        float4 u = U4[(S - 1) * 4];
                         float2 ha = make_float2(u.x, u.y), hb = make_float2(u.z, u.w);
                         float2 dA = ha, dB = hb;
-                        u = U4[(S - 2) * 4 + up];
+                        u = U4[(S - 2) * 4];
                         ha = ffma2(ha, r2a, make_float2(u.x, u.y));
                         hb = ffma2(hb, r2b, make_float2(u.z, u.w));
 #pragma unroll
                         for (int j = S - 3; j >= 0; --j) {
-                            u = U4[j * 4 + up];
+                            u = U4[j * 4];
                             dA = ffma2(dA, r2a, ha);
                             dB = ffma2(dB, r2b, hb);
                             ha = ffma2(ha, r2a, make_float2(u.x, u.y));
@@ -545,16 +575,14 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
                         }
                         const float2 Ga = fmul2(e2a, ha), Gb = fmul2(e2b, hb);                       // sum_j g
                         const float2 Xa = fmul2(fmul2(e2a, r2a), dA), Xb = fmul2(fmul2(e2b, r2b), dB);   // sum_j j g
-                        const float2 lya = make_float2((4 * up + 0.5f) * RS, (4 * up + 1.5f) * RS);
-                        const float2 lyb = make_float2((4 * up + 2.5f) * RS, (4 * up + 3.5f) * RS);
                         aG = fadd2(aG, fadd2(Ga, Gb));
                         aX = fadd2(aX, fadd2(Xa, Xb));
                         aYG = ffma2(lya, Ga, ffma2(lyb, Gb, aYG));
                         aYX = ffma2(lya, Xa, ffma2(lyb, Xb, aYX));
-                        if (up < 3) {
-                            e2a = fmul2(e2a, sg4); e2b = fmul2(e2b, sg4);
-                            r2a = fmul2(r2a, ta4); r2b = fmul2(r2b, ta4);
-                        }
+                        ++U4;
+                        e2a = fmul2(e2a, sg4); e2b = fmul2(e2b, sg4);
+                        r2a = fmul2(r2a, ta4); r2b = fmul2(r2b, ta4);
+                        lya = fadd2(lya, bc2(4.f * RS)); lyb = fadd2(lyb, bc2(4.f * RS));
                     }
                     const float G = aG.x + aG.y, X = aX.x + aX.y, YG = aYG.x + aYG.y, YX = aYX.x + aYX.y;
                     const float SX = fmaf(X, RS, G * LX0);              // sum lambda_x g
@@ -566,13 +594,18 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
                     float* gk = gimg + (size_t)k * plane;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
-                        if (cell[c] != 0.f) atomicAdd(gk + (size_t)cy0 * P.w + cxs[c], cell[c]);
-                        if (cell[3 + c] != 0.f) atomicAdd(gk + (size_t)cy1 * P.w + cxs[c], cell[3 + c]);
+                        if (cell[c] != 0.f) red_add_f32(gk + (size_t)cy0 * P.w + cxs[c], cell[c]);
+                        if (cell[3 + c] != 0.f) red_add_f32(gk + (size_t)cy1 * P.w + cxs[c], cell[3 + c]);
                     }
                 }
             }
         }
         __syncwarp();                                       // quads / U free for the next job
+        // ---- the box of the warp's next job (its latency is covered by the SM's other warps) -----------------------
+        if (job + gstride < P.njobs) {
+            const RCJob Jn = rc_decode(P, job + gstride);
+            rc_stage(P, &tm, cells, bar, Jn, lane);
+        }
     }
 }
 
@@ -610,16 +643,20 @@ static int rc_tensor_map(const float* low, int B, int C, int h, int w, CUtensorM
     return 0;
 }
 
-static size_t rc_warp_bytes(int C) {
-    const int CP = (C + RC_CH - 1) / RC_CH * RC_CH;
-    size_t b = (size_t)CP * (16 + 8) * 4 + (size_t)2 * RC_USTRIDE * 4 + 16;
+static size_t rc_cells_bytes(int C) {
+    size_t b = (size_t)C * 16 * 4;                                       // [C][2][8] floats
+    if (b < (size_t)2 * RC_USTRIDE * 4) b = (size_t)2 * RC_USTRIDE * 4;  // ... or the U tile / row records
     return (b + 127) / 128 * 128;
+}
+static size_t rc_quads_bytes(int C) {
+    const int CP = (C + RC_CH - 1) / RC_CH * RC_CH;
+    return (size_t)CP * 8 * 4 + 16;
 }
 
 // warps per CTA (one CTA per SM) for C classes; 0 = does not fit
 int rc_warps_for(int C) {
-    const size_t wb = rc_warp_bytes(C);
-    int nw = (int)((size_t)220 * 1024 / wb);
+    const size_t wb = rc_cells_bytes(C) + rc_quads_bytes(C);
+    int nw = (int)((size_t)227 * 1024 / wb);
     if (nw > 16) nw = 16;
     return nw >= 8 ? nw : 0;
 }
@@ -637,13 +674,14 @@ int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, in
     P.CP = (C + RC_CH - 1) / RC_CH * RC_CH;
     P.jpr = (w + 1 + 1) / 2;
     P.njobs = (long long)B * (h + 1) * P.jpr;
-    P.warp_bytes = (unsigned)rc_warp_bytes(C);
+    P.cells_bytes = (unsigned)rc_cells_bytes(C);
+    P.quads_bytes = (unsigned)rc_quads_bytes(C);
     P.use_tma = (C <= 256 && w % 4 == 0 && ((uintptr_t)d_low % 16) == 0 && !getenv("LC2IS_RC_NO_TMA")) ? 1 : 0;
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     if (P.use_tma)
         if (int e = rc_tensor_map(d_low, B, C, h, w, &tm)) return e;
-    const size_t smem = (size_t)P.warp_bytes * nw;
+    const size_t smem = ((size_t)P.cells_bytes + P.quads_bytes) * nw;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [] {

@@ -215,3 +215,22 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in line, k
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in line["config"]
+
+
+def test_ftn_decoder_mirrors_run_and_keep_the_reference_parameter_names():
+    """decoder.py:36-134 mirrors (pass-through PyTorch, upstream of the head): they run on torch >= 2 (the reference's
+    `_sa_block` override lacks `is_causal` there) and name their parameters like the reference."""
+    import torch
+    from lc2is_b200.model.decoder import FTNBlock, FTNDecoder, SRTransformerDecoder
+    torch.manual_seed(0)
+    dec = FTNDecoder([32, 64, 128, 256], 64, dropout=0.0).eval()
+    vis = [torch.randn(2, 16 * 16, 32), torch.randn(2, 8 * 8, 64), torch.randn(2, 4 * 4, 128), torch.randn(2, 2 * 2, 256)]
+    out = dec(vis, torch.randn(2, 5, 64))
+    assert out.shape == (2, 256, 64) and torch.isfinite(out).all()
+    names = set(dec.state_dict())
+    for n in ("linear_stage_2.weight", "linear_stage_3.weight", "linear2_stage_1.weight", "linear2_stage_4.bias",
+              "attention_stage_4.2.attention_block.sr.weight", "attention_stage_2.0.attention_block.norm.weight",
+              "attention_stage_3.1.attention_block.self_attn.in_proj_weight"):
+        assert n in names, n
+    blk = FTNBlock(SRTransformerDecoder(d_model=64, nhead=8, sr_ratio=2, dropout=0.0, batch_first=True)).eval()
+    assert blk(tgt=torch.randn(1, 16, 64), memory=torch.randn(1, 3, 64)).shape == (1, 64, 64)
