@@ -352,26 +352,41 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
             // at any time, and with the loop bodies unrolled the kernel ran out of instruction cache (ncu: no_instruction was
             // the top stall reason of the 148 KB version).
             float best[S], snap[S];                         // running maximum; its value at the last chunk boundary
-            int bch[S];
+            unsigned bchw[S / 4];                           // chunk of the maximum, one byte per pixel
 #pragma unroll
             for (int k = 0; k < S / 2; ++k) S2[k] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < S; ++j) { best[j] = -INFINITY; snap[j] = -INFINITY; bch[j] = 0; }
+            for (int j = 0; j < S; ++j) { best[j] = -INFINITY; snap[j] = -INFINITY; }
+#pragma unroll
+            for (int j = 0; j < S / 4; ++j) bchw[j] = 0u;
             const int nch = CP / CH;
             const float4* qp = Q;
+            // software pipeline over the class pairs: the exponentials of pair p+1 and the quads of pair p+2 are in
+            // flight while the chains of pair p run (a warp issues in order: without this every pair starts with the
+            // full LDS -> FFMA -> MUFU latency)
+            float v0a, da, v0b, db, Ea, ra, Eb, rb;
+            auto setup = [&](const float4 qa, const float4 qb, float& v0a_, float& da_, float& v0b_, float& db_,
+                             float& Ea_, float& ra_, float& Eb_, float& rb_) {
+                v0a_ = fmaf(ly, qa.y, qa.x); da_ = fmaf(ly, qa.w, qa.z);
+                v0b_ = fmaf(ly, qb.y, qb.x); db_ = fmaf(ly, qb.w, qb.z);
+                Ea_ = ex2f(fmaf(v0a_, LOG2E, -Mk)); ra_ = ex2f(da_ * LOG2E);
+                Eb_ = ex2f(fmaf(v0b_, LOG2E, -Mk)); rb_ = ex2f(db_ * LOG2E);
+            };
+            setup(qp[0], qp[2], v0a, da, v0b, db, Ea, ra, Eb, rb);
+            const float4* const qlast = Q + (CP - 2) * 2;   // the look-ahead stops at the last pair (CP >= 8)
+            float4 na = qp[4], nb = qp[6];
+            qp += 8;
 #pragma unroll 1
             for (int k = 0; k < nch; ++k) {
 #pragma unroll 1
               for (int p = 0; p < CH / 2; ++p) {
-                const float4 qa = qp[0], qb = qp[2];
-                qp += 4;
-                const float v0a = fmaf(ly, qa.y, qa.x), da = fmaf(ly, qa.w, qa.z);
-                const float v0b = fmaf(ly, qb.y, qb.x), db = fmaf(ly, qb.w, qb.z);
-                const float Ea = ex2f(fmaf(v0a, LOG2E, -Mk)), ra = ex2f(da * LOG2E);
-                const float Eb = ex2f(fmaf(v0b, LOG2E, -Mk)), rb = ex2f(db * LOG2E);
                 float2 e2a = make_float2(Ea, Ea * ra), e2b = make_float2(Eb, Eb * rb);
                 const float2 r2a = bc2(ra * ra), r2b = bc2(rb * rb);
                 const float2 da2 = bc2(da), db2 = bc2(db), va0 = bc2(v0a), vb0 = bc2(v0b);
+                setup(na, nb, v0a, da, v0b, db, Ea, ra, Eb, rb);      // pair p+1
+                qp = qp < qlast ? qp : qlast;
+                na = qp[0]; nb = qp[2];                                // pair p+2
+                qp += 4;
 #pragma unroll
                 for (int jj = 0; jj < S / 2; ++jj) {
                     S2[jj] = fadd2(S2[jj], fadd2(e2a, e2b));
@@ -382,10 +397,27 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
                 }
               }
               // chunk boundary: pixels whose maximum moved inside this chunk (strictly up) remember the chunk
+              const unsigned kk = (unsigned)k;
 #pragma unroll
-              for (int j = 0; j < S; ++j)
-                  if (best[j] != snap[j]) { snap[j] = best[j]; bch[j] = k; }
+              for (int j = 0; j < S; ++j) {
+                  // if (best != snap) { snap = best; byte (j & 3) of bchw[j / 4] = k; }  - three instructions
+                  if ((j & 3) == 0)
+                      asm("{\n.reg .pred p;\nsetp.neu.f32 p, %2, %0;\n@p mov.f32 %0, %2;\n@p prmt.b32 %1, %1, %3, 0x3214;\n}"
+                          : "+f"(snap[j]), "+r"(bchw[j >> 2]) : "f"(best[j]), "r"(kk));
+                  else if ((j & 3) == 1)
+                      asm("{\n.reg .pred p;\nsetp.neu.f32 p, %2, %0;\n@p mov.f32 %0, %2;\n@p prmt.b32 %1, %1, %3, 0x3240;\n}"
+                          : "+f"(snap[j]), "+r"(bchw[j >> 2]) : "f"(best[j]), "r"(kk));
+                  else if ((j & 3) == 2)
+                      asm("{\n.reg .pred p;\nsetp.neu.f32 p, %2, %0;\n@p mov.f32 %0, %2;\n@p prmt.b32 %1, %1, %3, 0x3410;\n}"
+                          : "+f"(snap[j]), "+r"(bchw[j >> 2]) : "f"(best[j]), "r"(kk));
+                  else
+                      asm("{\n.reg .pred p;\nsetp.neu.f32 p, %2, %0;\n@p mov.f32 %0, %2;\n@p prmt.b32 %1, %1, %3, 0x4210;\n}"
+                          : "+f"(snap[j]), "+r"(bchw[j >> 2]) : "f"(best[j]), "r"(kk));
+              }
             }
+            int bch[S];
+#pragma unroll
+            for (int j = 0; j < S; ++j) bch[j] = (int)((bchw[j >> 2] >> (8 * (j & 3))) & 0xffu);
             // ---- argmax phase 2: the FIRST class of the winning chunk that reaches the maximum ----------------------
 #pragma unroll
             for (int j = 0; j < S; ++j) { bch[j] *= CH; bidx[j] = bch[j]; }
@@ -453,9 +485,12 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
                 constexpr float WSC = 1.f / (float)(4 * S * S);
                 const float wt = -(float)(2 * S - (2 * i + 1)) * WSC, wb = -(float)(2 * i + 1) * WSC;   // top / bottom taps
                 float tsub = 0.f;
+                // (warp-uniform trip count: a loop the lanes leave one by one came back from its convergence barrier in
+                // pieces, and the class phase below then ran once per piece - ncu: 16 active threads, twice the instructions)
                 unsigned m = ce_start;
 #pragma unroll 1
-                while (m) {
+                while (__any_sync(0xffffffffu, m != 0)) {
+                    if (!m) continue;
                     const int j0 = __ffs(m) - 1;
                     m &= m - 1;
                     const int j1 = run_end(ce_start, vm, j0);
@@ -483,7 +518,8 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
                 unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
                 unsigned m = cm_start;
 #pragma unroll 1
-                while (m) {
+                while (__any_sync(0xffffffffu, m != 0)) {
+                    if (!m) continue;
                     const int j0 = __ffs(m) - 1;
                     m &= m - 1;
                     const unsigned long long cnt = (unsigned long long)(run_end(cm_start, cmv, j0) - j0);
