@@ -210,7 +210,9 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
-    const long long gw = (long long)blockIdx.x * nwarps + warp;
+    // jobs are dealt to the warps SM-first (consecutive jobs go to different SMs): the last, partial round of jobs then
+    // thins out every SM's warps evenly instead of leaving whole SMs idle (the SMs are throughput-bound, not the warps)
+    const long long gw = (long long)warp * gridDim.x + blockIdx.x;
     const long long gstride = (long long)gridDim.x * nwarps;
     if (gw >= P.njobs) return;                              // whole warp; there is no CTA barrier below
 
@@ -364,29 +366,17 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
             // software pipeline over the class pairs: the exponentials of pair p+1 and the quads of pair p+2 are in
             // flight while the chains of pair p run (a warp issues in order: without this every pair starts with the
             // full LDS -> FFMA -> MUFU latency)
-            float v0a, da, v0b, db, Ea, ra, Eb, rb;
-            auto setup = [&](const float4 qa, const float4 qb, float& v0a_, float& da_, float& v0b_, float& db_,
-                             float& Ea_, float& ra_, float& Eb_, float& rb_) {
-                v0a_ = fmaf(ly, qa.y, qa.x); da_ = fmaf(ly, qa.w, qa.z);
-                v0b_ = fmaf(ly, qb.y, qb.x); db_ = fmaf(ly, qb.w, qb.z);
-                Ea_ = ex2f(fmaf(v0a_, LOG2E, -Mk)); ra_ = ex2f(da_ * LOG2E);
-                Eb_ = ex2f(fmaf(v0b_, LOG2E, -Mk)); rb_ = ex2f(db_ * LOG2E);
+            struct PairSt { float v0a, da, v0b, db, Ea, ra, Eb, rb; };
+            auto setup = [&](const float4 qa, const float4 qb, PairSt& t) {
+                t.v0a = fmaf(ly, qa.y, qa.x); t.da = fmaf(ly, qa.w, qa.z);
+                t.v0b = fmaf(ly, qb.y, qb.x); t.db = fmaf(ly, qb.w, qb.z);
+                t.Ea = ex2f(fmaf(t.v0a, LOG2E, -Mk)); t.ra = ex2f(t.da * LOG2E);
+                t.Eb = ex2f(fmaf(t.v0b, LOG2E, -Mk)); t.rb = ex2f(t.db * LOG2E);
             };
-            setup(qp[0], qp[2], v0a, da, v0b, db, Ea, ra, Eb, rb);
-            const float4* const qlast = Q + (CP - 2) * 2;   // the look-ahead stops at the last pair (CP >= 8)
-            float4 na = qp[4], nb = qp[6];
-            qp += 8;
-#pragma unroll 1
-            for (int k = 0; k < nch; ++k) {
-#pragma unroll 1
-              for (int p = 0; p < CH / 2; ++p) {
-                float2 e2a = make_float2(Ea, Ea * ra), e2b = make_float2(Eb, Eb * rb);
-                const float2 r2a = bc2(ra * ra), r2b = bc2(rb * rb);
-                const float2 da2 = bc2(da), db2 = bc2(db), va0 = bc2(v0a), vb0 = bc2(v0b);
-                setup(na, nb, v0a, da, v0b, db, Ea, ra, Eb, rb);      // pair p+1
-                qp = qp < qlast ? qp : qlast;
-                na = qp[0]; nb = qp[2];                                // pair p+2
-                qp += 4;
+            auto chains = [&](const PairSt& t) {
+                float2 e2a = make_float2(t.Ea, t.Ea * t.ra), e2b = make_float2(t.Eb, t.Eb * t.rb);
+                const float2 r2a = bc2(t.ra * t.ra), r2b = bc2(t.rb * t.rb);
+                const float2 da2 = bc2(t.da), db2 = bc2(t.db), va0 = bc2(t.v0a), vb0 = bc2(t.v0b);
 #pragma unroll
                 for (int jj = 0; jj < S / 2; ++jj) {
                     S2[jj] = fadd2(S2[jj], fadd2(e2a, e2b));
@@ -395,6 +385,27 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
                     best[2 * jj] = fmax3f(va.x, vb.x, best[2 * jj]);
                     best[2 * jj + 1] = fmax3f(va.y, vb.y, best[2 * jj + 1]);
                 }
+            };
+            // two pairs per iteration (ping-pong states A / B: no register rotation)
+            PairSt A, Bq;
+            setup(qp[0], qp[2], A);
+            const float4* const qlast = Q + (CP - 2) * 2;   // the look-ahead stops at the last pair (CP >= 8)
+            float4 na = qp[4], nb = qp[6];
+            qp += 8;
+#pragma unroll 1
+            for (int k = 0; k < nch; ++k) {
+#pragma unroll 1
+              for (int p = 0; p < CH / 4; ++p) {
+                setup(na, nb, Bq);                                     // pair 2p+1
+                qp = qp < qlast ? qp : qlast;
+                na = qp[0]; nb = qp[2];                                // pair 2p+2
+                qp += 4;
+                chains(A);
+                setup(na, nb, A);                                      // pair 2p+2
+                qp = qp < qlast ? qp : qlast;
+                na = qp[0]; nb = qp[2];                                // pair 2p+3
+                qp += 4;
+                chains(Bq);
               }
               // chunk boundary: pixels whose maximum moved inside this chunk (strictly up) remember the chunk
               const unsigned kk = (unsigned)k;
@@ -570,71 +581,111 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
 #pragma unroll
             for (int c = 0; c < 3; ++c) cxs[c] = clampi2(kx0 + c, 0, P.w - 1);
             const float Mk0 = mx0 * LOG2E, Mk1 = mx1 * LOG2E;
-#pragma unroll 1
-            for (int kb = 0; kb < C; kb += 32) {
-                const int k = kb + lane;
-                const int kk = k < CP ? k : CP - 1;
-                float cell[6];
+            // NB blocks of 32 classes per sweep: one broadcast LDS.128 of U then feeds 4 * NB packed fma (with one block
+            // the class phase leaned on the shared-memory pipe: 16 LDS.128 per 62 FFMA2, ncu mio_throttle / short
+            // scoreboard); an odd last block goes through the NB = 1 instance.  (Scalar FFMA instead of FFMA2 measured the
+            // same here: ~3 cycles per FFMA2 with three register-pair operands = 2 x ~1.5 per scalar FFMA with three
+            // register operands - tools/micro/loops23.cu.)
+            auto sweep = [&](auto nb_tag, int kb) {
+                constexpr int NB = decltype(nb_tag)::value;
+                int kq[NB];
+                float cell[NB][6];
 #pragma unroll
-                for (int c = 0; c < 6; ++c) cell[c] = 0.f;
+                for (int b = 0; b < NB; ++b) {
+                    const int k = kb + 32 * b + lane;
+                    kq[b] = (k < CP ? k : CP - 1) * 2;
+#pragma unroll
+                    for (int c = 0; c < 6; ++c) cell[b][c] = 0.f;
+                }
 #pragma unroll
                 for (int g = 0; g < 2; ++g) {
                     if (!(g ? any1 : any0)) continue;
-                    const float4 q = reinterpret_cast<const float4*>(quads)[kk * 2 + g];     // p0, p1, q0, q1
-                    // row y: v0 = p0 + ly p1, delta = q0 + ly q1, ly = (y + 0.5) / 16
-                    const float aE0 = fmaf(fmaf(0.5f * RS, q.y, q.x), LOG2E, -(g ? Mk1 : Mk0));
-                    const float E0 = ex2f(aE0), sg = ex2f(q.y * (RS * LOG2E));
-                    const float r0 = ex2f(fmaf(0.5f * RS, q.w, q.z) * LOG2E), ta = ex2f(q.w * (RS * LOG2E));
-                    const float sg2 = sg * sg, ta2 = ta * ta;
-                    float2 e2a = make_float2(E0, E0 * sg), r2a = make_float2(r0, r0 * ta);
-                    float2 e2b = fmul2(e2a, bc2(sg2)), r2b = fmul2(r2a, bc2(ta2));
-                    const float2 sg4 = bc2(sg2 * sg2), ta4 = bc2(ta2 * ta2);
-                    float2 aG = make_float2(0.f, 0.f), aX = aG, aYG = aG, aYX = aG;
+                    float2 e2a[NB], e2b[NB], r2a[NB], r2b[NB], aG[NB], aX[NB], aYG[NB], aYX[NB];
+                    float sg4[NB], ta4[NB];
+#pragma unroll
+                    for (int b = 0; b < NB; ++b) {
+                        const float4 q = reinterpret_cast<const float4*>(quads)[kq[b] + g];      // p0, p1, q0, q1
+                        // row y: v0 = p0 + ly p1, delta = q0 + ly q1, ly = (y + 0.5) / 16
+                        const float aE0 = fmaf(fmaf(0.5f * RS, q.y, q.x), LOG2E, -(g ? Mk1 : Mk0));
+                        const float E0 = ex2f(aE0), sg = ex2f(q.y * (RS * LOG2E));
+                        const float r0 = ex2f(fmaf(0.5f * RS, q.w, q.z) * LOG2E), ta = ex2f(q.w * (RS * LOG2E));
+                        const float sg2 = sg * sg, ta2 = ta * ta;
+                        e2a[b] = make_float2(E0, E0 * sg); r2a[b] = make_float2(r0, r0 * ta);
+                        e2b[b] = fmul2(e2a[b], bc2(sg2)); r2b[b] = fmul2(r2a[b], bc2(ta2));
+                        sg4[b] = sg2 * sg2; ta4[b] = ta2 * ta2;
+                        aG[b] = make_float2(0.f, 0.f); aX[b] = aG[b]; aYG[b] = aG[b]; aYX[b] = aG[b];
+                    }
                     const float4* U4 = reinterpret_cast<const float4*>(Usm + g * RC_USTRIDE);
                     float2 lya = make_float2(0.5f * RS, 1.5f * RS), lyb = make_float2(2.5f * RS, 3.5f * RS);
 #pragma unroll 1
                     for (int up = 0; up < 4; ++up) {
                         // rows 4up..4up+3: chain a = rows (4up, 4up+1), chain b = rows (4up+2, 4up+3)
+                        float2 ha[NB], hb[NB], dA[NB], dB[NB];
                         float4 u = U4[(S - 1) * 4];
-                        float2 ha = make_float2(u.x, u.y), hb = make_float2(u.z, u.w);
-                        float2 dA = ha, dB = hb;
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+                            ha[b] = make_float2(u.x, u.y); hb[b] = make_float2(u.z, u.w);
+                            dA[b] = ha[b]; dB[b] = hb[b];
+                        }
                         u = U4[(S - 2) * 4];
-                        ha = ffma2(ha, r2a, make_float2(u.x, u.y));
-                        hb = ffma2(hb, r2b, make_float2(u.z, u.w));
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+                            ha[b] = ffma2(ha[b], r2a[b], make_float2(u.x, u.y));
+                            hb[b] = ffma2(hb[b], r2b[b], make_float2(u.z, u.w));
+                        }
 #pragma unroll
                         for (int j = S - 3; j >= 0; --j) {
                             u = U4[j * 4];
-                            dA = ffma2(dA, r2a, ha);
-                            dB = ffma2(dB, r2b, hb);
-                            ha = ffma2(ha, r2a, make_float2(u.x, u.y));
-                            hb = ffma2(hb, r2b, make_float2(u.z, u.w));
+#pragma unroll
+                            for (int b = 0; b < NB; ++b) {
+                                dA[b] = ffma2(dA[b], r2a[b], ha[b]);
+                                dB[b] = ffma2(dB[b], r2b[b], hb[b]);
+                                ha[b] = ffma2(ha[b], r2a[b], make_float2(u.x, u.y));
+                                hb[b] = ffma2(hb[b], r2b[b], make_float2(u.z, u.w));
+                            }
                         }
-                        const float2 Ga = fmul2(e2a, ha), Gb = fmul2(e2b, hb);                       // sum_j g
-                        const float2 Xa = fmul2(fmul2(e2a, r2a), dA), Xb = fmul2(fmul2(e2b, r2b), dB);   // sum_j j g
-                        aG = fadd2(aG, fadd2(Ga, Gb));
-                        aX = fadd2(aX, fadd2(Xa, Xb));
-                        aYG = ffma2(lya, Ga, ffma2(lyb, Gb, aYG));
-                        aYX = ffma2(lya, Xa, ffma2(lyb, Xb, aYX));
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+                            const float2 Ga = fmul2(e2a[b], ha[b]), Gb = fmul2(e2b[b], hb[b]);                // sum_j g
+                            const float2 Xa = fmul2(fmul2(e2a[b], r2a[b]), dA[b]);                            // sum_j j g
+                            const float2 Xb = fmul2(fmul2(e2b[b], r2b[b]), dB[b]);
+                            aG[b] = fadd2(aG[b], fadd2(Ga, Gb));
+                            aX[b] = fadd2(aX[b], fadd2(Xa, Xb));
+                            aYG[b] = ffma2(lya, Ga, ffma2(lyb, Gb, aYG[b]));
+                            aYX[b] = ffma2(lya, Xa, ffma2(lyb, Xb, aYX[b]));
+                            e2a[b] = fmul2(e2a[b], bc2(sg4[b])); e2b[b] = fmul2(e2b[b], bc2(sg4[b]));
+                            r2a[b] = fmul2(r2a[b], bc2(ta4[b])); r2b[b] = fmul2(r2b[b], bc2(ta4[b]));
+                        }
                         ++U4;
-                        e2a = fmul2(e2a, sg4); e2b = fmul2(e2b, sg4);
-                        r2a = fmul2(r2a, ta4); r2b = fmul2(r2b, ta4);
                         lya = fadd2(lya, bc2(4.f * RS)); lyb = fadd2(lyb, bc2(4.f * RS));
                     }
-                    const float G = aG.x + aG.y, X = aX.x + aX.y, YG = aYG.x + aYG.y, YX = aYX.x + aYX.y;
-                    const float SX = fmaf(X, RS, G * LX0);              // sum lambda_x g
-                    const float SYX = fmaf(YX, RS, YG * LX0);           // sum lambda_y lambda_x g
-                    const float gD = SYX, gB = SX - SYX, gC = YG - SYX, gA = (G - SX) - gC;
-                    cell[g] += gA; cell[g + 1] += gB; cell[3 + g] += gC; cell[3 + g + 1] += gD;
-                }
-                if (k < C) {
-                    float* gk = gimg + (size_t)k * plane;
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        if (cell[c] != 0.f) red_add_f32(gk + (size_t)cy0 * P.w + cxs[c], cell[c]);
-                        if (cell[3 + c] != 0.f) red_add_f32(gk + (size_t)cy1 * P.w + cxs[c], cell[3 + c]);
+                    for (int b = 0; b < NB; ++b) {
+                        const float G = aG[b].x + aG[b].y, X = aX[b].x + aX[b].y;
+                        const float YG = aYG[b].x + aYG[b].y, YX = aYX[b].x + aYX[b].y;
+                        const float SX = fmaf(X, RS, G * LX0);              // sum lambda_x g
+                        const float SYX = fmaf(YX, RS, YG * LX0);           // sum lambda_y lambda_x g
+                        const float gD = SYX, gB = SX - SYX, gC = YG - SYX, gA = (G - SX) - gC;
+                        cell[b][g] += gA; cell[b][g + 1] += gB; cell[b][3 + g] += gC; cell[b][3 + g + 1] += gD;
                     }
                 }
-            }
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    const int k = kb + 32 * b + lane;
+                    if (k < C) {
+                        float* gk = gimg + (size_t)k * plane;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            if (cell[b][c] != 0.f) red_add_f32(gk + (size_t)cy0 * P.w + cxs[c], cell[b][c]);
+                            if (cell[b][3 + c] != 0.f) red_add_f32(gk + (size_t)cy1 * P.w + cxs[c], cell[b][3 + c]);
+                        }
+                    }
+                }
+            };
+            int kb = 0;
+#pragma unroll 1
+            for (; kb + 32 < C; kb += 64) sweep(std::integral_constant<int, 2>{}, kb);
+            if (kb < C) sweep(std::integral_constant<int, 1>{}, kb);
         }
         __syncwarp();                                       // quads / U free for the next job
         // ---- the box of the warp's next job (its latency is covered by the SM's other warps) -----------------------
