@@ -66,6 +66,11 @@ int lc2is_proto_normalize(const float* d_t, int n_sets, int C, int D, int normal
  * d_t_hat    [n_sets, C_pad, D] bf16 from K0.
  * d_v_hat    [B*hw, D] bf16 out/workspace: normalised (or plain) patch rows as fed to the
  *            tensor cores; kept for the backward.
+ *            NULL (bf16 V, normalize = 1 only): the row normalisation runs INSIDE the GEMM - four extra warps sum the
+ *            squares of each row from the staged operand tiles while the MMAs run, the epilogue scales the row by
+ *            1/max(||v||,1e-12) - and no v_hat exists (the operand of the tensor cores is the raw V, the fp32 row factor
+ *            is applied to the fp32 accumulator: closer to the fp32 reference than rounding v_hat to bf16).  The backward
+ *            then takes V itself: lc2is_cosine_logits_bwd_ex(..., LC2IS_BWD_RAW_V).
  * d_inv_norm_v [B*hw] fp32 out: 1/max(||v||,1e-12) (1.0 if !normalize).
  * d_logits   [B, C, hw] fp32 out (class-plane major = the reference's 'b k h w'):
  *            logit_scale * <v_hat, t_hat>.  bf16 operands, fp32 accumulate (tcgen05/TMEM).
@@ -110,6 +115,11 @@ int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, const float*
  * d_grad_v second (d_grad_t = NULL, this flag), so that a data-parallel caller can all-reduce the prototype gradient
  * while the patch-gradient GEMM runs. */
 #define LC2IS_BWD_REUSE_PREP 1
+/* LC2IS_BWD_RAW_V: `d_v_hat` is the RAW bf16 V (what lc2is_cosine_logits_fwd took when it was called with
+ * d_v_hat = NULL and normalised inside the GEMM) - v_hat = V * inv_norm_v is never materialised: the bf16 operand of the
+ * two GEMMs is G * inv_norm_v and the normalise-backward of the patches is folded into the dV epilogue.  Needs
+ * normalize = 1 and an fp32 gradient. */
+#define LC2IS_BWD_RAW_V 2
 int lc2is_cosine_logits_bwd_ex(const void* d_grad_logits, int g_dtype, const float* d_logits,
                                const void* d_v_hat, const float* d_inv_norm_v,
                                const void* d_t_hat, const float* d_inv_norm_t,

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "liblc2is_b200.so")
 
 F32, BF16 = 0, 1
 BILINEAR, BICUBIC = 0, 1
+BWD_REUSE_PREP, BWD_RAW_V = 1, 2      # flags of lc2is_cosine_logits_bwd_ex
 
 
 class Lc2isError(RuntimeError):

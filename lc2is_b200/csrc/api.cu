@@ -531,8 +531,9 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
             STEP_RC(lc2is_count_valid(d_labels + lab_off, (int64_t)nb * H * W, C, ignore_index, d_nvalid, stream));
         mark("prepass", st);
         if (i == 0) STEP_RC(lc2is_proto_normalize(d_t, 1, C, D, 1, d_that, d_invt, stream));
+        // (row normalisation inside the GEMM: no v_hat; the backward takes the raw V)
         STEP_RC(lc2is_cosine_logits_fwd(d_v + v_off, LC2IS_BF16, nb, hw, D, d_that, 1, C, 1, logit_scale,
-                                        d_vhat + v_off, d_invv + (size_t)b0 * hw, lg, stream));
+                                        nullptr, d_invv + (size_t)b0 * hw, lg, stream));
         mark("k1", st);
         if (fused) {
             // (two-byte labels packed on the host arrive un-counted: the CE warps count them)
@@ -553,9 +554,9 @@ static int head_step_enqueue(const void* h_v, const float* h_t, const int64_t* h
     STEP_RC(lc2is_mean_scale(d_nvalid, 1.0f, d_gscale, stream));
     if (do_backward) {
         STEP_CUDA(cudaMemsetAsync(ws + L.grad_t, 0, (size_t)C * D * 4, st));
-        STEP_RC(lc2is_cosine_logits_bwd(d_glow, LC2IS_F32, d_logits, d_vhat, d_invv, d_that, d_invt, B, hw, D, 1, C,
-                                        1, logit_scale, d_gscale, ws + L.grad_v, LC2IS_BF16,
-                                        (float*)(ws + L.grad_t), ws + L.bwd_ws, stream));
+        STEP_RC(lc2is_cosine_logits_bwd_ex(d_glow, LC2IS_F32, d_logits, d_v, d_invv, d_that, d_invt, B, hw, D, 1, C,
+                                           1, logit_scale, d_gscale, ws + L.grad_v, LC2IS_BF16,
+                                           (float*)(ws + L.grad_t), ws + L.bwd_ws, stream, LC2IS_BWD_RAW_V));
     }
     mark("bwd", st);
     STEP_RC(lc2is_finalize_loss(d_loss_sum, d_nvalid, d_loss, stream));

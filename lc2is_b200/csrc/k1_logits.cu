@@ -122,6 +122,10 @@ struct K1Params {
     int B, hw, C, C_pad, n_sets;
     int NB, n_ntiles, tiles_per_img, num_kb, stages;
     float scale;
+    // EPI 0 with fuse_norm: A is the RAW bf16 V; warps 6-9 sum the squares of each row from the staged A tiles while
+    // the MMAs run and the epilogue scales the row by 1 / max(||v||, 1e-12) (F.normalize) - no v_hat round trip
+    int fuse_norm;
+    float* inv_v;          // [B*hw] out (fuse_norm): the row factors, for the backward
 };
 
 // Row-major epilogue staging.  In TMEM a thread owns a ROW, so storing straight from registers makes every warp store
@@ -211,7 +215,10 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tfull = empty + K1_MAX_STAGES;
     uint64_t* tempty = tfull + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* nfull = tempty + 3;                                // fuse_norm: row factors of accumulator buffer i ready
     uint8_t* epi_scr = reinterpret_cast<uint8_t*>(full) + 256;   // EPI 1 only: 4 warps x 4 KB (16-byte aligned)
+    float* inv_s = reinterpret_cast<float*>(epi_scr);            // EPI 0 + fuse_norm: [2][128] row factors
+    const bool fuse_norm = EPI == 0 && P.fuse_norm;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = P.B * P.tiles_per_img * P.n_ntiles;
@@ -219,8 +226,12 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&tmA);
         tc::prefetch_tmap(&tmB);
-        for (int i = 0; i < P.stages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, 1); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, EPI == 0 ? 4 : K1_EPI_WARPS_RM); }
+        // a stage is free when its MMAs have retired AND (fuse_norm) the four norm warps have read it
+        for (int i = 0; i < P.stages; ++i) { tc::mbar_init(full + i, 1); tc::mbar_init(empty + i, fuse_norm ? 5 : 1); }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(tfull + i, 1); tc::mbar_init(tempty + i, EPI == 0 ? 4 : K1_EPI_WARPS_RM);
+            tc::mbar_init(nfull + i, 4);
+        }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_ptr, 512);
@@ -229,7 +240,47 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
-    if (warp == 0) {
+    if (EPI == 0 && warp >= 6) {
+        // ===== norm warps (fuse_norm): lane = one row of the 128-row A tile =====
+        if (fuse_norm) {
+            const int row = (warp - 6) * 32 + lane;
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                const uint32_t bphase = (it >> 1) & 1;
+                const int mt = tile / P.n_ntiles;
+                const int b = mt / P.tiles_per_img, ti = mt - b * P.tiles_per_img;
+                tc::mbar_wait(tempty + buf, bphase ^ 1);       // the epilogue of tile it-2 has read inv_s[buf]
+                float ss = 0.f;
+                for (int kb = 0; kb < P.num_kb; ++kb) {
+                    tc::mbar_wait(full + stage, phase);
+                    const uint8_t* ar = smem + (size_t)stage * stage_bytes + row * 128;
+                    // the row's eight 16-byte chunks in any order (a sum); lane-rotated so that the eight rows of a
+                    // swizzle atom read eight different chunk positions (no bank conflict)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(ar + (((i + lane) & 7) << 4));
+                        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
+                            ss = fmaf(lo, lo, ss); ss = fmaf(hi, hi, ss);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(empty + stage);
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                }
+                const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+                inv_s[buf * 128 + row] = inv;
+                const int p = ti * K1_BM + row;
+                if (p < P.hw && P.inv_v) P.inv_v[(size_t)b * P.hw + p] = inv;
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(nfull + buf);
+            }
+        }
+    } else if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
@@ -275,7 +326,7 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc::umma_commit(tfull + buf);                   // accumulator ready
             }
         }
-    } else {
+    } else if (EPI != 0 || warp < 6) {
         // ===== epilogue: TMEM -> registers -> global (class-plane major) =====
         const int q = warp & 3;                                 // TMEM lane quarter this warp may read
         int it = 0;
@@ -292,6 +343,11 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t taddr = tmem_base + buf * 256 + ((uint32_t)(q * 32) << 16);
             const int n0 = nt * P.NB;
             if constexpr (EPI == 0) {
+                float sc = P.scale;
+                if (fuse_norm) {
+                    tc::mbar_wait(nfull + buf, bphase);
+                    sc *= inv_s[buf * 128 + q * 32 + lane];
+                }
                 for (int col = 0; col < P.NB; col += 16) {
                     if (n0 + col >= P.C) break;                 // warp-uniform
                     uint32_t r[16];
@@ -300,7 +356,7 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const int c = n0 + col + j;
-                        if (rvalid && c < P.C) __stcs(orow + (size_t)c * P.hw, __uint_as_float(r[j]) * P.scale);
+                        if (rvalid && c < P.C) __stcs(orow + (size_t)c * P.hw, __uint_as_float(r[j]) * sc);
                     }
                 }
             } else {
@@ -586,7 +642,12 @@ extern "C" int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int 
                                        void* d_v_hat, float* d_inv_norm_v, float* d_logits,
                                        lc2is_stream_t stream) {
     if (int e = ensure_device()) return e;
-    if (!d_v || !d_t_hat || !d_v_hat || !d_logits) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (!d_v || !d_t_hat || !d_logits) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    // d_v_hat == NULL: the normalisation runs inside the GEMM on the raw bf16 V (no v_hat is written; the backward then
+    // takes V itself with LC2IS_BWD_RAW_V)
+    const bool fuse = d_v_hat == nullptr;
+    if (fuse && (v_dtype != LC2IS_BF16 || !normalize || !d_inv_norm_v))
+        return fail(LC2IS_ERR_ARG, "d_v_hat may only be NULL for bf16 V with normalize = 1 and d_inv_norm_v given%s");
     if (B < 0 || hw <= 0 || C <= 0 || D <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
     if (D % K1_BK) return fail(LC2IS_ERR_SHAPE, "D must be a multiple of 64 (got %s%lld)", "", D);
     if (n_sets != 1 && n_sets != B) return fail(LC2IS_ERR_SHAPE, "n_sets must be 1 or B%s");
@@ -595,13 +656,15 @@ extern "C" int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int 
     cudaStream_t st = (cudaStream_t)stream;
     const long long M = (long long)B * hw;
     // ---- K1a: normalise rows, round to bf16 -------------------------------------------------------
-    if (v_dtype == LC2IS_F32)
+    if (fuse) {
+        // (inside the GEMM)
+    } else if (v_dtype == LC2IS_F32)
         launch_rownorm<float>((const float*)d_v, 1, (int)M, (int)M, D, normalize, (__nv_bfloat16*)d_v_hat, d_inv_norm_v, st);
     else if (v_dtype == LC2IS_BF16)
         launch_rownorm<__nv_bfloat16>((const __nv_bfloat16*)d_v, 1, (int)M, (int)M, D, normalize, (__nv_bfloat16*)d_v_hat, d_inv_norm_v, st);
     else
         return fail(LC2IS_ERR_ARG, "v_dtype must be LC2IS_F32 or LC2IS_BF16%s");
-    LC2IS_CHECK_LAUNCH("rownorm_kernel(v)");
+    if (!fuse) LC2IS_CHECK_LAUNCH("rownorm_kernel(v)");
 
     // ---- K1: GEMM ------------------------------------------------------------------------------------
     K1Params P;
@@ -613,22 +676,24 @@ extern "C" int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int 
     P.tiles_per_img = (hw + K1_BM - 1) / K1_BM;
     P.num_kb = D / K1_BK;
     P.scale = logit_scale;
+    P.fuse_norm = fuse ? 1 : 0;
+    P.inv_v = fuse ? d_inv_norm_v : nullptr;
     const int stage_bytes = K1_A_BYTES + P.NB * 128;
     int stages = (200 * 1024) / stage_bytes;
     if (stages > K1_MAX_STAGES) stages = K1_MAX_STAGES;
     if (stages > P.num_kb * 2) stages = P.num_kb * 2;
     if (stages < 2) stages = 2;
     P.stages = stages;
-    size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+    size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*row factors*/;
     if (smem < 120 * 1024) smem = 120 * 1024;      // one CTA per SM: it owns all 512 TMEM columns
     CUtensorMap tmA, tmB;
-    if (int e = make_tmap_2d_bf16(&tmA, d_v_hat, (uint64_t)M, (uint64_t)D, K1_BM, K1_BK)) return e;
+    if (int e = make_tmap_2d_bf16(&tmA, fuse ? d_v : d_v_hat, (uint64_t)M, (uint64_t)D, K1_BM, K1_BK)) return e;
     if (int e = make_tmap_2d_bf16(&tmB, d_t_hat, (uint64_t)n_sets * P.C_pad, (uint64_t)D, P.NB, K1_BK)) return e;
     LC2IS_CUDA(cudaFuncSetAttribute(k1_logits_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int total_tiles = B * P.tiles_per_img * P.n_ntiles;
     int grid = sm_count();
     if (grid > total_tiles) grid = total_tiles;
-    k1_logits_kernel<0><<<grid, K1_THREADS, smem, st>>>(tmA, tmB, P);
+    k1_logits_kernel<0><<<grid, fuse ? K1_THREADS + 128 : K1_THREADS, smem, st>>>(tmA, tmB, P);
     LC2IS_CHECK_LAUNCH("k1_logits_kernel");
     return 0;
 }
@@ -649,6 +714,7 @@ extern "C" int lc2is_linear_fwd(const void* d_x_bf16, const void* d_w_bf16, cons
     if (M == 0) return 0;
     K1Params P;
     P.out = nullptr; P.out_rm = d_y; P.bias = d_bias; P.out_f32 = y_dtype == LC2IS_F32;
+    P.fuse_norm = 0; P.inv_v = nullptr;
     P.B = 1; P.hw = (int)M; P.C = N; P.C_pad = N; P.n_sets = 1;
     // 2-SM form (CTA pairs, 256 x 256 tiles) for shapes it tiles exactly and that fill the GPU more than once;
     // LC2IS_LINEAR_2SM=0 / 1 forces the choice

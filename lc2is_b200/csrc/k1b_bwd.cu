@@ -71,7 +71,9 @@ constexpr int PREPF_CPW = 8;                  // classes per warp and class roun
 __global__ void __launch_bounds__(PREPF_W * 32)
 k1b_prep_f32_kernel(const float* __restrict__ G, const float* __restrict__ L, int B, int C, int C_pad, int hw,
                     int n_sets, int want_proj, int px_blocks, __nv_bfloat16* __restrict__ Gb, float* __restrict__ r,
-                    float* __restrict__ rt) {
+                    float* __restrict__ rt, const float* __restrict__ row_scale) {
+    // row_scale (LC2IS_BWD_RAW_V): the bf16 operand is G[m,c] * inv||v_m||, so that both GEMMs can run on the RAW V:
+    //   dThat = (G inv)^T V = G^T Vhat,   dV = s (G inv) That - V inv^2 r   (the projections r, rt use the unscaled G)
     // px_blocks consecutive 128-pixel blocks per CTA: the class sums of a warp stay in registers across them, so rt
     // receives one reduction per (class, CTA) - with one block per CTA the 128^2 grid would hammer 150 addresses
     // with 300 K reductions
@@ -95,6 +97,8 @@ k1b_prep_f32_kernel(const float* __restrict__ G, const float* __restrict__ L, in
             const float* l = L + (size_t)b * C * hw + p;
             __nv_bfloat16* gb = Gb + (size_t)b * C_pad * hw + p;
             float4 racc = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 rs = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (row_scale && in) rs = __ldg(reinterpret_cast<const float4*>(row_scale + (size_t)b * hw + p));
 #pragma unroll
             for (int k = 0; k < PREPF_CPW; ++k) {
                 const int c = cr + warp + k * PREPF_W;
@@ -105,7 +109,7 @@ k1b_prep_f32_kernel(const float* __restrict__ G, const float* __restrict__ L, in
                     if (want_proj) lv = __ldg(reinterpret_cast<const float4*>(l + (size_t)c * hw));
                 }
                 if (in) {
-                    __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x, gv.y), hi = __floats2bfloat162_rn(gv.z, gv.w);
+                    __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x * rs.x, gv.y * rs.y), hi = __floats2bfloat162_rn(gv.z * rs.z, gv.w * rs.w);
                     uint2 pk;
                     pk.x = *reinterpret_cast<unsigned*>(&lo); pk.y = *reinterpret_cast<unsigned*>(&hi);
                     *reinterpret_cast<uint2*>(gb + (size_t)c * hw) = pk;
@@ -151,6 +155,7 @@ struct DvParams {
     int B, hw, D, C_pad, n_sets;
     int tiles_per_img, n_ntiles, num_kb, stages;
     int normalize, out_f32;
+    int raw_v;                  // v_hat points at the RAW bf16 V and G was scaled by inv||v|| (LC2IS_BWD_RAW_V)
     float scale;
 };
 constexpr int DV_BM = 128, DV_BN = 256, DV_KB = 16;
@@ -249,7 +254,10 @@ k1b_dv_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ C
             const bool rvalid = p < P.hw;
             const size_t m = (size_t)b * P.hw + (rvalid ? p : 0);
             const float inv = rvalid ? __ldg(P.inv_v + m) : 0.f;
-            const float rr = (rvalid && P.normalize) ? __ldg(P.r + m) * gs : 0.f;
+            float rr = (rvalid && P.normalize) ? __ldg(P.r + m) * gs : 0.f;
+            // raw V: acc already carries inv (G was scaled by it): dV = s acc - v (inv^2 r)
+            const float oinv = P.raw_v ? 1.f : inv;
+            if (P.raw_v) rr *= inv * inv;
             // 64 channels = 128 bytes of v_hat per row at a time.  The two warps of a lane quarter take alternate groups.
             // v_hat is fetched coalesced (4 rows x 128 bytes per load) one group AHEAD into registers - the first group
             // before the accumulator is even ready - parked in the warp's swizzled scratch and read back by the thread that
@@ -301,8 +309,8 @@ k1b_dv_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ C
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float va = __uint_as_float(w[j] << 16), vb = __uint_as_float(w[j] & 0xffff0000u);
-                            o[2 * j] = (__uint_as_float(acc[2 * j]) * sg - va * rr) * inv;
-                            o[2 * j + 1] = (__uint_as_float(acc[2 * j + 1]) * sg - vb * rr) * inv;
+                            o[2 * j] = (__uint_as_float(acc[2 * j]) * sg - va * rr) * oinv;
+                            o[2 * j + 1] = (__uint_as_float(acc[2 * j + 1]) * sg - vb * rr) * oinv;
                         }
                     } else {
 #pragma unroll
@@ -534,6 +542,9 @@ extern "C" int lc2is_cosine_logits_bwd_ex(const void* d_grad_logits, int g_dtype
     float* d_rt = (float*)(ws + L.rt);
     float* d_dtraw = (float*)(ws + L.dt_raw);
     const bool reuse = (flags & LC2IS_BWD_REUSE_PREP) != 0;
+    const bool raw_v = (flags & LC2IS_BWD_RAW_V) != 0;
+    if (raw_v && (!normalize || g_dtype != LC2IS_F32))
+        return fail(LC2IS_ERR_ARG, "LC2IS_BWD_RAW_V needs normalize = 1 and an fp32 gradient (its bf16 operand is scaled by inv||v||)%s");
     if (reuse && d_grad_t) return fail(LC2IS_ERR_ARG, "LC2IS_BWD_REUSE_PREP is for a dV-only call (d_grad_t must be NULL)%s");
     if (!reuse) LC2IS_CUDA(cudaMemsetAsync(ws + L.r, 0, L.gbf - L.r, st));  // r, rt and dt_raw
 
@@ -549,7 +560,7 @@ extern "C" int lc2is_cosine_logits_bwd_ex(const void* d_grad_logits, int g_dtype
         dim3 grid((nblk + px_blocks - 1) / px_blocks, B, PREPF_CS);
         k1b_prep_f32_kernel<<<grid, PREPF_W * 32, 0, st>>>((const float*)d_grad_logits, d_logits, B, C, C_pad, hw,
                                                            n_sets, normalize, px_blocks, (__nv_bfloat16*)(ws + L.gbf),
-                                                           d_r, d_rt);
+                                                           d_r, d_rt, raw_v ? d_inv_norm_v : nullptr);
         LC2IS_CHECK_LAUNCH("k1b_prep_f32_kernel");
     } else if (normalize) {
         dim3 grid((hw + PREP_PX - 1) / PREP_PX, B);
@@ -567,7 +578,7 @@ extern "C" int lc2is_cosine_logits_bwd_ex(const void* d_grad_logits, int g_dtype
         P.num_kb = C_pad / DV_KB;
         P.stages = P.num_kb * 2 < 8 ? P.num_kb * 2 : 8;       // the K loop is short: 8 x 12 KB leaves room for the epilogue scratch
         if (P.stages < 2) P.stages = 2;
-        P.normalize = normalize; P.out_f32 = gv_dtype == LC2IS_F32; P.scale = logit_scale;
+        P.normalize = normalize; P.out_f32 = gv_dtype == LC2IS_F32; P.scale = logit_scale; P.raw_v = raw_v ? 1 : 0;
         CUtensorMap tmG, tmT;
         if (int e = make_tmap_3d_bf16(&tmG, d_grad_logits_bf16, B, C_pad, hw, DV_KB, 64)) return e;
         if (int e = make_tmap_2d_bf16(&tmT, d_t_hat, (uint64_t)n_sets * C_pad, D, DV_KB, 64)) return e;

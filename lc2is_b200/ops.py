@@ -60,8 +60,10 @@ def linear_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, out_dty
 
 # ---- K1 -----------------------------------------------------------------------------------
 def cosine_logits_fwd(v: Tensor, t_hat: Tensor, C: int, hw_shape: Tuple[int, int], normalize: bool = True,
-                      logit_scale: float = 1.0) -> Tuple[Tensor, Tensor, Tensor]:
-    """v [B,hw,D] fp32/bf16, t_hat from K0 -> (logits fp32 [B,C,h,w], v_hat bf16 [B*hw,D], inv_norm_v)."""
+                      logit_scale: float = 1.0, fuse_norm: bool = False) -> Tuple[Tensor, Optional[Tensor], Tensor]:
+    """v [B,hw,D] fp32/bf16, t_hat from K0 -> (logits fp32 [B,C,h,w], v_hat bf16 [B*hw,D], inv_norm_v).
+    fuse_norm (bf16 v, normalize): the row normalisation runs inside the GEMM on the raw V; v_hat is None and the
+    backward takes v itself (``cosine_logits_bwd(..., raw_v=True)``)."""
     if not v.is_cuda:
         raise _lib.Lc2isError("v must be a CUDA tensor (lc2is_b200 has no CPU fallback)")
     v = v.contiguous()
@@ -69,7 +71,9 @@ def cosine_logits_fwd(v: Tensor, t_hat: Tensor, C: int, hw_shape: Tuple[int, int
     h, w = hw_shape
     assert h * w == hw
     n_sets = t_hat.shape[0]
-    v_hat = torch.empty(B * hw, D, dtype=torch.bfloat16, device=v.device)
+    if fuse_norm and not (v.dtype == torch.bfloat16 and normalize):
+        raise _lib.Lc2isError("fuse_norm needs bf16 v and normalize=True")
+    v_hat = None if fuse_norm else torch.empty(B * hw, D, dtype=torch.bfloat16, device=v.device)
     inv_v = torch.empty(B * hw, dtype=torch.float32, device=v.device)
     logits = torch.empty(B, C, h, w, dtype=torch.float32, device=v.device)
     check(lib.lc2is_cosine_logits_fwd(ptr(v), _dt(v), B, hw, D, ptr(t_hat), n_sets, C, int(normalize),
@@ -91,12 +95,13 @@ def grad_to_bf16(grad: Tensor) -> Tensor:
 def cosine_logits_bwd(grad: Tensor, logits: Tensor, v_hat: Tensor, inv_v: Tensor, t_hat: Tensor,
                       inv_t: Tensor, C: int, normalize: bool = True, logit_scale: float = 1.0,
                       grad_scale: Optional[Tensor] = None, grad_v_dtype=torch.float32,
-                      grad_t: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+                      grad_t: Optional[Tensor] = None, raw_v: bool = False) -> Tuple[Tensor, Tensor]:
     """grad: dL/dlogits, bf16 [B,C_pad,hw] or fp32 [B,C,h,w] (converted inside the projection pass).
+    raw_v: `v_hat` is the raw bf16 V of a fuse_norm forward (fp32 grad only).
     -> (grad_v [B,hw,D], grad_t fp32 [n_sets,C,D]); grad_t is accumulated into if given."""
     B = logits.shape[0]
     hw = logits[0, 0].numel()
-    D = v_hat.shape[1]
+    D = v_hat.shape[-1]
     n_sets = t_hat.shape[0]
     dev = logits.device
     grad = grad.contiguous()
@@ -105,9 +110,10 @@ def cosine_logits_bwd(grad: Tensor, logits: Tensor, v_hat: Tensor, inv_v: Tensor
         grad_t = torch.zeros(n_sets, C, D, dtype=torch.float32, device=dev)
     nbytes = int(lib.lc2is_cosine_logits_bwd_workspace(B, hw, D, n_sets, C))
     ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
-    check(lib.lc2is_cosine_logits_bwd(ptr(grad), _dt(grad), ptr(logits), ptr(v_hat), ptr(inv_v), ptr(t_hat), ptr(inv_t),
-                                      B, hw, D, n_sets, C, int(normalize), float(logit_scale), ptr(grad_scale),
-                                      ptr(grad_v), _dt(grad_v), ptr(grad_t), ptr(ws), stream_ptr()),
+    check(lib.lc2is_cosine_logits_bwd_ex(ptr(grad), _dt(grad), ptr(logits), ptr(v_hat), ptr(inv_v), ptr(t_hat), ptr(inv_t),
+                                         B, hw, D, n_sets, C, int(normalize), float(logit_scale), ptr(grad_scale),
+                                         ptr(grad_v), _dt(grad_v), ptr(grad_t), ptr(ws), stream_ptr(),
+                                         _lib.BWD_RAW_V if raw_v else 0),
           "lc2is_cosine_logits_bwd")
     return grad_v, grad_t
 

@@ -77,7 +77,10 @@ class HeadStep:
         e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
         self.t_hat = e(1, Cp, D, dt=torch.bfloat16)
         self.inv_t = e(1, C)
-        self.v_hat = e(M, D, dt=torch.bfloat16)
+        # bf16 V + normalize: the row normalisation runs inside the logits GEMM and the backward takes the raw V
+        # (lc2is_cosine_logits_fwd with d_v_hat = NULL, LC2IS_BWD_RAW_V) - no v_hat round trip
+        self.fuse_norm = bool(normalize and v_dtype == torch.bfloat16)
+        self.v_hat = None if self.fuse_norm else e(M, D, dt=torch.bfloat16)
         self.inv_v = e(M)
         self.logits = e(B, C, h, w)
         self.split = bool(lib.lc2is_ce_split_supported(h, w, H, W))     # label prepass + packed-label K2 / K3
@@ -217,9 +220,13 @@ class HeadStep:
         self._mark("K0+K1 logits")
         check(lib.lc2is_proto_normalize(ptr(t), 1, C, D, int(self.normalize), ptr(self.t_hat), ptr(self.inv_t), st),
               "proto_normalize")
+        fuse = self.fuse_norm and v.dtype == torch.bfloat16
+        if not fuse and self.v_hat is None:
+            self.v_hat = torch.empty(B * hw, D, dtype=torch.bfloat16, device=v.device)
         check(lib.lc2is_cosine_logits_fwd(ptr(v), BF16 if v.dtype == torch.bfloat16 else F32, B, hw, D,
                                           ptr(self.t_hat), 1, C, int(self.normalize), self.logit_scale,
-                                          ptr(self.v_hat), ptr(self.inv_v), ptr(self.logits), st), "cosine_logits_fwd")
+                                          None if fuse else ptr(self.v_hat), ptr(self.inv_v), ptr(self.logits), st),
+              "cosine_logits_fwd")
         self._mark("K2 upsample+CE")
         if self.k2_events is not None:
             self.k2_events[0].record()
@@ -240,10 +247,12 @@ class HeadStep:
             w_valid.wait()                                        # stream-level wait, no host sync
         check(lib.lc2is_mean_scale(ptr(blk.n_valid), 1.0, ptr(blk.gscale), st), "mean_scale")
         if self.backward:
-            check(lib.lc2is_cosine_logits_bwd(ptr(blk.grad_low), F32, ptr(self.logits), ptr(self.v_hat),
-                                              ptr(self.inv_v), ptr(self.t_hat), ptr(self.inv_t), B, hw, D, 1, C,
-                                              int(self.normalize), self.logit_scale, ptr(blk.gscale),
-                                              ptr(self.grad_v), BF16, ptr(blk.grad_t), ptr(self.bwd_ws), st),
+            check(lib.lc2is_cosine_logits_bwd_ex(ptr(blk.grad_low), F32, ptr(self.logits),
+                                                 ptr(v) if fuse else ptr(self.v_hat),
+                                                 ptr(self.inv_v), ptr(self.t_hat), ptr(self.inv_t), B, hw, D, 1, C,
+                                                 int(self.normalize), self.logit_scale, ptr(blk.gscale),
+                                                 ptr(self.grad_v), BF16, ptr(blk.grad_t), ptr(self.bwd_ws), st,
+                                                 _lib.BWD_RAW_V if fuse else 0),
                   "cosine_logits_bwd")
         self._mark("K3 argmax+confmat")
         if self.fused:

@@ -31,25 +31,6 @@ def _worker(rank, world, port, out):
     step.flush()                                             # ... and the last call's here
     cm_global = step.global_confmat().clone()                # ONE int64 all-reduce for both steps
     torch.cuda.synchronize()
-    eager = (float(step.loss), step.grad_t.clone(), int(step.n_valid))
-    # the same two calls replayed from CUDA graphs (collectives captured with the kernels)
-    graph_ok, graph_err = True, ""
-    try:
-        step.reset_metrics()
-        g1 = step.capture(vd, td, ld)
-        g2 = step.capture(vd, td, ld)
-        torch.cuda.synchronize()
-        step._cur, step._pending = g1.block ^ 1, None        # rewind the bookkeeping to before the captures
-        g1()
-        g2()
-        step.flush()
-        cm_graph = step.global_confmat().clone()
-        torch.cuda.synchronize()
-        graph_ok = bool(torch.equal(cm_graph, cm_global)) and int(step.n_valid) == eager[2] and \
-            abs(float(step.loss) - eager[0]) <= 1e-6 * abs(eager[0]) and \
-            float((step.grad_t - eager[1]).abs().max()) <= 1e-3 * float(eager[1].abs().max())
-    except Exception as e:  # noqa: BLE001
-        graph_ok, graph_err = False, repr(e)
     if rank == 0:
         ref = HeadStep(Bg, h, h, H, H, C, ignore_index=0, device=dev, distributed=False)
         ref(v.to(dev), t.to(dev), labels.to(dev))
@@ -60,7 +41,6 @@ def _worker(rank, world, port, out):
             "loss": (float(step.loss), float(ref.loss)),
             "gt_err": float((step.grad_t - ref.grad_t).abs().max() / ref.grad_t.abs().max()),
             "gv_err": float((step.grad_v.float() - ref.grad_v[:b].float()).abs().max() / ref.grad_v.float().abs().max()),
-            "graph_ok": graph_ok, "graph_err": graph_err,
         }
         torch.save(res, out)
     dist.barrier()
@@ -79,4 +59,3 @@ def test_two_gpu_step_matches_single_gpu(tmp_path):
     assert abs(r["loss"][0] - r["loss"][1]) <= 2e-6 * abs(r["loss"][1])
     assert r["gt_err"] < 2e-3, r                             # bf16 GEMM operands, different split-K partition
     assert r["gv_err"] < 2e-2, r
-    assert r["graph_ok"], r["graph_err"]

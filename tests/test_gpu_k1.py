@@ -191,3 +191,55 @@ def test_text_to_patch_module_matches_reference_module(golden_dir):
     ref_g = torch.autograd.grad(ref_v.square().mean(), [img, m.visual.weight, m.visual.bias])
     for got, ref in ((img.grad, ref_g[0]), (m.visual.weight.grad, ref_g[1]), (m.visual.bias.grad, ref_g[2])):
         assert float((got - ref).abs().max()) <= 3e-2 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("B,hw,C,scale", [
+    (2, 1024, 150, 1.0),          # 32^2 grid, one tile per SM
+    (1, 16384, 151, 14.285714),   # 128^2 grid: several tiles per CTA (double-buffered row factors)
+    (3, 200, 19, 1.0),            # ragged: hw not a multiple of 128 (rows of the next image / zero rows in the tile)
+    (2, 256, 847, 1.0),           # four N-tiles: the norm is recomputed per N-tile
+])
+def test_logits_fused_norm(B, hw, C, scale):
+    """d_v_hat = NULL: the row normalisation runs inside the GEMM (norm warps + epilogue scaling), no v_hat.
+    Operands of the tensor cores are the RAW bf16 V and bf16 t_hat; the fp32 row factor multiplies the accumulator."""
+    D = 512
+    v = synthetic.make_patch_embeddings(B, hw, D, dtype=torch.bfloat16)
+    t = synthetic.make_prototypes(C, D)
+    t_hat, _ = ops.proto_normalize(t.to(DEV), True)
+    h = int(hw ** 0.5); hw_shape = (h, hw // h) if h * (hw // h) == hw else (1, hw)
+    logits, v_hat, inv_v = ops.cosine_logits_fwd(v.to(DEV), t_hat, C, hw_shape, True, scale, fuse_norm=True)
+    assert v_hat is None
+    v32 = v.float()
+    torch.testing.assert_close(inv_v.cpu(), 1 / v32.norm(dim=2).reshape(-1).clamp_min(1e-12), rtol=1e-5, atol=0)
+    got = logits.reshape(B, C, hw).cpu()
+    ref_same = scale * inv_v.cpu().view(B, 1, hw) * torch.einsum("bpd,cd->bcp", v32, t_hat[0, :C].float().cpu())
+    assert float((got - ref_same).abs().max()) <= 2e-6 * max(float(ref_same.abs().max()), scale)
+    ref = O.cosine_logits(v32, t.float(), normalize=True, logit_scale=scale, hw_shape=hw_shape).reshape(B, C, hw)
+    assert float((got - ref).abs().max()) <= 4e-3 * scale
+    # and the legacy two-kernel route agrees within the bf16 rounding of v_hat
+    legacy, _, _ = ops.cosine_logits_fwd(v.to(DEV), t_hat, C, hw_shape, True, scale)
+    assert float((legacy.reshape(B, C, hw).cpu() - got).abs().max()) <= 4e-3 * scale
+
+
+@pytest.mark.parametrize("B,hw,C", [(2, 256, 151), (1, 1024, 150), (2, 200, 19), (1, 256, 847)])
+def test_backward_raw_v(B, hw, C):
+    """LC2IS_BWD_RAW_V: both backward GEMMs on the raw V (the bf16 operand is G * inv||v||, the normalise-backward sits in
+    the dV epilogue) against the fp32 autograd oracle and against the v_hat route."""
+    D = 512
+    g = torch.Generator().manual_seed(33)
+    v = synthetic.make_patch_embeddings(B, hw, D, dtype=torch.bfloat16)
+    t = synthetic.make_prototypes(C, D)
+    h = int(hw ** 0.5); hw_shape = (h, hw // h) if h * (hw // h) == hw else (1, hw)
+    G = torch.randn(B, C, *hw_shape, generator=g) * 1e-3
+    gv_ref, gt_ref = O.cosine_logits_backward(v.float(), t, G, normalize=True)
+    t_hat, inv_t = ops.proto_normalize(t.to(DEV), True)
+    vd, Gd = v.to(DEV), G.to(DEV)
+    logits, _, inv_v = ops.cosine_logits_fwd(vd, t_hat, C, hw_shape, True, 1.0, fuse_norm=True)
+    gv, gt = ops.cosine_logits_bwd(Gd, logits, vd, inv_v, t_hat, inv_t, C, raw_v=True)
+    ev = float((gv.cpu() - gv_ref).abs().max() / gv_ref.abs().max())
+    et = float((gt[0].cpu() - gt_ref).abs().max() / gt_ref.abs().max())
+    assert ev < 2e-2 and et < 2e-2, (ev, et)
+    logits2, v_hat, inv_v2 = ops.cosine_logits_fwd(vd, t_hat, C, hw_shape, True, 1.0)
+    gv2, gt2 = ops.cosine_logits_bwd(Gd, logits2, v_hat, inv_v2, t_hat, inv_t, C)
+    assert float((gv - gv2).abs().max()) <= 2e-2 * float(gv2.abs().max())
+    assert float((gt - gt2).abs().max()) <= 2e-2 * float(gt2.abs().max())
