@@ -235,6 +235,19 @@ int lc2is_argmax_confmat_lowres_packed(const float* d_low, int N, int C, int h, 
                                        int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                        lc2is_stream_t stream);
 
+/* RAGGED batch in one launch: image i of d_low [N,C,h,w] is resized (bilinear / bicubic, ATen's
+ * `size=` scale in/out) to ITS OWN H_i x W_i, argmaxed and compared with its own ground truth.  Replaces the per-image
+ * Python loops of compute_gt_mIOU (metrics.py:61-79) and generate_masks (utils.py:15-22).
+ * d_desc    [N][4] int64: { element offset of image i in d_labels / d_pred, H_i, W_i, first tile of image i } with
+ *           first tile = running sum of lc2is_ragged_tiles(H_j, W_j), j < i; n_tiles = the total.
+ * d_labels  flat int64 (image i: H_i*W_i elements at its offset) or NULL (masks only); targets outside [0,C) are skipped.
+ * d_confmat [C,C] / d_per_image [N,3,C] ACCUMULATED or NULL; d_pred flat int64 out (same offsets) or NULL. */
+long long lc2is_ragged_tiles(int H, int W);
+int lc2is_argmax_confmat_ragged(const float* d_low, int N, int C, int h, int w, int mode,
+                                const int64_t* d_desc, long long n_tiles, const int64_t* d_labels,
+                                int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
+                                lc2is_stream_t stream);
+
 /* K2 (split form) and K3 in ONE warp-specialised kernel for the x16 geometry (what the whole-step entries run when
  * lc2is_ce_argmax_fused_supported): the taps are staged once per 16 groups, four warps of a CTA run the
  * cross-entropy strips (FP32-pipe bound), four the argmax rows (ALU / issue bound).  Same results as

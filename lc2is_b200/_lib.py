@@ -61,6 +61,8 @@ SIGNATURES = {
     "lc2is_argmax_confmat_lowres": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, _p, c_int,
                                             c_int, _p, _p, _p, _p]),
     "lc2is_argmax_confmat_lowres_packed": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, _p, _p, _p]),
+    "lc2is_ragged_tiles": (c_int64, [c_int, c_int]),
+    "lc2is_argmax_confmat_ragged": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, _p, c_int64, _p, _p, _p, _p, _p]),
     "lc2is_ce_argmax_fused_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "lc2is_ce_argmax_fused_packed": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, _p, _p, c_int, _p, _p, _p, _p, _p]),
     "lc2is_pack_labels": (c_int, [_p, c_int64, c_int, c_int64, _p, _p, _p]),

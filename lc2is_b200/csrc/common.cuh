@@ -97,4 +97,20 @@ __device__ __forceinline__ float lg2f(float x) {
     return y;
 }
 
+// ---- interpolation weights (torch ATen/native/UpSample.h) ---------------------------------------
+// bicubic: A = -0.75, src = scale*(dst+0.5)-0.5 NOT clamped, taps floor(src)-1..+2 index-clamped
+// (UpSample.h:398-438, upsample_get_value_bounded).  bilinear: src clamped to >= 0
+// (UpSample.h:289-312), taps idx0, min(idx0+1, in-1).
+__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
+__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+    const float A = -0.75f;
+    c[0] = cubic2(t + 1.f, A);
+    c[1] = cubic1(t, A);
+    c[2] = cubic1(1.f - t, A);
+    c[3] = cubic2(2.f - t, A);
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+
 }  // namespace lc2is

@@ -201,22 +201,6 @@ k3_full_kernel(const T* __restrict__ logits, int N, int C, int H, int W,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Interpolation weights (torch ATen/native/UpSample.h).
-// bicubic: A = -0.75, src = scale*(dst+0.5)-0.5 NOT clamped, taps floor(src)-1..+2 index-clamped
-// (UpSample.h:398-438, upsample_get_value_bounded).  bilinear: src clamped to >= 0
-// (UpSample.h:289-312), taps idx0, min(idx0+1, in-1).
-__device__ __forceinline__ float cubic1(float x, float A) { return ((A + 2.f) * x - (A + 3.f)) * x * x + 1.f; }
-__device__ __forceinline__ float cubic2(float x, float A) { return ((A * x - 5.f * A) * x + 8.f * A) * x - 4.f * A; }
-__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
-    const float A = -0.75f;
-    c[0] = cubic2(t + 1.f, A);
-    c[1] = cubic1(t, A);
-    c[2] = cubic1(1.f - t, A);
-    c[3] = cubic2(2.f - t, A);
-}
-__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
-
-// ---------------------------------------------------------------------------------------------
 // k3_low_fast: power-of-two scale s in {4, 8, 16}.  Same geometry as K2 (k2_upsample_ce.cu): a GROUP is
 // the bps x bps (bps = s/4) 4x4-pixel blocks that share one set of taps; one thread owns one block.
 // The CTA stages the index-clamped source cells of its 32 x 64 pixel tile in shared memory once
@@ -228,36 +212,6 @@ __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? l
 // Non-finite taps (inf / NaN) send the warp down the per-pixel path that reproduces
 // argmax(softmax(x)) = 0 for poisoned pixels.  Counts go to global memory with warp-aggregated
 // (match.any) 64-bit atomics: a 32 x 64 tile holds few distinct (target, prediction) pairs.
-__device__ __forceinline__ unsigned long long pk2f(float x, float y) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
-    return r;
-}
-__device__ __forceinline__ float2 up2f(unsigned long long r) {
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
-    return d;
-}
-__device__ __forceinline__ float2 fadd2f(float2 a, float2 b) {
-    unsigned long long d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2f(a.x, a.y)), "l"(pk2f(b.x, b.y)));
-    return up2f(d);
-}
-__device__ __forceinline__ float2 fmul2f(float2 a, float2 b) {
-    unsigned long long d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk2f(a.x, a.y)), "l"(pk2f(b.x, b.y)));
-    return up2f(d);
-}
-__device__ __forceinline__ float2 ffma2f(float2 a, float2 b, float2 c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk2f(a.x, a.y)), "l"(pk2f(b.x, b.y)), "l"(pk2f(c.x, c.y)));
-    return up2f(d);
-}
-__device__ __forceinline__ void cp_async4_k3(void* smem, const void* gmem) {
-    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem));
-}
-
 struct K3LowParams {
     const float* low;
     const long long* labels;
@@ -294,7 +248,7 @@ k3_low_fast_kernel(const K3LowParams P) {
         const int c = idx / cs, r = idx - c * cs;
         const int i = r / ncx, j = r - i * ncx;
         const int gy = clampi(cy0 + i, 0, P.h - 1), gx = clampi(cx0 + j, 0, P.w - 1);
-        cp_async4_k3(st + idx, lowb + ((size_t)c * P.h + gy) * P.w + gx);
+        cp_async4(st + idx, lowb + ((size_t)c * P.h + gy) * P.w + gx);
     }
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
     __syncthreads();
@@ -346,14 +300,14 @@ k3_low_fast_kernel(const K3LowParams P) {
                 const float Tv = dd * rs * rs;                  // growth of the column step per row
                 float2 v01 = make_float2(l00, l00 + Pv), s01 = make_float2(Q0, Q0 + Tv);
                 const float2 P2 = make_float2(Pv + Pv, Pv + Pv), T2 = make_float2(Tv + Tv, Tv + Tv);
-                float2 v23 = fadd2f(v01, P2), s23 = fadd2f(s01, T2);
+                float2 v23 = fadd2(v01, P2), s23 = fadd2(s01, T2);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     am_upd(best[0 * 4 + j], bidx[0 * 4 + j], v01.x, c);
                     am_upd(best[1 * 4 + j], bidx[1 * 4 + j], v01.y, c);
                     am_upd(best[2 * 4 + j], bidx[2 * 4 + j], v23.x, c);
                     am_upd(best[3 * 4 + j], bidx[3 * 4 + j], v23.y, c);
-                    if (j < 3) { v01 = fadd2f(v01, s01); v23 = fadd2f(v23, s23); }
+                    if (j < 3) { v01 = fadd2(v01, s01); v23 = fadd2(v23, s23); }
                 }
             }
         } else {
@@ -381,20 +335,20 @@ k3_low_fast_kernel(const K3LowParams P) {
                     const float t0 = p[a * ncx], t1 = p[a * ncx + 1], t2 = p[a * ncx + 2], t3 = p[a * ncx + 3];
 #pragma unroll
                     for (int jp = 0; jp < 2; ++jp) {
-                        float2 acc = fmul2f(make_float2(t0, t0), wxp[jp][0]);
-                        acc = ffma2f(make_float2(t1, t1), wxp[jp][1], acc);
-                        acc = ffma2f(make_float2(t2, t2), wxp[jp][2], acc);
-                        hr[a][jp] = ffma2f(make_float2(t3, t3), wxp[jp][3], acc);
+                        float2 acc = fmul2(make_float2(t0, t0), wxp[jp][0]);
+                        acc = ffma2(make_float2(t1, t1), wxp[jp][1], acc);
+                        acc = ffma2(make_float2(t2, t2), wxp[jp][2], acc);
+                        hr[a][jp] = ffma2(make_float2(t3, t3), wxp[jp][3], acc);
                     }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int jp = 0; jp < 2; ++jp) {
-                        float2 acc = fmul2f(hr[0][jp], make_float2(wy[i][0], wy[i][0]));
-                        acc = ffma2f(hr[1][jp], make_float2(wy[i][1], wy[i][1]), acc);
-                        acc = ffma2f(hr[2][jp], make_float2(wy[i][2], wy[i][2]), acc);
-                        acc = ffma2f(hr[3][jp], make_float2(wy[i][3], wy[i][3]), acc);
+                        float2 acc = fmul2(hr[0][jp], make_float2(wy[i][0], wy[i][0]));
+                        acc = ffma2(hr[1][jp], make_float2(wy[i][1], wy[i][1]), acc);
+                        acc = ffma2(hr[2][jp], make_float2(wy[i][2], wy[i][2]), acc);
+                        acc = ffma2(hr[3][jp], make_float2(wy[i][3], wy[i][3]), acc);
                         am_upd(best[i * 4 + jp * 2], bidx[i * 4 + jp * 2], acc.x, c);
                         am_upd(best[i * 4 + jp * 2 + 1], bidx[i * 4 + jp * 2 + 1], acc.y, c);
                     }
@@ -605,7 +559,7 @@ __device__ __forceinline__ void k3_strip_rows(const K3SParams& P, const float4* 
                 const float2 vb0 = make_float2(fmaf(rlb, lx0, Lb), fmaf(rlb, lx0, Lb)), db = make_float2(rlb * rsx, rlb * rsx);
 #pragma unroll
                 for (int jj = 0; jj < S / 2; ++jj) {
-                    const float2 va = ffma2f(J2[jj], da, va0), vb = ffma2f(J2[jj], db, vb0);
+                    const float2 va = ffma2(J2[jj], da, va0), vb = ffma2(J2[jj], db, vb0);
                     cm[2 * jj] = fmaxf(fmaxf(va.x, vb.x), cm[2 * jj]);
                     cm[2 * jj + 1] = fmaxf(fmaxf(va.y, vb.y), cm[2 * jj + 1]);
                 }
@@ -716,7 +670,7 @@ k3_strip_kernel(const K3SParams P) {
         const float* src = P.low + (size_t)n * C * plane + (size_t)yy * P.w + xx;
         float* dst = st + r;
         for (int c = lane / CS; c < C; c += CSTEP) {
-            if (ok) cp_async4_k3(dst + c * CS, src + (size_t)c * plane);
+            if (ok) cp_async4(dst + c * CS, src + (size_t)c * plane);
             else dst[c * CS] = 0.f;
         }
         for (int c = C + lane / CS; c < C + CH; c += CSTEP) dst[c * CS] = -3.0e38f;    // padding never wins

@@ -90,14 +90,21 @@ def compute_mIOU(outputs: Tensor, labels: Tensor, n_cls: int, ignore_index: Opti
 
 def compute_gt_mIOU(outputs: Tensor, gt_list: List[Tensor], sizes: Tensor, n_cls: int = 151,
                     ignore_index: Optional[int] = 0) -> dict:
-    """metrics.py:61-79: bicubic to each image's ORIGINAL size against ragged ground truth."""
+    """metrics.py:61-79: bicubic to each image's ORIGINAL size against ragged ground truth.  ONE launch per chunk of
+    images (lc2is_argmax_confmat_ragged over a descriptor table) instead of one resize + metric call per image."""
     dev = _device()
+    N = len(gt_list)
+    C, h, w = outputs.shape[1:]
+    if C != n_cls:
+        raise ValueError(f"outputs have {C} classes, n_cls={n_cls}")
+    step = max(1, _CHUNK_BYTES // (C * h * w * 4))
     mious = []
-    for i in range(len(gt_list)):
-        H, W = (int(x) for x in sizes[i])
-        o = _to_dev(outputs[i:i + 1], dev, torch.float32)
-        g = _to_dev(gt_list[i].reshape(1, H, W), dev, torch.int64)
-        _, pi, _ = ops.argmax_confmat(o, g, per_image=True, size=(H, W), mode="bicubic")
+    for i in range(0, N, step):
+        j = min(N, i + step)
+        sz = [(int(sizes[k][0]), int(sizes[k][1])) for k in range(i, j)]
+        flat = torch.cat([gt_list[k].reshape(-1).to(torch.int64) for k in range(i, j)])
+        _, pi, _, _ = ops.argmax_confmat_ragged(_to_dev(outputs[i:j], dev, torch.float32), sz,
+                                                _to_dev(flat, dev, torch.int64), mode="bicubic")
         mious.append(_per_image_miou(pi, ignore_index))
     return dict(mIOU_gt=torch.concat(mious).mean().item())
 

@@ -232,6 +232,43 @@ def argmax_confmat_packed(low: Tensor, labels_packed: Tensor, size: Tuple[int, i
     return confmat, pi, pred
 
 
+def ragged_descriptors(sizes) -> Tuple[Tensor, int, int]:
+    """The descriptor table of lc2is_argmax_confmat_ragged for images of sizes [(H_i, W_i)]: int64 [N,4] rows
+    {element offset, H, W, first tile} (a CPU tensor), the total number of tiles and of elements."""
+    rows, off, tile = [], 0, 0
+    for H, W in sizes:
+        H, W = int(H), int(W)
+        rows.append((off, H, W, tile))
+        off += H * W
+        tile += int(lib.lc2is_ragged_tiles(H, W))
+    return torch.tensor(rows, dtype=torch.int64).reshape(-1, 4), tile, off
+
+
+def argmax_confmat_ragged(low: Tensor, sizes, labels_flat: Optional[Tensor] = None, mode: str = "bicubic",
+                          confmat: Optional[Tensor] = None, per_image: bool = True, want_pred: bool = False):
+    """ONE launch for a ragged batch: low [N,C,h,w] fp32 (CUDA); image i is resized to sizes[i] = (H_i, W_i), argmaxed
+    and compared with labels_flat (int64, the images' label maps flattened and concatenated; None = masks only).
+    -> (confmat | None, per_image int64 [N,3,C] | None, pred_flat int64 | None, desc (CPU int64 [N,4]))."""
+    low = _req(low, torch.float32, "low")
+    N, C, h, w = low.shape
+    desc, n_tiles, n_elem = ragged_descriptors(sizes)
+    if desc.shape[0] != N:
+        raise _lib.Lc2isError("one size per image")
+    dev = low.device
+    d_desc = desc.to(dev, non_blocking=True)
+    if labels_flat is not None:
+        labels_flat = _req(labels_flat, torch.int64, "labels_flat")
+        if labels_flat.numel() != n_elem:
+            raise _lib.Lc2isError(f"labels_flat has {labels_flat.numel()} elements, the sizes add up to {n_elem}")
+    else:
+        per_image, confmat = False, None
+    pi = torch.zeros(N, 3, C, dtype=torch.int64, device=dev) if per_image else None
+    pred = torch.empty(n_elem, dtype=torch.int64, device=dev) if want_pred else None
+    check(lib.lc2is_argmax_confmat_ragged(ptr(low), N, C, h, w, _MODE[mode], ptr(d_desc), n_tiles, ptr(labels_flat),
+                                          ptr(confmat), ptr(pi), ptr(pred), stream_ptr()), "lc2is_argmax_confmat_ragged")
+    return confmat, pi, pred, desc
+
+
 def pack_labels(labels: Tensor, C: int, ignore_index: int, n_valid: Optional[Tensor] = None):
     """int64 labels -> (packed uint16 of the same shape, n_valid int64[1] accumulated)."""
     labels = _req(labels, torch.int64, "labels")

@@ -8,16 +8,14 @@ from . import ops
 
 def generate_masks(preds: torch.Tensor, sizes: torch.Tensor) -> List[torch.Tensor]:
     """utils.py:15-22: bicubic to each image's original size, then argmax(dim=0) -> int64 [H_i,W_i].
-    Runs K3's fused resize+argmax (the confusion matrix it also produces is discarded)."""
+    One launch of the ragged resize+argmax kernel for the whole batch (lc2is_argmax_confmat_ragged)."""
     dev = torch.device("cuda", torch.cuda.current_device())
-    masks = []
-    for pred, size in zip(preds, sizes):
-        H, W = (int(x) for x in size)
-        o = pred.unsqueeze(0).to(dev, torch.float32).contiguous()
-        dummy = torch.zeros(1, 1, 1, dtype=torch.int64, device=dev)
-        _, _, m = ops.argmax_confmat(o, dummy, want_pred=True, size=(H, W), mode="bicubic")
-        masks.append(m[0])
-    return masks
+    if isinstance(preds, (list, tuple)):
+        preds = torch.stack(list(preds))
+    sz = [(int(s[0]), int(s[1])) for s in sizes]
+    low = preds.to(dev, torch.float32).contiguous()
+    _, _, flat, desc = ops.argmax_confmat_ragged(low, sz, None, mode="bicubic", want_pred=True)
+    return [flat[int(o):int(o) + H * W].view(H, W) for (o, H, W, _), (H, W) in zip(desc.tolist(), sz)]
 
 
 def count_params(model: torch.nn.Module, trainable: bool = False):

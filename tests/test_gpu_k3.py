@@ -333,3 +333,68 @@ def test_bf16_dominant_class_does_not_overflow_the_16bit_counters():
     ref = torch.zeros(C, C, dtype=torch.int64)
     ref[1, 2] = N * H * H
     assert torch.equal(cm.cpu(), ref)
+
+
+# ---- ragged batch in one launch (lc2is_argmax_confmat_ragged; metrics.py:61-79, utils.py:15-22) -----------------------
+def _ragged_case(N, C, h, sizes, seed, nonfinite=False):
+    g = torch.Generator().manual_seed(seed)
+    low = torch.randn(N, C, h, h, generator=g)
+    if nonfinite:
+        low[0, 3, 2, 5] = float("inf")
+        low[1, 0, h - 1, 0] = float("nan")
+        low[1, 4, 0, h - 1] = float("-inf")
+    gt = [torch.randint(0, C, (a, b), generator=g) for a, b in sizes]
+    gt[0][0, :3] = C + 5                                     # targets outside [0, C) are skipped
+    return low, gt
+
+
+@pytest.mark.parametrize("mode", ["bicubic", "bilinear"])
+@pytest.mark.parametrize("nonfinite", [False, True])
+def test_ragged_kernel_equals_the_per_image_kernel(mode, nonfinite):
+    """One launch over the descriptor table == one lc2is_argmax_confmat_lowres call per image (k3_low_gen_kernel, the
+    per-pixel ATen-order chains), bit for bit: masks, per-image counts and the confusion matrix.  Sizes: enlarged >= 3x
+    (5-wide window), 1.5x - 3x (6-wide window), shrunk / barely enlarged (exact per-pixel path), single pixels, sizes
+    that are not multiples of the 4 x 4 blocks or the 64 x 32 tiles."""
+    C, h = 23, 16
+    sizes = [(64, 64), (71, 50), (37, 90), (24, 31), (17, 19), (16, 16), (9, 7), (1, 1), (130, 67), (48, 3)]
+    N = len(sizes)
+    low, gt = _ragged_case(N, C, h, sizes, 11, nonfinite)
+    flat = torch.cat([t.reshape(-1) for t in gt])
+    cm = torch.zeros(C, C, dtype=torch.int64, device=DEV)
+    _, pi, pred, desc = ops.argmax_confmat_ragged(low.to(DEV), sizes, flat.to(DEV), mode=mode, confmat=cm, want_pred=True)
+    cm_ref = torch.zeros(C, C, dtype=torch.int64, device=DEV)
+    for i, (H, W) in enumerate(sizes):
+        _, pi_i, pred_i = ops.argmax_confmat(low[i:i + 1].to(DEV), gt[i].view(1, H, W).to(DEV), confmat=cm_ref,
+                                             per_image=True, want_pred=True, size=(H, W), mode=mode)
+        o = int(desc[i, 0])
+        assert torch.equal(pred[o:o + H * W].view(H, W), pred_i[0]), (i, H, W)
+        assert torch.equal(pi[i], pi_i[0]), (i, H, W)
+    assert torch.equal(cm, cm_ref)
+    assert int(cm.sum()) == sum(a * b for a, b in sizes) - 3
+
+
+def test_ragged_kernel_vs_oracle_tie_safe_and_miou():
+    """Against the reference lines on CPU (oracle): masks agree wherever the top-2 gap exceeds the fp32 evaluation-order
+    noise, and compute_gt_mIOU / generate_masks through the mirror give the oracle's numbers."""
+    C, h = 151, 32
+    sizes = [(128, 128), (171, 96), (100, 133), (97, 255)]
+    low, gt = _ragged_case(len(sizes), C, h, sizes, 5)
+    for t in gt:
+        t.clamp_(max=C - 1)
+    masks = utils.generate_masks(low, torch.tensor(sizes))
+    for i, (H, W) in enumerate(sizes):
+        up = F.interpolate(low[i:i + 1], mode="bicubic", size=(H, W))
+        safe = _safe_mask(up, 1e-4)[0]
+        assert safe.float().mean() > 0.99
+        assert torch.equal(masks[i].cpu()[safe], O.argmax_reference(up)[0][safe])
+    ref = O.compute_gt_mIOU(low, gt, sizes, n_cls=C, ignore_index=0)["mIOU_gt"]
+    got = metrics.compute_gt_mIOU(low, gt, torch.tensor(sizes), n_cls=C, ignore_index=0)["mIOU_gt"]
+    assert abs(got - ref) < 2e-4                              # a handful of near-tie pixels out of 80 k
+
+
+def test_ragged_entry_rejects_bad_arguments():
+    low = torch.zeros(1, 3, 4, 4, device=DEV)
+    with pytest.raises(Exception):
+        ops.argmax_confmat_ragged(low, [(8, 8), (4, 4)], None, want_pred=True)          # one size per image
+    with pytest.raises(Exception):
+        ops.argmax_confmat_ragged(low, [(8, 8)], torch.zeros(3, dtype=torch.int64, device=DEV))   # label count

@@ -29,13 +29,13 @@ for r in rr[2:]:
     traffic[nm] = int(float(r[ir]) * mul[units[ir]] + float(r[iw]) * mul[units[iw]])
 summ = subprocess.run([sys.executable, "tools/ncu_summary.py", rep], capture_output=True, text=True).stdout
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-kern = None; h2 = None; data = {}
+kern = None; h2 = None; data = {}; hdrs = {}
 for r in csv.reader(src.splitlines()):
     if r and r[0] == "Kernel Name": kern = r[1]; data[kern] = []; continue
-    if r and r[0] == "Address": h2 = r; continue
+    if r and r[0] == "Address": h2 = r; hdrs[kern] = r; continue
     if h2 and len(r) == len(h2) and kern: data[kern].append(r)
-ix = {k: i for i, k in enumerate(h2)}
-def opmix(d):
+def opmix(d, h2):
+    ix = {k: i for i, k in enumerate(h2)}          # (the column set differs from kernel to kernel)
     ti = sum(int(r[ix["Instructions Executed"]]) for r in d); o = {}
     for r in d:
         t = r[ix["Source"]].split(); op = t[1] if t and t[0].startswith("@") else (t[0] if t else "?")
@@ -55,7 +55,7 @@ for blk in summ.split("-" * 60):
     dk = [k for k in data if k.split("(")[0].split("::")[-1].split("<")[0] in kn][0]
     open(f"profiles/{tag}_{key[0]}_ncu_full.txt", "w").write(
         f"# {tag} {key[0]}: ncu --set full --clock-control none --import-source on (one launch inside the step: "
-        f"`python tools/run_one.py step A 16`, cfg2 G-A B=16 C=150)\n\n## metrics\n{blk.strip()}\n\n## executed SASS opcodes\n{opmix(data[dk])}\n")
+        f"`python tools/run_one.py step A 16`, cfg2 G-A B=16 C=150)\n\n## metrics\n{blk.strip()}\n\n## executed SASS opcodes\n{opmix(data[dk], hdrs[dk])}\n")
 try: tj = json.load(open("profiles/traffic.json"))
 except Exception: tj = {}
 tj["note"] = "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, cfg2 G-A B=16 C=150 (profiles/*_ncu_full.txt)"
