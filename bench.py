@@ -345,22 +345,29 @@ def run_b200(a):
         step(dev_sets[i % nset][0], t_dev, dev_sets[i % nset][1])
     torch.cuda.synchronize()
     graphs, graph_err = None, None
-    if world > 1:
-        # NCCL collectives captured into a CUDA graph hung ProcessGroupNCCL's watchdog on this stack (torch 2.11 /
-        # NCCL 2.28, 2 ranks): the data-parallel runs time eager launches
-        graph_err = "not attempted with a process group (captured NCCL collectives hung the NCCL watchdog)"
+    if world > 1 and (step.comm is None or os.environ.get("LC2IS_DP_GRAPH") == "0"):
+        # torch.distributed's NCCL collectives captured into a CUDA graph hung ProcessGroupNCCL's watchdog on this stack
+        # (torch 2.11 / NCCL 2.28): without the direct ncclAllReduce route the data-parallel runs time eager launches
+        graph_err = "not attempted (collectives through torch.distributed are not captured)"
     elif not a.no_graph:
         state = (step._cur, step._pending)
         try:
             graphs = [step.capture(dev_sets[i][0], t_dev, dev_sets[i][1]) for i in range(nset)]
             torch.cuda.synchronize()
             assert (step._cur, step._pending) == state
-            for i in range(nset):                             # one untimed replay of every graph
-                graphs[i]()
-            torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
             graphs, graph_err = None, repr(e)[:300]
             step._cur, step._pending = state
+            torch.cuda.synchronize()
+        if world > 1:                                         # all ranks replay graphs, or none does
+            ok = torch.tensor([1 if graphs is not None else 0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok) == 0 and graphs is not None:
+                graphs, graph_err = None, "capture failed on another rank"
+                step._cur, step._pending = state
+        if graphs is not None:
+            for i in range(nset):                             # one untimed replay of every graph
+                graphs[i]()
             torch.cuda.synchronize()
 
     def one_step(i):
@@ -589,6 +596,7 @@ def run_b200(a):
 
     if rank != 0:
         if world > 1:
+            torch.cuda.synchronize()
             dist.destroy_process_group()
         return
 

@@ -40,6 +40,7 @@ namespace lc2is {
 constexpr int RC_S = 16;                 // scale
 constexpr int RC_CH = 8;                 // classes per argmax chunk (even)
 constexpr int RC_USTRIDE = 16 * 16 + 16; // floats per group in the U tile (+16: the two groups land in different banks)
+constexpr int RC_CTR_SLOTS = 64;         // job-counter pairs (see launch_k23_rc)
 constexpr float RC_PAD = -1.0e30f;       // padding classes: exp -> 0, never the argmax
 // column indices of a pixel pair, (2k, 2k+1): constant-bank operands of the packed fma that evaluates the row
 __constant__ float2 RC_J2[RC_S / 2] = {{0.f, 1.f}, {2.f, 3.f}, {4.f, 5.f}, {6.f, 7.f}, {8.f, 9.f}, {10.f, 11.f}, {12.f, 13.f}, {14.f, 15.f}};
@@ -59,6 +60,7 @@ struct RCParams {
     int jpr;                         // jobs per group row = ceil((w + 1) / 2)
     int use_tma;
     long long njobs;
+    unsigned* ctr;                   // {next job of the dynamic rounds, finished warps}: zero at launch, reset by the last warp
     unsigned cells_bytes;            // shared memory per warp: TMA landing zone (later the U tile), multiple of 128
     unsigned quads_bytes;            // shared memory per warp: quads + mbarrier
 };
@@ -210,11 +212,20 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
-    // jobs are dealt to the warps SM-first (consecutive jobs go to different SMs): the last, partial round of jobs then
-    // thins out every SM's warps evenly instead of leaving whole SMs idle (the SMs are throughput-bound, not the warps)
+    // The first job of every warp is dealt statically, SM-first (consecutive jobs go to different SMs); every further job
+    // is taken from a global counter when the warp STARTS its current job (the box of the next job is issued at its end):
+    // a CTA that starts late - an NCCL kernel of the data-parallel step holding its SM - or runs slowly just takes fewer
+    // jobs instead of stretching the kernel's tail (static dealing cost 33 us per step at 2 GPUs).  The last warp to
+    // finish resets the counter pair for the next launch.
     const long long gw = (long long)warp * gridDim.x + blockIdx.x;
     const long long gstride = (long long)gridDim.x * nwarps;
-    if (gw >= P.njobs) return;                              // whole warp; there is no CTA barrier below
+    auto retire = [&]() {
+        if (lane == 0 && atomicAdd(P.ctr + 1, 1u) == (unsigned)gstride - 1u) {
+            P.ctr[0] = 0u;
+            P.ctr[1] = 0u;
+        }
+    };
+    if (gw >= P.njobs) { retire(); return; }                // whole warp; there is no CTA barrier below
 
     const int C = P.C, CP = P.CP;
     // all landing zones first (each a multiple of 128 bytes, the alignment TMA wants), then the per-warp rest
@@ -243,8 +254,14 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
     const int gi = lane >> 4, i = lane & 15;
     const float ly = ((float)i + 0.5f) * RS;
 
+    long long next_job = 0;
 #pragma unroll 1
-    for (long long job = gw; job < P.njobs; job += gstride) {
+    for (long long job = gw; job < P.njobs; job = next_job) {
+        {
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(P.ctr, 1u);
+            next_job = gstride + (long long)__shfl_sync(0xffffffffu, t, 0);
+        }
         const RCJob J = rc_decode(P, job);
         const int n = J.n, ky = J.ky, kx0 = J.kx0;
         // ---- wait for the taps -----------------------------------------------------------------------------
@@ -689,11 +706,12 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
         }
         __syncwarp();                                       // quads / U free for the next job
         // ---- the box of the warp's next job (its latency is covered by the SM's other warps) -----------------------
-        if (job + gstride < P.njobs) {
-            const RCJob Jn = rc_decode(P, job + gstride);
+        if (next_job < P.njobs) {
+            const RCJob Jn = rc_decode(P, next_job);
             rc_stage(P, &tm, cells, bar, Jn, lane);
         }
     }
+    retire();
 }
 
 // ---- host: 4-D fp32 tensor map of the low-resolution logits, cached per (pointer, shape) ---------------------------
@@ -771,10 +789,16 @@ int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, in
     const size_t smem = ((size_t)P.cells_bytes + P.quads_bytes) * nw;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
+    static unsigned* ctr_pool = nullptr;                    // RC_CTR_SLOTS self-resetting counter pairs, used round-robin
     std::call_once(once, [] {
         attr_err = cudaFuncSetAttribute(k23_rc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess) attr_err = cudaMalloc(&ctr_pool, RC_CTR_SLOTS * 2 * sizeof(unsigned));
+        if (attr_err == cudaSuccess) attr_err = cudaMemset(ctr_pool, 0, RC_CTR_SLOTS * 2 * sizeof(unsigned));
     });
-    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "cudaFuncSetAttribute(k23_rc_kernel)");
+    if (attr_err != cudaSuccess) return cuda_fail(attr_err, "k23_rc_kernel set-up (shared-memory attribute / job counters)");
+    // launches in flight at the same time (different streams) must not share a pair: 64 pairs in rotation
+    static std::atomic<unsigned> seq{0};
+    P.ctr = ctr_pool + 2 * (seq.fetch_add(1, std::memory_order_relaxed) % RC_CTR_SLOTS);
     long long ctas = (P.njobs + nw - 1) / nw;
     if (ctas > sm_count()) ctas = sm_count();
     k23_rc_kernel<16><<<(unsigned)ctas, nw * 32, smem, st>>>(tm, P);

@@ -10,6 +10,7 @@ Used by bench.py and usable as the data-parallel engine shim.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -43,6 +44,16 @@ class _Block:
         self.n_valid = self.scalars[8:16].view(torch.int64)
         self.gscale = self.scalars[16:20].view(torch.float32)
         self.loss = self.scalars[20:24].view(torch.float32)
+
+
+class _Join:
+    """`wait()`: the current stream waits for everything enqueued on the exchange stream so far (no host sync)."""
+
+    def __init__(self, stream):
+        self.stream = stream
+
+    def wait(self):
+        torch.cuda.current_stream().wait_stream(self.stream)
 
 
 class HeadStep:
@@ -95,6 +106,14 @@ class HeadStep:
         self.extra = [torch.zeros(extra_bucket_floats, dtype=torch.float32, device=dev) for _ in range(2)] \
             if extra_bucket_floats else None
         self._pending = None           # block whose bucket has not been all-reduced yet (distributed only)
+        # the exchange steps go through ncclAllReduce on a stream of their own, forked / joined with events: plain
+        # stream-ordered launches that overlap the head kernels and can be captured into the step's CUDA graph
+        # (LC2IS_DP_TORCH_NCCL=1: torch.distributed's process group instead - not capturable on this stack)
+        self.comm = None
+        if self.distributed and os.environ.get("LC2IS_DP_TORCH_NCCL") != "1":
+            from . import nccl
+            self.comm = nccl.default_comm(dev)
+        self._xs = torch.cuda.Stream(device=dev) if self.comm is not None else None
         self.confmat = torch.zeros(C, C, dtype=torch.int64, device=dev)        # this rank's counts, accumulated
         self._confmat_global = torch.zeros(C, C, dtype=torch.int64, device=dev) if self.distributed else None
         nbytes = int(lib.lc2is_cosine_logits_bwd_workspace(B, self.hw, D, 1, C))
@@ -108,7 +127,14 @@ class HeadStep:
     def _blk(self) -> _Block:
         return self._blocks[self._cur]
 
-    loss = property(lambda self: self._blk.loss)
+    @property
+    def loss(self) -> torch.Tensor:
+        """Mean loss of the most recent call (data-parallel: over the GLOBAL batch, valid after flush())."""
+        blk = self._blk
+        if self.distributed:
+            return (blk.bucket.views[1] / blk.n_valid).reshape(1)       # all-reduced loss sum / all-reduced count
+        return blk.loss
+
     n_valid = property(lambda self: self._blk.n_valid)
     grad_t = property(lambda self: self._blk.grad_t)
     grad_low = property(lambda self: self._blk.grad_low)
@@ -134,22 +160,33 @@ class HeadStep:
         if not self.distributed:
             return self.confmat
         self._confmat_global.copy_(self.confmat)
-        dp.allreduce_confmat_(self._confmat_global)
+        if self.comm is not None:
+            self.comm.all_reduce_(self._confmat_global)
+        else:
+            dp.allreduce_confmat_(self._confmat_global)
         return self._confmat_global
+
+    def _allreduce_async(self, *tensors):
+        """SUM all-reduce of the tensors, asynchronous to the current stream; -> objects with .wait()."""
+        if self.comm is None:
+            return [dp.allreduce_sum_async(t) for t in tensors]
+        self._xs.wait_stream(torch.cuda.current_stream())
+        if len(tensors) == 1:
+            self.comm.all_reduce_(tensors[0], self._xs)
+        else:
+            self.comm.all_reduce_many_(tensors, self._xs)
+        return [_Join(self._xs)]
 
     # ---- data-parallel exchange of a finished block ------------------------------------------------------------
     def _start_exchange(self, k: int):
         """All-reduce block k's gradient bucket (+ the upstream gradients riding with it) asynchronously."""
-        works = [dp.allreduce_sum_async(self._blocks[k].bucket.flat)]
         if self.extra is not None:
-            works.append(dp.allreduce_sum_async(self.extra[k]))
-        return works
+            return self._allreduce_async(self._blocks[k].bucket.flat, self.extra[k])
+        return self._allreduce_async(self._blocks[k].bucket.flat)
 
     def _finish_exchange(self, k: int, works) -> None:
         for wk in works:
             wk.wait()                                             # stream-level wait, no host sync
-        blk = self._blocks[k]
-        blk.loss.copy_(blk.bucket.views[1] / blk.n_valid)
 
     def flush(self) -> None:
         """Complete the most recent call: all-reduce its gradient bucket (distributed only; enqueued, no host sync)."""
@@ -158,27 +195,51 @@ class HeadStep:
             self._finish_exchange(k, self._start_exchange(k))
 
     def capture(self, v: torch.Tensor, t: torch.Tensor, labels: torch.Tensor):
-        """Record ``self(v, t, labels)`` for the NEXT accumulator block into a CUDA graph; returns ``replay()``.
+        """Record ``self(v, t, labels)`` for the NEXT accumulator block into CUDA graphs; returns ``replay()``.
         The tensors' addresses are baked in (refill them in place).  Graphs alternate blocks like eager calls do, so
-        capture one per (input set, block) in the order they will be replayed and replay them in that order."""
+        capture one per (input set, block) in the order they will be replayed and replay them in that order.
+
+        Single GPU: the whole call is ONE graph.  Data-parallel: the kernels between the exchange steps are three graphs
+        (labels | logits + CE/argmax | backward) and the two ncclAllReduce launches stay eager on the exchange stream -
+        a single graph holding the NCCL nodes and their cross-stream edges took as long to LAUNCH as the step takes to run
+        (0.37 ms of host time per replay against 0.004 ms for the kernel-only graph)."""
         assert self.timers is None and self.k2_events is None, "no event timers inside a captured step"
         k = self._cur ^ 1
         pending = self._pending
-        g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
-                self._enqueue(v, t, labels, k, pending)
-        torch.cuda.current_stream().wait_stream(side)
+
+        def record(fn):
+            g = torch.cuda.CUDAGraph()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                    fn()
+            torch.cuda.current_stream().wait_stream(side)
+            return g
+        if not self.distributed:
+            graphs = [record(lambda: self._enqueue(v, t, labels, k, pending))]
+        else:
+            graphs = [record(lambda: self._part_labels(labels, k)), record(lambda: self._part_forward(v, t, labels, k)),
+                      record(lambda: self._part_backward(v, labels, k))]
         # capturing does not execute: leave the bookkeeping as if the call had not happened
         nxt_pending = k if self.distributed else None
 
         def replay():
             assert self._cur == (k ^ 1) and self._pending == pending, "replay graphs in the order they were captured"
-            g.replay()
+            if not self.distributed:
+                graphs[0].replay()
+            else:
+                graphs[0].replay()
+                w_valid = self._allreduce_async(self._blocks[k].n_valid)
+                works_prev = self._start_exchange(pending) if pending is not None else None
+                graphs[1].replay()
+                for wk in w_valid:
+                    wk.wait()
+                graphs[2].replay()
+                if works_prev is not None:
+                    self._finish_exchange(pending, works_prev)
             self._cur, self._pending = k, nxt_pending
-        replay.graph = g
+        replay.graphs = graphs
         replay.block = k
         # the graphs of a rotation are captured back to back: advance the bookkeeping so that the next capture
         # records the other block (and this block's pending exchange)
@@ -194,12 +255,27 @@ class HeadStep:
         self._pending = k if self.distributed else None
 
     def _enqueue(self, v, t, labels, k: int, pending) -> None:
-        st = stream_ptr()
-        B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
-        dist_on = self.distributed
-        blk = self._blocks[k]
-        # the previous call's bucket goes out first: its all-reduce runs on NCCL's stream next to this whole call
+        # exchange stream: this call's valid count first (K1b needs it; 8 bytes), then the previous call's gradient bucket -
+        # both run next to K0 / K1 and are done before the fused kernel has taken every SM's registers (an NCCL kernel
+        # that is launched later than that only starts when the fused kernel ends, and is then exposed)
+        self._part_labels(labels, k)
+        w_valid = self._allreduce_async(self._blocks[k].n_valid) if self.distributed else None
         works_prev = self._start_exchange(pending) if pending is not None else None
+        self._part_forward(v, t, labels, k)
+        self._mark("K1b backward")
+        if w_valid is not None:
+            for wk in w_valid:
+                wk.wait()                                         # stream-level wait, no host sync
+        self._part_backward(v, labels, k)
+        if works_prev is not None:
+            self._finish_exchange(pending, works_prev)
+        self._mark(None)
+
+    def _part_labels(self, labels, k: int) -> None:
+        """zero-fill of block k + everything that depends on the labels only (packing, valid count)."""
+        st = stream_ptr()
+        B, C, h, w, H, W = self.B, self.C, self.h, self.w, self.H, self.W
+        blk = self._blocks[k]
         self._mark("zero-fill")
         blk.acc32.zero_()                                        # bucket, grad_low, scalars: one fill
         glow = ptr(blk.grad_low) if self.backward else None
@@ -216,11 +292,20 @@ class HeadStep:
         else:
             check(lib.lc2is_count_valid(ptr(labels), labels.numel(), C, self.ignore_index, ptr(blk.n_valid), st),
                   "count_valid")
-        w_valid = dp.allreduce_sum_async(blk.n_valid) if dist_on else None
+
+    def _fuse(self, v) -> bool:
+        return self.fuse_norm and v.dtype == torch.bfloat16
+
+    def _part_forward(self, v, t, labels, k: int) -> None:
+        """K0 -> K1 -> K2 (+ K3 in the same kernel at x16)."""
+        st = stream_ptr()
+        B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
+        blk = self._blocks[k]
+        glow = ptr(blk.grad_low) if self.backward else None
         self._mark("K0+K1 logits")
         check(lib.lc2is_proto_normalize(ptr(t), 1, C, D, int(self.normalize), ptr(self.t_hat), ptr(self.inv_t), st),
               "proto_normalize")
-        fuse = self.fuse_norm and v.dtype == torch.bfloat16
+        fuse = self._fuse(v)
         if not fuse and self.v_hat is None:
             self.v_hat = torch.empty(B * hw, D, dtype=torch.bfloat16, device=v.device)
         check(lib.lc2is_cosine_logits_fwd(ptr(v), BF16 if v.dtype == torch.bfloat16 else F32, B, hw, D,
@@ -242,9 +327,13 @@ class HeadStep:
                                                 None, ptr(blk.loss_sum), glow, None, st), "upsample_ce_fwd_bwd")
         if self.k2_events is not None:
             self.k2_events[1].record()
-        self._mark("K1b backward")
-        if w_valid is not None:
-            w_valid.wait()                                        # stream-level wait, no host sync
+
+    def _part_backward(self, v, labels, k: int) -> None:
+        """1 / N_valid -> K1b -> K3 (where it is a separate kernel) -> the loss."""
+        st = stream_ptr()
+        B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
+        blk = self._blocks[k]
+        fuse = self._fuse(v)
         check(lib.lc2is_mean_scale(ptr(blk.n_valid), 1.0, ptr(blk.gscale), st), "mean_scale")
         if self.backward:
             check(lib.lc2is_cosine_logits_bwd_ex(ptr(blk.grad_low), F32, ptr(self.logits),
@@ -264,13 +353,10 @@ class HeadStep:
             check(lib.lc2is_argmax_confmat_lowres(ptr(self.logits), B, C, h, w, H, W, BILINEAR, ptr(labels), H, W,
                                                   ptr(self.confmat), None, None, st), "argmax_confmat_lowres")
         self._mark("finalize")
-        if dist_on:
+        if self.distributed:
             blk.bucket.views[1].copy_(blk.loss_sum)              # fp32 copy of the loss sum rides in the bucket
-            if works_prev is not None:
-                self._finish_exchange(pending, works_prev)
         else:
             check(lib.lc2is_finalize_loss(ptr(blk.loss_sum), ptr(blk.n_valid), ptr(blk.loss), st), "finalize_loss")
-        self._mark(None)
 
 
 class HostStep:
