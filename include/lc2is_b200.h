@@ -88,6 +88,17 @@ int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int hw, int D,
 int lc2is_linear_fwd(const void* d_x_bf16, const void* d_w_bf16, const float* d_bias,
                      long long M, int N, int K, void* d_y, int y_dtype, lc2is_stream_t stream);
 
+/* Backward of the same projection (autograd of model/text_patch.py:12,17; y = x W^T + b), all on tcgen05:
+ *   d_gx [M,K] (gx_dtype) = gy . W      lc2is_linear_fwd's pipeline on the transposed weight (built in d_ws)
+ *   d_gw [N,K] fp32      += gy^T . x    split-K over the rows, both operands MN-major, fp32 L2 reductions (ACCUMULATES:
+ *                                       zero it, or let several micro-batches add up like autograd does)
+ *   d_gb [N]   fp32      += column sums of gy
+ * gy [M,N], x [M,K], W [N,K] bf16; N and K multiples of 64.  Any of d_gx / d_gw / d_gb may be NULL.
+ * d_ws: lc2is_linear_bwd_workspace(N, K) bytes (the transposed weight for d_gx, the split-K partial sums for d_gw). */
+int64_t lc2is_linear_bwd_workspace(int N, int K);
+int lc2is_linear_bwd(const void* d_gy_bf16, const void* d_x_bf16, const void* d_w_bf16, long long M, int N, int K,
+                     void* d_gx, int gx_dtype, float* d_gw, float* d_gb, void* d_ws, lc2is_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * K1b cosine_logits_bwd.  Replaces autograd of the K1 lines (loss.backward(), engine.py:100).
  * d_grad_logits: dL/dlogits, g_dtype LC2IS_BF16: [B, C_pad, hw] bf16 (rows C..C_pad-1 zero; K2's

@@ -369,12 +369,18 @@ constexpr int DT_BM = 128, DT_KB = 64;
 constexpr int DT_A_BYTES = 2 * DT_KB * 128;           // 2 boxes [64 p][64 d] = 16 KB
 constexpr int DT_MAX_STAGES = 8;
 
+// B_MN = false: B = G [b][class][pixel], K-major (the prototype gradient).  B_MN = true: B = a row-major [rows][N] matrix,
+// i.e. MN-major like A (the weight gradient of TextToPatch.visual: dW^T tile = X^T . Gy, lc2is_linear_bwd).
+// MT = number of 128-row M tiles per CTA (accumulators side by side in TMEM; MT = 2 halves the L2 traffic of B per flop -
+// the split-K weight gradient is L2-bound).  STORE: the partial tile is written with plain stores to slice `ks` of a
+// [ksplit][C][D] workspace (summed by reduce_partials_kernel) instead of fp32 reductions into dt_raw.
+template <bool B_MN, int MT, bool STORE>
 __global__ void __launch_bounds__(KB_THREADS, 1)
 k1b_dt_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmG, const DtParams P) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base_u32 = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* smem = smem_raw + (base_u32 - tc::smem_u32(smem_raw));
-    const int stage_bytes = DT_A_BYTES + P.NB * 128;
+    const int stage_bytes = MT * DT_A_BYTES + P.NB * 128;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
     uint64_t* empty = full + DT_MAX_STAGES;
     uint64_t* tfull = empty + DT_MAX_STAGES;
@@ -400,7 +406,7 @@ k1b_dt_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
         tc::mbar_init(tfull, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 1) tc::tmem_alloc(tmem_ptr, 256);
+    if (warp == 1) tc::tmem_alloc(tmem_ptr, MT * 256);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -417,28 +423,38 @@ k1b_dt_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
                     tc::mbar_arrive_expect_tx(full + stage, (uint32_t)stage_bytes);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j)   // A: Vhat[b*hw + kl*64 .. +64][dt*128 + j*64 .. +64]
-                        tc::tma_load_2d(sa + j * DT_KB * 128, &tmV, full + stage, dt * DT_BM + j * 64,
+                    for (int j = 0; j < 2 * MT; ++j)   // A: Vhat[b*hw + kl*64 .. +64][dt*128*MT + j*64 .. +64]
+                        tc::tma_load_2d(sa + j * DT_KB * 128, &tmV, full + stage, dt * DT_BM * MT + j * 64,
                                         b * P.hw + kl * DT_KB);
-                    // B: G[b][nt*NB .. +NB][kl*64 .. +64]   (K-major; OOB pixels / classes read as 0)
-                    tc::tma_load_3d(sa + DT_A_BYTES, &tmG, full + stage, kl * DT_KB, nt * P.NB, b);
+                    if (B_MN) {                   // B: Gy[b*hw + kl*64 .. +64][nt*NB + j*64 .. +64], boxes [64 k][64 n]
+                        for (int j = 0; j < P.NB / 64; ++j)
+                            tc::tma_load_2d(sa + MT * DT_A_BYTES + j * DT_KB * 128, &tmG, full + stage, nt * P.NB + j * 64,
+                                            b * P.hw + kl * DT_KB);
+                    } else {
+                        // B: G[b][nt*NB .. +NB][kl*64 .. +64]   (K-major; OOB pixels / classes read as 0)
+                        tc::tma_load_3d(sa + MT * DT_A_BYTES, &tmG, full + stage, kl * DT_KB, nt * P.NB, b);
+                    }
                     if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
             }
         } else if (warp == 1) {
             if (lane == 0) {
-                const uint32_t idesc = tc::make_idesc_bf16(DT_BM, P.NB, 1, 0);
+                const uint32_t idesc = tc::make_idesc_bf16(DT_BM, P.NB, 1, B_MN ? 1 : 0);
                 int stage = 0; uint32_t phase = 0;
                 for (int kb = kb_lo; kb < kb_hi; ++kb) {
                     tc::mbar_wait(full + stage, phase);
                     tc::tc_fence_after();
                     const uint32_t sa = base_u32 + stage * stage_bytes;
-                    const uint64_t adesc = tc::make_smem_desc(sa, DT_KB * 128, 1024);        // MN-major A
-                    const uint64_t bdesc = tc::make_smem_desc(sa + DT_A_BYTES, 16, 1024);    // K-major B
+                    const uint64_t bdesc = B_MN ? tc::make_smem_desc(sa + MT * DT_A_BYTES, DT_KB * 128, 1024)   // MN-major B
+                                                : tc::make_smem_desc(sa + MT * DT_A_BYTES, 16, 1024);           // K-major B
 #pragma unroll
-                    for (int k = 0; k < DT_KB / 16; ++k)   // A: +16 K-rows = 2 atoms = 2048 B; B: +32 B
-                        tc::umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(2 * k), idesc,
-                                      (kb != kb_lo) || (k != 0));
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint64_t adesc = tc::make_smem_desc(sa + mt * DT_A_BYTES, DT_KB * 128, 1024);   // MN-major A
+#pragma unroll
+                        for (int k = 0; k < DT_KB / 16; ++k)   // MN-major: +16 K-rows = 2 atoms = 2048 B; K-major B: +32 B
+                            tc::umma_bf16(tmem_base + (uint32_t)(mt * P.NB), adesc + (uint64_t)(k * 128),
+                                          bdesc + (uint64_t)(B_MN ? k * 128 : 2 * k), idesc, (kb != kb_lo) || (k != 0));
+                    }
                     tc::umma_commit(empty + stage);
                     if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
@@ -446,21 +462,27 @@ k1b_dt_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
             }
         } else {
             const int q = warp & 3;
-            const int d = dt * DT_BM + q * 32 + lane;
             tc::mbar_wait(tfull, 0);
             tc::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-            float* out = P.dt_raw + (size_t)set * P.C * P.D + d;
             const int c0 = nt * P.NB;
-            for (int col = 0; col < P.NB; col += 16) {
-                if (c0 + col >= P.C) break;
-                uint32_t acc[16];
-                tc::tmem_ld16(taddr + col, acc);
-                tc::tmem_ld_wait();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const int d = (dt * MT + mt) * DT_BM + q * 32 + lane;
+                const uint32_t taddr = tmem_base + (uint32_t)(mt * P.NB) + ((uint32_t)(q * 32) << 16);
+                float* out = P.dt_raw + (size_t)(STORE ? ks : set) * P.C * P.D + d;
+                for (int col = 0; col < P.NB; col += 16) {
+                    if (c0 + col >= P.C) break;
+                    uint32_t acc[16];
+                    tc::tmem_ld16(taddr + col, acc);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = c0 + col + j;
-                    if (c < P.C && d < P.D) atomicAdd(out + (size_t)c * P.D, __uint_as_float(acc[j]));
+                    for (int j = 0; j < 16; ++j) {
+                        const int c = c0 + col + j;
+                        if (c < P.C && d < P.D) {
+                            if (STORE) out[(size_t)c * P.D] = __uint_as_float(acc[j]);     // lanes: consecutive d
+                            else atomicAdd(out + (size_t)c * P.D, __uint_as_float(acc[j]));
+                        }
+                    }
                 }
             }
         }
@@ -469,7 +491,20 @@ k1b_dt_kernel(const __grid_constant__ CUtensorMap tmV, const __grid_constant__ C
     __syncthreads();
     if (warp == 1) {
         tc::tc_fence_after();
-        tc::tmem_dealloc(tmem_base, 256);
+        tc::tmem_dealloc(tmem_base, MT * 256);
+    }
+}
+
+// out[i] += sum_s part[s][i]   (the split-K slices of the weight gradient)
+__global__ void __launch_bounds__(256)
+reduce_partials_kernel(const float4* __restrict__ part, int nslices, long long n4, float4* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = out[i];
+        for (int s = 0; s < nslices; ++s) {
+            const float4 v = __ldcs(part + (size_t)s * n4 + i);
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        }
+        out[i] = a;
     }
 }
 
@@ -493,6 +528,90 @@ k1b_dt_finish_kernel(const float* __restrict__ dt_raw, const float* __restrict__
             v = (v - th * rt[(size_t)set * C + c]) * inv_t[(size_t)set * C + c];
         }
         grad_t[i] += gs * v;
+    }
+}
+
+// ---- TextToPatch.visual backward helpers ---------------------------------------------------------------------------
+// W [N][K] -> Wt [K][N] (bf16): the weight in the layout lc2is_linear_fwd wants for gx = gy . W
+__global__ void __launch_bounds__(256)
+transpose_bf16_kernel(const __nv_bfloat16* __restrict__ in, int N, int K, __nv_bfloat16* __restrict__ out) {
+    __shared__ __nv_bfloat16 tile[32][33];
+    const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8)
+        if (n0 + r < N && k0 + tx < K) tile[r][tx] = in[(size_t)(n0 + r) * K + k0 + tx];
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8)
+        if (k0 + r < K && n0 + tx < N) out[(size_t)(k0 + r) * N + n0 + tx] = tile[tx][r];
+}
+// part[cta][n] = sum over the CTA's rows of gy[m][n]: a pure HBM stream (16-byte loads, eight columns per thread, eight
+// loads in flight); colsum_finish_kernel adds the CTAs' partial sums to gb (same-address reductions from ~600 CTAs
+// serialise in L2: 107 us for 268 MB with atomics)
+constexpr int CS_THREADS = 1024;                           // 2 CTAs per SM: latency is hidden by warps, not by unrolling
+__global__ void __launch_bounds__(CS_THREADS)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ gy, long long M, int N, float* __restrict__ part) {
+    const int nvec = N / 8;                                   // N % 8 == 0
+    const int tpr = nvec < CS_THREADS ? nvec : CS_THREADS;                  // threads that own a column group in this CTA's pass
+    const int rows_per_pass = CS_THREADS / tpr;
+    const int cg = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
+    for (int v0 = 0; v0 < nvec; v0 += tpr) {
+        const int vcol = v0 + cg;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (vcol < nvec && rsub < rows_per_pass)
+        {
+            const long long stride = (long long)gridDim.x * rows_per_pass;
+            const uint4* src = reinterpret_cast<const uint4*>(gy) + vcol;
+            const size_t rowv = (size_t)N / 8;                 // 16-byte vectors per row
+            auto add = [&](const uint4 q) {
+                const unsigned wd[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[2 * i] += __uint_as_float(wd[i] << 16);
+                    acc[2 * i + 1] += __uint_as_float(wd[i] & 0xffff0000u);
+                }
+            };
+            long long m0 = (long long)blockIdx.x * rows_per_pass + rsub;
+            for (; m0 + 7 * stride < M; m0 += 8 * stride) {   // eight unconditional 16-byte loads in flight per thread
+                uint4 q[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) q[u] = __ldcs(src + (size_t)(m0 + u * stride) * rowv);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) add(q[u]);
+            }
+            for (; m0 < M; m0 += stride) add(__ldcs(src + (size_t)m0 * rowv));
+        }
+        // the CTA's row groups are summed in shared memory first: one reduction per column and CTA
+        __shared__ float red[CS_THREADS][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+        __syncthreads();
+        if (vcol < nvec && rsub == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float t = 0.f;
+                for (int r = 0; r < rows_per_pass; ++r) t += red[r * tpr + cg][i];
+                part[(size_t)blockIdx.x * N + vcol * 8 + i] = t;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_finish_kernel(const float* __restrict__ part, int nparts, int N, float* __restrict__ gb) {
+    // 32 columns per CTA, the partial sums split eight ways (a thread that walked all of them alone was latency-bound)
+    __shared__ float red[8][32];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.x * 32 + tx;
+    float t = 0.f;
+    if (n < N)
+        for (int b = ty; b < nparts; b += 8) t += part[(size_t)b * N + n];
+    red[ty][tx] = t;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+#pragma unroll
+        for (int r = 1; r < 8; ++r) t += red[r][tx];
+        gb[n] += t;
     }
 }
 
@@ -614,8 +733,8 @@ extern "C" int lc2is_cosine_logits_bwd_ex(const void* d_grad_logits, int g_dtype
         if (int e = make_tmap_3d_bf16(&tmG, d_grad_logits_bf16, B, C_pad, hw, P.NB, 64)) return e;
         size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
         if (smem < 120 * 1024) smem = 120 * 1024;
-        LC2IS_CUDA(cudaFuncSetAttribute(k1b_dt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k1b_dt_kernel<<<base_items * ksplit, KB_THREADS, smem, st>>>(tmV, tmG, P);
+        LC2IS_CUDA(cudaFuncSetAttribute(k1b_dt_kernel<false, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1b_dt_kernel<false, 1, false><<<base_items * ksplit, KB_THREADS, smem, st>>>(tmV, tmG, P);
         LC2IS_CHECK_LAUNCH("k1b_dt_kernel");
         long long total = (long long)n_sets * C * D;
         long long blocks = (total + 255) / 256;
@@ -638,4 +757,87 @@ extern "C" int lc2is_cosine_logits_bwd(const void* d_grad_logits, int g_dtype, c
     return lc2is_cosine_logits_bwd_ex(d_grad_logits, g_dtype, d_logits, d_v_hat, d_inv_norm_v, d_t_hat, d_inv_norm_t, B, hw,
                                       D, n_sets, C, normalize, logit_scale, d_grad_scale, d_grad_v, gv_dtype, d_grad_t,
                                       d_ws, stream, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TextToPatch.visual backward (autograd of model/text_patch.py:12,17; y = x W^T + b):
+//   gx [M,K]  = gy [M,N] . W [N,K]       lc2is_linear_fwd's tcgen05 pipeline on the transposed weight (workspace)
+//   gw [N,K] += gy^T . x                  tcgen05 split-K over the rows, both operands MN-major, fp32 L2 reductions
+//   gb [N]   += column sums of gy
+constexpr int LINEAR_BWD_MAX_COLSUM_CTAS = 1024;            // per-CTA partial column sums of gy (workspace bound)
+constexpr int LINEAR_BWD_MAX_SLICES = 32;                  // split-K slices of the weight gradient (workspace bound)
+extern "C" int64_t lc2is_linear_bwd_workspace(int N, int K) {
+    // the transposed bf16 weight (gx) + LINEAR_BWD_MAX_SLICES fp32 partial weight gradients (gw)
+    return ((int64_t)N * K * 2 + 255) / 256 * 256 + (int64_t)LINEAR_BWD_MAX_SLICES * N * K * 4 +
+           (int64_t)LINEAR_BWD_MAX_COLSUM_CTAS * N * 4;
+}
+
+extern "C" int lc2is_linear_bwd(const void* d_gy_bf16, const void* d_x_bf16, const void* d_w_bf16, long long M, int N,
+                                int K, void* d_gx, int gx_dtype, float* d_gw, float* d_gb, void* d_ws,
+                                lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (M < 0 || N <= 0 || K <= 0) return fail(LC2IS_ERR_SHAPE, "bad shape%s");
+    if (N % 64 || K % 64) return fail(LC2IS_ERR_SHAPE, "N and K must be multiples of 64%s");
+    if (M > 0x7fffffffLL / 2) return fail(LC2IS_ERR_SHAPE, "M too large%s");
+    if (!d_gy_bf16) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    if (M == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_gx) {
+        if (!d_w_bf16 || !d_ws) return fail(LC2IS_ERR_ARG, "gx needs the weight and the workspace%s");
+        dim3 grid((K + 31) / 32, (N + 31) / 32);
+        transpose_bf16_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)d_w_bf16, N, K, (__nv_bfloat16*)d_ws);
+        LC2IS_CHECK_LAUNCH("transpose_bf16_kernel");
+        // gx[m][k] = sum_n gy[m][n] Wt[k][n]: "x" = gy (inner size N), "W" = Wt [K out][N in]
+        if (int e = lc2is_linear_fwd(d_gy_bf16, d_ws, nullptr, M, K, N, d_gx, gx_dtype, stream)) return e;
+    }
+    if (d_gw) {
+        if (!d_x_bf16 || !d_ws) return fail(LC2IS_ERR_ARG, "gw needs x and the workspace%s");
+        // out[n][k] += sum_m gy[m][n] x[m][k]: A = x (M side = the K input features, 256 per CTA), B = gy (N side);
+        // every CTA stores its partial tile into slice ks of the workspace, reduce_partials_kernel adds the slices to gw
+        DtParams P;
+        float* part = reinterpret_cast<float*>(static_cast<uint8_t*>(d_ws) + ((size_t)N * K * 2 + 255) / 256 * 256);
+        P.dt_raw = part; P.B = 1; P.hw = (int)M; P.D = K; P.C = N; P.C_pad = N; P.n_sets = 1;
+        P.NB = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : 64);
+        P.n_ntiles = N / P.NB;
+        P.n_dtiles = (K + 2 * DT_BM - 1) / (2 * DT_BM);
+        P.kb_per_img = (int)((M + DT_KB - 1) / DT_KB);
+        const int base_items = P.n_dtiles * P.n_ntiles;
+        int ksplit = sm_count() / base_items;
+        if (ksplit < 1) ksplit = 1;
+        if (ksplit > P.kb_per_img) ksplit = P.kb_per_img;
+        if (ksplit > LINEAR_BWD_MAX_SLICES) ksplit = LINEAR_BWD_MAX_SLICES;
+        P.ksplit = ksplit;
+        const int stage_bytes = 2 * DT_A_BYTES + P.NB * 128;
+        int stages = (200 * 1024) / stage_bytes;
+        if (stages > DT_MAX_STAGES) stages = DT_MAX_STAGES;
+        P.stages = stages;
+        CUtensorMap tmX, tmGy;
+        if (int e = make_tmap_2d_bf16(&tmX, d_x_bf16, (uint64_t)M, K, DT_KB, 64)) return e;
+        if (int e = make_tmap_2d_bf16(&tmGy, d_gy_bf16, (uint64_t)M, N, DT_KB, 64)) return e;
+        size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+        if (smem < 120 * 1024) smem = 120 * 1024;
+        LC2IS_CUDA(cudaFuncSetAttribute(k1b_dt_kernel<true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k1b_dt_kernel<true, 2, true><<<base_items * ksplit, KB_THREADS, smem, st>>>(tmX, tmGy, P);
+        LC2IS_CHECK_LAUNCH("k1b_dt_kernel<linear dW>");
+        const long long n4 = (long long)N * K / 4;
+        long long blocks = (n4 + 255) / 256;
+        if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+        reduce_partials_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(part), ksplit, n4,
+                                                                 reinterpret_cast<float4*>(d_gw));
+        LC2IS_CHECK_LAUNCH("reduce_partials_kernel");
+    }
+    if (d_gb) {
+        if (!d_ws) return fail(LC2IS_ERR_ARG, "gb needs the workspace%s");
+        if (N % 8) return fail(LC2IS_ERR_SHAPE, "N must be a multiple of 8%s");
+        float* cpart = reinterpret_cast<float*>(static_cast<uint8_t*>(d_ws) + ((size_t)N * K * 2 + 255) / 256 * 256 +
+                                                (size_t)LINEAR_BWD_MAX_SLICES * N * K * 4);
+        long long blocks = (M + 255) / 256;
+        if (blocks > sm_count() * 2) blocks = sm_count() * 2;
+        if (blocks > LINEAR_BWD_MAX_COLSUM_CTAS) blocks = LINEAR_BWD_MAX_COLSUM_CTAS;
+        colsum_bf16_kernel<<<(unsigned)blocks, CS_THREADS, 0, st>>>((const __nv_bfloat16*)d_gy_bf16, M, N, cpart);
+        LC2IS_CHECK_LAUNCH("colsum_bf16_kernel");
+        colsum_finish_kernel<<<(N + 31) / 32, 256, 0, st>>>(cpart, (int)blocks, N, d_gb);
+        LC2IS_CHECK_LAUNCH("colsum_finish_kernel");
+    }
+    return 0;
 }

@@ -58,6 +58,28 @@ def linear_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, out_dty
     return y
 
 
+def linear_bwd(gy: Tensor, x: Tensor, weight: Tensor, need_gx: bool = True, need_gw: bool = True, need_gb: bool = True,
+               gx_dtype=torch.bfloat16, gw: Optional[Tensor] = None, gb: Optional[Tensor] = None):
+    """Backward of y = x W^T + b on tcgen05 (lc2is_linear_bwd).  gy [M,N], x [M,K], weight [N,K]: bf16.
+    -> (gx [M,K] gx_dtype | None, gw fp32 [N,K] | None, gb fp32 [N] | None); `gw` / `gb` given: accumulated into."""
+    gy = _req(gy, torch.bfloat16, "gy")
+    x = _req(x, torch.bfloat16, "x")
+    weight = _req(weight, torch.bfloat16, "weight")
+    M, N = gy.shape
+    K = x.shape[1]
+    dev = gy.device
+    gx = torch.empty(M, K, dtype=gx_dtype, device=dev) if need_gx else None
+    if need_gw and gw is None:
+        gw = torch.zeros(N, K, dtype=torch.float32, device=dev)
+    if need_gb and gb is None:
+        gb = torch.zeros(N, dtype=torch.float32, device=dev)
+    ws = torch.empty(int(lib.lc2is_linear_bwd_workspace(N, K)), dtype=torch.uint8, device=dev)
+    check(lib.lc2is_linear_bwd(ptr(gy), ptr(x), ptr(weight), M, N, K, ptr(gx), _dt(gx) if need_gx else 0,
+                               ptr(gw) if need_gw else None, ptr(gb) if need_gb else None, ptr(ws), stream_ptr()),
+          "lc2is_linear_bwd")
+    return gx, (gw if need_gw else None), (gb if need_gb else None)
+
+
 # ---- K1 -----------------------------------------------------------------------------------
 def cosine_logits_fwd(v: Tensor, t_hat: Tensor, C: int, hw_shape: Tuple[int, int], normalize: bool = True,
                       logit_scale: float = 1.0, fuse_norm: bool = False) -> Tuple[Tensor, Optional[Tensor], Tensor]:

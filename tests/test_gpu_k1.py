@@ -176,10 +176,10 @@ def test_linear_projection_gemm_two_sm_form(M, K, N, out_dtype):
 
 def test_text_to_patch_module_matches_reference_module(golden_dir):
     """TextToPatch (model/text_patch.py:4-18) with the reference's weights: same parameter names, text first, visual
-    projection forward on the tcgen05 GEMM, gradients through torch."""
+    projection forward AND backward on the tcgen05 GEMMs (bf16 operands, fp32 accumulation, fp32 weight gradient)."""
     from lc2is_b200.model.text_patch import TextToPatch
     torch.manual_seed(3)
-    m = TextToPatch(768, 512, 512).to(DEV)
+    m = TextToPatch(768, 512, 512, tensor_cores=True).to(DEV)
     assert sorted(k for k, _ in m.named_parameters()) == ["textual.bias", "textual.weight", "visual.bias", "visual.weight"]
     img = torch.randn(2, 64, 768, device=DEV, requires_grad=True)
     text = torch.randn(151, 512, device=DEV)
@@ -191,6 +191,46 @@ def test_text_to_patch_module_matches_reference_module(golden_dir):
     ref_g = torch.autograd.grad(ref_v.square().mean(), [img, m.visual.weight, m.visual.bias])
     for got, ref in ((img.grad, ref_g[0]), (m.visual.weight.grad, ref_g[1]), (m.visual.bias.grad, ref_g[2])):
         assert float((got - ref).abs().max()) <= 3e-2 * float(ref.abs().max())
+    assert m.visual.weight.grad.dtype == torch.float32
+    # fp32 inputs without the opt-in keep nn.Linear's fp32 arithmetic; bf16 inputs take the tensor-core path
+    m32 = TextToPatch(768, 512, 512).to(DEV)
+    m32.load_state_dict(m.state_dict())
+    _, v32 = m32(img.detach(), text)
+    assert torch.equal(v32, torch.nn.functional.linear(img.detach(), m.visual.weight, m.visual.bias))
+    _, vb = m32(img.detach().to(torch.bfloat16), text)
+    assert vb.dtype == torch.bfloat16 and float((vb.float() - ref_v).abs().max()) <= 3e-2 * float(ref_v.abs().max())
+
+
+@pytest.mark.parametrize("M,K,N,gx_dtype", [(300, 768, 512, torch.bfloat16), (4096, 768, 512, torch.float32),
+                                              (129, 64, 64, torch.float32), (5000, 384, 192, torch.bfloat16),
+                                              (32768, 768, 512, torch.bfloat16), (70000, 128, 256, torch.float32)])
+def test_linear_projection_backward(M, K, N, gx_dtype):
+    """lc2is_linear_bwd (autograd of text_patch.py:12,17): dX, dW, db against fp32 matmuls of the same bf16-rounded
+    operands (accumulation order / split-K reduction order only).  Tolerances: dX 2e-5 (fp32 out) or 2^-7 (bf16 out)
+    of max|dX|; dW and db 2e-5 of their maxima (fp32 accumulation over up to 70000 rows)."""
+    g = torch.Generator(device=DEV).manual_seed(21)
+    x = torch.randn(M, K, generator=g, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, generator=g, device=DEV) * K ** -0.5).to(torch.bfloat16)
+    gy = torch.randn(M, N, generator=g, device=DEV).to(torch.bfloat16)
+    gx, gw, gb = ops.linear_bwd(gy, x, w, gx_dtype=gx_dtype)
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref_gx = gy.float() @ w.float()
+        ref_gw = gy.double().t() @ x.double()
+        ref_gb = gy.double().sum(0)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    tol = 2e-5 if gx_dtype == torch.float32 else 1.0 / 128
+    assert float((gx.float() - ref_gx).abs().max()) <= tol * float(ref_gx.abs().max())
+    assert gw.dtype == torch.float32 and float((gw.double() - ref_gw).abs().max()) <= 2e-5 * float(ref_gw.abs().max())
+    assert float((gb.double() - ref_gb).abs().max()) <= 2e-5 * float(ref_gb.abs().max())
+    # accumulation into caller-owned buffers (two micro-batches) and partial requests
+    gw2, gb2 = gw.clone(), gb.clone()
+    out = ops.linear_bwd(gy, x, w, need_gx=False, gw=gw2, gb=gb2)
+    assert out[0] is None
+    assert float((gw2.double() - 2 * ref_gw).abs().max()) <= 4e-5 * float(ref_gw.abs().max())
+    assert float((gb2.double() - 2 * ref_gb).abs().max()) <= 4e-5 * float(ref_gb.abs().max())
 
 
 @pytest.mark.parametrize("B,hw,C,scale", [
