@@ -48,6 +48,7 @@ def parse():
     p.add_argument("--kernel-times", action="store_true", help="extra pass: per-section CUDA-event times (not the timed run)")
     p.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     p.add_argument("--no-secondary", action="store_true", help="skip the cfg3 / G-B / cfg4 / cfg5 legs")
+    p.add_argument("--legs", default="cfg3_eval,G-B,cfg4,cfg5", help="comma-separated secondary legs to run")
     return p.parse_args()
 
 
@@ -587,6 +588,8 @@ def run_b200(a):
             ("cfg5", lambda: _step_leg("cfg5 open-vocabulary stress", "5", 8, 847, world, rank, dev, dist, steps=5, warmup=2)),
         ]
         for name, fn in legs:
+            if name not in a.legs.split(","):
+                continue
             try:
                 secondary[name] = fn()
             except Exception as e:  # noqa: BLE001

@@ -37,10 +37,6 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
         if backend == "nccl":
             torch.cuda.set_device(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # every message of this path is small (8 B valid count, 0.3 - 3 MB gradient bucket, 180 kB confusion matrix): two
-        # channels = two CTAs per collective are enough and leave the SMs to the head kernels (measured at 2 GPUs:
-        # 0.369 -> 0.360 ms per step)
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         kwargs = {}
         if backend == "nccl":
             kwargs["device_id"] = torch.device("cuda", local_rank)

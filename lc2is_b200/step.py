@@ -47,13 +47,15 @@ class _Block:
 
 
 class _Join:
-    """`wait()`: the current stream waits for everything enqueued on the exchange stream so far (no host sync)."""
+    """`wait()`: the current stream waits for what was enqueued on the exchange stream UP TO the creation of this object
+    (an event recorded there) - not for collectives issued later on the same stream (no host sync)."""
 
     def __init__(self, stream):
-        self.stream = stream
+        self.event = torch.cuda.Event()
+        self.event.record(stream)
 
     def wait(self):
-        torch.cuda.current_stream().wait_stream(self.stream)
+        torch.cuda.current_stream().wait_event(self.event)
 
 
 class HeadStep:
