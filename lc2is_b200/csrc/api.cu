@@ -56,7 +56,7 @@ __global__ void finalize_loss_kernel(const double* loss_sum, const long long* n_
 using namespace lc2is;
 
 extern "C" const char* lc2is_last_error(void) { return g_err; }
-extern "C" int lc2is_abi_version(void) { return 4; }
+extern "C" int lc2is_abi_version(void) { return 5; }
 extern "C" int64_t lc2is_launch_count(void) { return g_launches.load(); }
 
 extern "C" int lc2is_mean_scale(const int64_t* d_n_valid, float mult, float* d_scale, lc2is_stream_t stream) {

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/lc2is_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == syms, "ctypes SIGNATURES out of sync with the header"
-    assert lib.lc2is_abi_version() == 4
+    assert lib.lc2is_abi_version() == 5
 
 
 def test_class_pad():
