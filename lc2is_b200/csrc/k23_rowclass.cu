@@ -114,7 +114,9 @@ __device__ __forceinline__ void rc_stage(const RCParams& P, const CUtensorMap* t
     }
 }
 
-template <int S>
+// COLS: the labels / predictions of a job are handled by a sweep over the 16 pixel COLUMNS (match.any over the 32 rows)
+// instead of per-row run loops (LC2IS_RC_RUNS=1 selects the run loops).
+template <int S, bool COLS>
 __global__ void __launch_bounds__(512, 1)
 k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RCParams P) {
     static_assert(S == 16, "x16 geometry");
@@ -128,15 +130,15 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
     // a CTA that starts late - an NCCL kernel of the data-parallel step holding its SM - or runs slowly just takes fewer
     // jobs instead of stretching the kernel's tail (static dealing cost 33 us per step at 2 GPUs).  The last warp to
     // finish resets the counter pair for the next launch.
-    const long long gw = (long long)warp * gridDim.x + blockIdx.x;
-    const long long gstride = (long long)gridDim.x * nwarps;
+    const int gw = warp * (int)gridDim.x + (int)blockIdx.x;                   // (njobs < 2^31: checked at launch)
+    const int gstride = (int)gridDim.x * nwarps;
     auto retire = [&]() {
         if (lane == 0 && atomicAdd(P.ctr + 1, 1u) == (unsigned)gstride - 1u) {
             P.ctr[0] = 0u;
             P.ctr[1] = 0u;
         }
     };
-    if (gw >= P.njobs) { retire(); return; }                // whole warp; there is no CTA barrier below
+    if (gw >= (int)P.njobs) { retire(); return; }                // whole warp; there is no CTA barrier below
 
     const int C = P.C, CP = P.CP;
     // all landing zones first (each a multiple of 128 bytes, the alignment TMA wants), then the per-warp rest
@@ -165,13 +167,14 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
     const int gi = lane >> 4, i = lane & 15;
     const float ly = ((float)i + 0.5f) * RS;
 
-    long long next_job = 0;
+    const int njobs = (int)P.njobs;
+    int next_job = 0;
 #pragma unroll 1
-    for (long long job = gw; job < P.njobs; job = next_job) {
+    for (int job = gw; job < njobs; job = next_job) {
         {
             unsigned t = 0;
             if (lane == 0) t = atomicAdd(P.ctr, 1u);
-            next_job = gstride + (long long)__shfl_sync(0xffffffffu, t, 0);
+            next_job = gstride + (int)__shfl_sync(0xffffffffu, t, 0);
         }
         const RCJob J = rc_decode(P, job);
         const int n = J.n, ky = J.ky, kx0 = J.kx0;
@@ -388,87 +391,160 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
         {
             const unsigned inmask = !row_in ? 0u : (x0 < 0 ? 0xff00u : (x0 + S > P.W ? 0x00ffu : 0xffffu));
             unsigned* rec = reinterpret_cast<unsigned*>(Usm) + lane;
-            unsigned ce_start = 0, cm_start = 0, cmv = 0;
-            int prev_lab = -1, prev_key = -1;
+            if constexpr (COLS) {
+                // ---- column sweep: column j of all 32 rows at once ---------------------------------------------------
+                //   confusion matrix: one 64-bit reduction per distinct (target, prediction) pair of the column
+                //   cross-entropy   : the pixel's target logit; the -onehot term as exact integer tap weights summed over the
+                //                     rows of the same group that carry the same label (their row-weight sums follow from
+                //                     the match mask alone), four float reductions per distinct (label, group)
 #pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const unsigned lab = (lw16[j >> 1] >> (16 * (j & 1))) & 0xffffu;
-                const int t = (int)(lab & 0x7fffu);                           // bit 15: ignore flag of the CE
-                const bool c = (vm >> j) & 1u, v = ((inmask >> j) & 1u) && t < C;
-                const int key = t * C + bidx[j];
-                if (c && (int)lab != prev_lab) ce_start |= 1u << j;
-                if (v && key != prev_key) cm_start |= 1u << j;
-                prev_lab = c ? (int)lab : -1;
-                prev_key = v ? key : -1;
-                cmv |= (v ? 1u : 0u) << j;
-                rec[j * 32] = lab | ((unsigned)bidx[j] << 16);
-            }
-            if (P.pred != nullptr && inmask) {
-                long long* prow = P.pred + ((size_t)n * P.H + y) * P.W + x0;
+                for (int j = 0; j < S; ++j) {
+                    const unsigned lab = (lw16[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                    rec[j * 32] = lab | ((unsigned)bidx[j] << 16);
+                }
+                if (P.pred != nullptr && inmask) {
+                    long long* prow = P.pred + ((size_t)n * P.H + y) * P.W + x0;
 #pragma unroll
-                for (int j = 0; j < S; ++j)
-                    if ((inmask >> j) & 1u) prow[j] = bidx[j];
-            }
-            // end of the run that starts at j0: the next column that starts a run or is not counted
-            auto run_end = [](unsigned starts, unsigned counted, int j0) {
-                const unsigned brk = ((starts | ~counted) & 0xffffu) >> (j0 + 1);
-                return brk ? j0 + __ffs(brk) : S;
-            };
-            // -- cross-entropy runs
-            {
+                    for (int j = 0; j < S; ++j)
+                        if ((inmask >> j) & 1u) prow[j] = bidx[j];
+                }
                 const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
                 const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);
                 const int oA = Ya * P.w + Xa, oB = Ya * P.w + Xb, oC = Yb * P.w + Xa, oD = Yb * P.w + Xb;
                 const float* lbase = P.low + (size_t)n * C * plane;
                 float* gbase = (P.grad && P.onehot) ? P.grad + (size_t)n * C * plane : nullptr;
+                unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
                 constexpr float WSC = 1.f / (float)(4 * S * S);
-                const float wt = -(float)(2 * S - (2 * i + 1)) * WSC, wb = -(float)(2 * i + 1) * WSC;   // top / bottom taps
                 float tsub = 0.f;
-                // (warp-uniform trip count: a loop the lanes leave one by one came back from its convergence barrier in
-                // pieces, and the class phase below then ran once per piece - ncu: 16 active threads, twice the instructions)
-                unsigned m = ce_start;
-#pragma unroll 1
-                while (__any_sync(0xffffffffu, m != 0)) {
-                    if (!m) continue;
-                    const int j0 = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int j1 = run_end(ce_start, vm, j0);
-                    const int lab = (int)(rec[j0 * 32] & 0xffffu);
-                    const int len = j1 - j0, sumj = (len * (j0 + j1 - 1)) >> 1;     // sum of the run's column indices
-                    const int sw1 = 2 * sumj + len, sw0 = 2 * S * len - sw1;          // sums of (2j+1), 2S - (2j+1)
-                    float4 q;
-                    if (!slow) q = Q[lab * 2];
-                    else {
-                        const float* t4 = lbase + (size_t)lab * plane;
-                        q = rc_quad<RC_S>(__ldg(t4 + oA), __ldg(t4 + oB), __ldg(t4 + oC), __ldg(t4 + oD));
+#pragma unroll 4
+                for (int j = 0; j < S; ++j) {
+                    const unsigned r = rec[j * 32];
+                    const unsigned lab = r & 0xffffu;
+                    const int t = (int)(lab & 0x7fffu), pr = (int)(r >> 16);      // bit 15: ignore flag of the CE
+                    const bool c = (vm >> j) & 1u, v = ((inmask >> j) & 1u) && t < C;
+                    const unsigned actv = __ballot_sync(0xffffffffu, v);
+                    if (v) {
+                        const int key = t * C + pr;
+                        const unsigned m = __match_any_sync(actv, key);
+                        if (lane == __ffs(m) - 1) {
+                            const unsigned long long cnt = (unsigned long long)__popc(m);
+                            atomicAdd(&P.confmat[key], cnt);
+                            if (pimg) {
+                                if (t == pr) atomicAdd(&pimg[t], cnt);
+                                atomicAdd(&pimg[C + t], cnt);
+                                atomicAdd(&pimg[2 * C + pr], cnt);
+                            }
+                        }
                     }
-                    // sum over the run of v(j) = v0 + j * delta
-                    tsub += fmaf((float)sumj, fmaf(ly, q.w, q.z), (float)len * fmaf(ly, q.y, q.x));
-                    if (gbase) {
-                        float* gp = gbase + (size_t)lab * plane;
-                        red_add_f32(gp + oA, wt * (float)sw0); red_add_f32(gp + oB, wt * (float)sw1);
-                        red_add_f32(gp + oC, wb * (float)sw0); red_add_f32(gp + oD, wb * (float)sw1);
+                    const unsigned actc = __ballot_sync(0xffffffffu, c);
+                    if (c) {
+                        float4 q;
+                        if (!slow) q = Q[lab * 2];
+                        else {
+                            const float* t4 = lbase + (size_t)lab * plane;
+                            q = rc_quad<RC_S>(__ldg(t4 + oA), __ldg(t4 + oB), __ldg(t4 + oC), __ldg(t4 + oD));
+                        }
+                        tsub += fmaf((float)j, fmaf(ly, q.w, q.z), fmaf(ly, q.y, q.x));
+                        if (gbase) {
+                            const unsigned m = __match_any_sync(actc, lab | ((unsigned)gi << 16));
+                            if (lane == __ffs(m) - 1) {
+                                const unsigned mm = (m >> (16 * gi)) & 0xffffu;          // bit i = row i of this group
+                                const int cnt = __popc(mm);
+                                const int si = __popc(mm & 0xAAAAu) + 2 * __popc(mm & 0xCCCCu) + 4 * __popc(mm & 0xF0F0u) +
+                                               8 * __popc(mm & 0xFF00u);                // sum of the row indices
+                                const int sb = 2 * si + cnt, st = 2 * S * cnt - sb;      // sums of (2i+1), 2S - (2i+1)
+                                const float c1 = -WSC * (float)(2 * j + 1), c0 = -WSC * (float)(2 * S - (2 * j + 1));
+                                float* gp = gbase + (size_t)lab * plane;
+                                red_add_f32(gp + oA, c0 * (float)st); red_add_f32(gp + oB, c1 * (float)st);
+                                red_add_f32(gp + oC, c0 * (float)sb); red_add_f32(gp + oD, c1 * (float)sb);
+                            }
+                        }
                     }
                 }
                 loss -= tsub;
-            }
-            // -- confusion-matrix runs
-            {
-                unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
-                unsigned m = cm_start;
-#pragma unroll 1
-                while (__any_sync(0xffffffffu, m != 0)) {
-                    if (!m) continue;
-                    const int j0 = __ffs(m) - 1;
-                    m &= m - 1;
-                    const unsigned long long cnt = (unsigned long long)(run_end(cm_start, cmv, j0) - j0);
-                    const unsigned r = rec[j0 * 32];
-                    const int t = (int)(r & 0x7fffu), pr = (int)(r >> 16);
-                    atomicAdd(&P.confmat[t * C + pr], cnt);
-                    if (pimg) {
-                        if (t == pr) atomicAdd(&pimg[t], cnt);
-                        atomicAdd(&pimg[C + t], cnt);
-                        atomicAdd(&pimg[2 * C + pr], cnt);
+            } else {
+                unsigned ce_start = 0, cm_start = 0, cmv = 0;
+                int prev_lab = -1, prev_key = -1;
+    #pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    const unsigned lab = (lw16[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+                    const int t = (int)(lab & 0x7fffu);                           // bit 15: ignore flag of the CE
+                    const bool c = (vm >> j) & 1u, v = ((inmask >> j) & 1u) && t < C;
+                    const int key = t * C + bidx[j];
+                    if (c && (int)lab != prev_lab) ce_start |= 1u << j;
+                    if (v && key != prev_key) cm_start |= 1u << j;
+                    prev_lab = c ? (int)lab : -1;
+                    prev_key = v ? key : -1;
+                    cmv |= (v ? 1u : 0u) << j;
+                    rec[j * 32] = lab | ((unsigned)bidx[j] << 16);
+                }
+                if (P.pred != nullptr && inmask) {
+                    long long* prow = P.pred + ((size_t)n * P.H + y) * P.W + x0;
+    #pragma unroll
+                    for (int j = 0; j < S; ++j)
+                        if ((inmask >> j) & 1u) prow[j] = bidx[j];
+                }
+                // end of the run that starts at j0: the next column that starts a run or is not counted
+                auto run_end = [](unsigned starts, unsigned counted, int j0) {
+                    const unsigned brk = ((starts | ~counted) & 0xffffu) >> (j0 + 1);
+                    return brk ? j0 + __ffs(brk) : S;
+                };
+                // -- cross-entropy runs
+                {
+                    const int Ya = clampi2(ky, 0, P.h - 1), Yb = clampi2(ky + 1, 0, P.h - 1);
+                    const int Xa = clampi2(kx, 0, P.w - 1), Xb = clampi2(kx + 1, 0, P.w - 1);
+                    const int oA = Ya * P.w + Xa, oB = Ya * P.w + Xb, oC = Yb * P.w + Xa, oD = Yb * P.w + Xb;
+                    const float* lbase = P.low + (size_t)n * C * plane;
+                    float* gbase = (P.grad && P.onehot) ? P.grad + (size_t)n * C * plane : nullptr;
+                    constexpr float WSC = 1.f / (float)(4 * S * S);
+                    const float wt = -(float)(2 * S - (2 * i + 1)) * WSC, wb = -(float)(2 * i + 1) * WSC;   // top / bottom taps
+                    float tsub = 0.f;
+                    // (warp-uniform trip count: a loop the lanes leave one by one came back from its convergence barrier in
+                    // pieces, and the class phase below then ran once per piece - ncu: 16 active threads, twice the instructions)
+                    unsigned m = ce_start;
+    #pragma unroll 1
+                    while (__any_sync(0xffffffffu, m != 0)) {
+                        if (!m) continue;
+                        const int j0 = __ffs(m) - 1;
+                        m &= m - 1;
+                        const int j1 = run_end(ce_start, vm, j0);
+                        const int lab = (int)(rec[j0 * 32] & 0xffffu);
+                        const int len = j1 - j0, sumj = (len * (j0 + j1 - 1)) >> 1;     // sum of the run's column indices
+                        const int sw1 = 2 * sumj + len, sw0 = 2 * S * len - sw1;          // sums of (2j+1), 2S - (2j+1)
+                        float4 q;
+                        if (!slow) q = Q[lab * 2];
+                        else {
+                            const float* t4 = lbase + (size_t)lab * plane;
+                            q = rc_quad<RC_S>(__ldg(t4 + oA), __ldg(t4 + oB), __ldg(t4 + oC), __ldg(t4 + oD));
+                        }
+                        // sum over the run of v(j) = v0 + j * delta
+                        tsub += fmaf((float)sumj, fmaf(ly, q.w, q.z), (float)len * fmaf(ly, q.y, q.x));
+                        if (gbase) {
+                            float* gp = gbase + (size_t)lab * plane;
+                            red_add_f32(gp + oA, wt * (float)sw0); red_add_f32(gp + oB, wt * (float)sw1);
+                            red_add_f32(gp + oC, wb * (float)sw0); red_add_f32(gp + oD, wb * (float)sw1);
+                        }
+                    }
+                    loss -= tsub;
+                }
+                // -- confusion-matrix runs
+                {
+                    unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
+                    unsigned m = cm_start;
+    #pragma unroll 1
+                    while (__any_sync(0xffffffffu, m != 0)) {
+                        if (!m) continue;
+                        const int j0 = __ffs(m) - 1;
+                        m &= m - 1;
+                        const unsigned long long cnt = (unsigned long long)(run_end(cm_start, cmv, j0) - j0);
+                        const unsigned r = rec[j0 * 32];
+                        const int t = (int)(r & 0x7fffu), pr = (int)(r >> 16);
+                        atomicAdd(&P.confmat[t * C + pr], cnt);
+                        if (pimg) {
+                            if (t == pr) atomicAdd(&pimg[t], cnt);
+                            atomicAdd(&pimg[C + t], cnt);
+                            atomicAdd(&pimg[2 * C + pr], cnt);
+                        }
                     }
                 }
             }
@@ -617,7 +693,7 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
         }
         __syncwarp();                                       // quads / U free for the next job
         // ---- the box of the warp's next job (its latency is covered by the SM's other warps) -----------------------
-        if (next_job < P.njobs) {
+        if (next_job < njobs) {
             const RCJob Jn = rc_decode(P, next_job);
             rc_stage(P, &tm, cells, bar, Jn, lane);
         }
@@ -690,6 +766,7 @@ int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, in
     P.CP = (C + RC_CH - 1) / RC_CH * RC_CH;
     P.jpr = (w + 1 + 1) / 2;
     P.njobs = (long long)B * (h + 1) * P.jpr;
+    if (P.njobs > 0x3fffffffLL) return fail(LC2IS_ERR_SHAPE, "too many groups for one launch%s");
     P.cells_bytes = (unsigned)rc_cells_bytes(C);
     P.quads_bytes = (unsigned)rc_quads_bytes(C);
     P.use_tma = (C <= 256 && w % 4 == 0 && ((uintptr_t)d_low % 16) == 0 && !getenv("LC2IS_RC_NO_TMA")) ? 1 : 0;
@@ -702,7 +779,9 @@ int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, in
     static cudaError_t attr_err = cudaSuccess;
     static unsigned* ctr_pool = nullptr;                    // RC_CTR_SLOTS self-resetting counter pairs, used round-robin
     std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(k23_rc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_err = cudaFuncSetAttribute(k23_rc_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(k23_rc_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (attr_err == cudaSuccess) attr_err = cudaMalloc(&ctr_pool, RC_CTR_SLOTS * 2 * sizeof(unsigned));
         if (attr_err == cudaSuccess) attr_err = cudaMemset(ctr_pool, 0, RC_CTR_SLOTS * 2 * sizeof(unsigned));
     });
@@ -712,7 +791,9 @@ int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, in
     P.ctr = ctr_pool + 2 * (seq.fetch_add(1, std::memory_order_relaxed) % RC_CTR_SLOTS);
     long long ctas = (P.njobs + nw - 1) / nw;
     if (ctas > sm_count()) ctas = sm_count();
-    k23_rc_kernel<16><<<(unsigned)ctas, nw * 32, smem, st>>>(tm, P);
+    static const bool runs = getenv("LC2IS_RC_RUNS") != nullptr;
+    if (runs) k23_rc_kernel<16, false><<<(unsigned)ctas, nw * 32, smem, st>>>(tm, P);
+    else k23_rc_kernel<16, true><<<(unsigned)ctas, nw * 32, smem, st>>>(tm, P);
     LC2IS_CHECK_LAUNCH("k23_rc_kernel");
     return 0;
 }
