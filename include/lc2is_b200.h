@@ -88,6 +88,19 @@ int lc2is_cosine_logits_fwd(const void* d_v, int v_dtype, int B, int hw, int D,
 int lc2is_linear_fwd(const void* d_x_bf16, const void* d_w_bf16, const float* d_bias,
                      long long M, int N, int K, void* d_y, int y_dtype, lc2is_stream_t stream);
 
+/* Producer of the projection: bicubic x4 upsample of the decoder's TOKEN-major feature map, written directly as the
+ * row-major operand of TextToPatch.visual.  Replaces model/model.py:42-44 (rearrange to [B,C,h,w], F.interpolate(bicubic,
+ * scale_factor=4), rearrange back - an fp32 [B,C,4h,4w] intermediate and two layout passes) and their autograd backward.
+ * d_x [B, h*w, C] fp32 / bf16 -> d_y [B, 16*h*w, C] fp32 / bf16 (ATen's taps: A = -0.75, src = 0.25*(dst+0.5)-0.5, clamped
+ * indices, horizontal then vertical chains).  C % 4 == 0, 16-byte aligned pointers.
+ * backward: d_gx [B, h*w, C] = the transpose applied to d_gy [B, 16*h*w, C]; two gather passes (no atomics) through an fp32
+ * workspace of lc2is_bicubic4_tokens_bwd_workspace bytes. */
+int lc2is_bicubic4_tokens_fwd(const void* d_x, int x_dtype, int B, int h, int w, int C, void* d_y, int y_dtype,
+                              lc2is_stream_t stream);
+int64_t lc2is_bicubic4_tokens_bwd_workspace(int B, int h, int w, int C);
+int lc2is_bicubic4_tokens_bwd(const void* d_gy, int gy_dtype, int B, int h, int w, int C, void* d_gx, int gx_dtype,
+                              void* d_ws, lc2is_stream_t stream);
+
 /* Backward of the same projection (autograd of model/text_patch.py:12,17; y = x W^T + b), all on tcgen05:
  *   d_gx [M,K] (gx_dtype) = gy . W      lc2is_linear_fwd's pipeline on the transposed weight (built in d_ws)
  *   d_gw [N,K] fp32      += gy^T . x    split-K over the rows, both operands MN-major, fp32 L2 reductions (ACCUMULATES:

@@ -43,6 +43,9 @@ SIGNATURES = {
     "lc2is_cosine_logits_fwd": (c_int, [_p, c_int, c_int, c_int, c_int, _p, c_int, c_int, c_int, c_float,
                                         _p, _p, _p, _p]),
     "lc2is_linear_fwd": (c_int, [_p, _p, _p, c_int64, c_int, c_int, _p, c_int, _p]),
+    "lc2is_bicubic4_tokens_fwd": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, _p, c_int, _p]),
+    "lc2is_bicubic4_tokens_bwd_workspace": (c_int64, [c_int, c_int, c_int, c_int]),
+    "lc2is_bicubic4_tokens_bwd": (c_int, [_p, c_int, c_int, c_int, c_int, c_int, _p, c_int, _p, _p]),
     "lc2is_linear_bwd_workspace": (c_int64, [c_int, c_int]),
     "lc2is_linear_bwd": (c_int, [_p, _p, _p, c_int64, c_int, c_int, _p, c_int, _p, _p, _p, _p]),
     "lc2is_cosine_logits_bwd_workspace": (c_int64, [c_int, c_int, c_int, c_int, c_int]),

@@ -62,6 +62,28 @@ def cosine_logits(v: Tensor, t: Tensor, *, normalize: bool = True, logit_scale: 
     return _CosineLogits.apply(v, t, bool(normalize), float(logit_scale), (h, w))
 
 
+class _UpsampleTokens(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x: Tensor, hw_shape, out_dtype):
+        ctx.meta = (hw_shape, x.dtype)
+        return ops.bicubic4_tokens_fwd(x, hw_shape, out_dtype)
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        hw_shape, xdt = ctx.meta
+        gx = ops.bicubic4_tokens_bwd(gy, hw_shape, torch.bfloat16 if xdt == torch.bfloat16 else torch.float32)
+        return gx.to(xdt), None, None
+
+
+def upsample_tokens_bicubic4(x: Tensor, hw_shape: Optional[Tuple[int, int]] = None, out_dtype=torch.bfloat16) -> Tensor:
+    """model.py:42-44 in one kernel: ``x [B, h*w, C]`` (the decoder's tokens) -> ``[B, 16*h*w, C]``, the bicubic x4 upsampled
+    feature map still token-major - i.e. already the operand of ``TextToPatch.visual`` (bf16 by default: the tensor-core
+    projection rounds its operands to bf16 anyway; pass ``torch.float32`` for the reference's dtype).  Differentiable."""
+    h, w = _hw_shape(x.shape[1], hw_shape)
+    return _UpsampleTokens.apply(x, (h, w), out_dtype)
+
+
 class _SegHeadLoss(torch.autograd.Function):
 
     @staticmethod

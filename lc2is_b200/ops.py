@@ -58,6 +58,36 @@ def linear_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, out_dty
     return y
 
 
+def bicubic4_tokens_fwd(x: Tensor, hw_shape: Tuple[int, int], out_dtype=torch.bfloat16) -> Tensor:
+    """x [B, h*w, C] fp32/bf16 (token-major) -> [B, 16*h*w, C]: bicubic x4 of model.py:42-44 without the layout changes."""
+    if not x.is_cuda:
+        raise _lib.Lc2isError("x must be a CUDA tensor (lc2is_b200 has no CPU fallback)")
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    x = x.contiguous()
+    B, P, C = x.shape
+    h, w = hw_shape
+    assert h * w == P
+    y = torch.empty(B, 16 * P, C, dtype=out_dtype, device=x.device)
+    check(lib.lc2is_bicubic4_tokens_fwd(ptr(x), _dt(x), B, h, w, C, ptr(y), _dt(y), stream_ptr()), "lc2is_bicubic4_tokens_fwd")
+    return y
+
+
+def bicubic4_tokens_bwd(gy: Tensor, hw_shape: Tuple[int, int], out_dtype=torch.float32) -> Tensor:
+    """gy [B, 16*h*w, C] -> gx [B, h*w, C]: the transpose of bicubic4_tokens_fwd (two gather passes)."""
+    if gy.dtype not in (torch.float32, torch.bfloat16):
+        gy = gy.float()
+    gy = gy.contiguous()
+    B, P16, C = gy.shape
+    h, w = hw_shape
+    assert 16 * h * w == P16
+    gx = torch.empty(B, h * w, C, dtype=out_dtype, device=gy.device)
+    ws = torch.empty(int(lib.lc2is_bicubic4_tokens_bwd_workspace(B, h, w, C)), dtype=torch.uint8, device=gy.device)
+    check(lib.lc2is_bicubic4_tokens_bwd(ptr(gy), _dt(gy), B, h, w, C, ptr(gx), _dt(gx), ptr(ws), stream_ptr()),
+          "lc2is_bicubic4_tokens_bwd")
+    return gx
+
+
 def linear_bwd(gy: Tensor, x: Tensor, weight: Tensor, need_gx: bool = True, need_gw: bool = True, need_gb: bool = True,
                gx_dtype=torch.bfloat16, gw: Optional[Tensor] = None, gb: Optional[Tensor] = None):
     """Backward of y = x W^T + b on tcgen05 (lc2is_linear_bwd).  gy [M,N], x [M,K], weight [N,K]: bf16.

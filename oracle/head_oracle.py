@@ -155,6 +155,16 @@ def contrastive_loss(outputs: Tensor, labels: Tensor, ignore_index: int = -100, 
     return (loss_textual + loss_visual) / 2, loss_visual, loss_textual
 
 
+def upsample_tokens_bicubic4(dec_v: Tensor, h: int) -> Tensor:
+    """model/model.py:42-44 restated (einops rearranges written as permutes): token-major features [B, h*w, C] ->
+    bicubic x4 -> [B, 16*h*w, C]."""
+    B, P, C = dec_v.shape
+    w = P // h
+    x = dec_v.permute(0, 2, 1).reshape(B, C, h, w)                       # "b (h w) c -> b c h w"
+    x = F.interpolate(input=x, mode="bicubic", scale_factor=4)
+    return x.reshape(B, C, 16 * P).permute(0, 2, 1).contiguous()         # "b c h w -> b (h w) c"
+
+
 def argmax_reference(logits: Tensor) -> Tensor:
     """What ``JaccardIndex`` sees in the reference: ``argmax(Softmax2d(x), dim=class)``
     (metrics.py:92 feeds ``softmax2D(output)``; torchmetrics argmaxes float preds).

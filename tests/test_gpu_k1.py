@@ -283,3 +283,50 @@ def test_backward_raw_v(B, hw, C):
     gv2, gt2 = ops.cosine_logits_bwd(Gd, logits2, v_hat, inv_v2, t_hat, inv_t, C)
     assert float((gv - gv2).abs().max()) <= 2e-2 * float(gv2.abs().max())
     assert float((gt - gt2).abs().max()) <= 2e-2 * float(gt2.abs().max())
+
+
+# ---- producer of the projection: bicubic x4 of the token-major feature map (model/model.py:42-44) -----------------------
+@pytest.mark.parametrize("B,h,w,C,in_dtype,out_dtype", [
+    (2, 8, 8, 64, torch.float32, torch.float32), (1, 32, 32, 768, torch.float32, torch.bfloat16),
+    (2, 5, 7, 12, torch.float32, torch.float32), (1, 1, 1, 4, torch.float32, torch.float32),
+    (2, 6, 4, 32, torch.bfloat16, torch.bfloat16), (1, 2, 9, 8, torch.bfloat16, torch.float32)])
+def test_bicubic4_tokens_forward_and_backward(B, h, w, C, in_dtype, out_dtype):
+    """lc2is_bicubic4_tokens_fwd / _bwd against the reference lines (oracle.upsample_tokens_bicubic4 = rearrange +
+    F.interpolate(bicubic, x4) + rearrange on CPU, and its autograd).  Tolerance: fp32 evaluation order (1e-5 of the maximum)
+    or the bf16 rounding of the output (2^-8 relative)."""
+    from lc2is_b200 import head
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(B, h * w, C, generator=g).to(in_dtype)
+    xr = x.float().clone().requires_grad_(True)
+    if h == w:
+        ref = O.upsample_tokens_bicubic4(xr, h)
+    else:                                                    # the reference line needs the grid shape for non-square maps
+        t = xr.permute(0, 2, 1).reshape(B, C, h, w)
+        ref = torch.nn.functional.interpolate(t, mode="bicubic", scale_factor=4).reshape(B, C, 16 * h * w).permute(0, 2, 1)
+    xd = x.to(DEV).requires_grad_(True)
+    y = head.upsample_tokens_bicubic4(xd, (h, w), out_dtype)
+    assert y.shape == (B, 16 * h * w, C) and y.dtype == out_dtype
+    tol = 1e-5 if out_dtype == torch.float32 else 2.0 ** -8
+    assert float((y.float().cpu() - ref).abs().max()) <= tol * float(ref.abs().max())
+    gy = torch.randn(B, 16 * h * w, C, generator=g).to(torch.bfloat16).float()       # representable in either output dtype
+    ref.backward(gy)
+    y.backward(gy.to(DEV).to(out_dtype))
+    tolg = 1e-5 if in_dtype == torch.float32 else 2.0 ** -7                         # bf16 input: gradient rounded to bf16
+    assert xd.grad.dtype == in_dtype
+    assert float((xd.grad.float().cpu() - xr.grad).abs().max()) <= tolg * float(xr.grad.abs().max())
+
+
+def test_bicubic4_tokens_feed_the_projection():
+    """The chain of model.py:42-47 on the kernels: tokens -> bicubic x4 (bf16 rows) -> TextToPatch.visual (tcgen05), against
+    the reference lines in fp32 (bf16 operand rounding: 2e-2 of the maximum)."""
+    from lc2is_b200 import head
+    from lc2is_b200.model.text_patch import TextToPatch
+    torch.manual_seed(2)
+    B, h, C = 2, 8, 768
+    m = TextToPatch(C, 512, 512).to(DEV)
+    dec = torch.randn(B, h * h, C, device=DEV)
+    up = head.upsample_tokens_bicubic4(dec, (h, h))                       # bf16 rows -> tensor-core projection
+    _, v = m(up, torch.randn(151, 512, device=DEV))
+    ref = torch.nn.functional.linear(O.upsample_tokens_bicubic4(dec.cpu(), h).to(DEV), m.visual.weight, m.visual.bias)
+    assert v.shape == (B, 16 * h * h, 512)
+    assert float((v.float() - ref).abs().max()) <= 2e-2 * float(ref.abs().max())
