@@ -161,7 +161,8 @@ def run_reference(a):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a, h, w), "sample": sample},
+        "config": {"workload": workload_name(a, h, w), "global_batch": a.gpus * a.batch, "parallelism": f"dp{a.gpus}",
+                   "backward": not a.no_backward},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -657,10 +658,12 @@ def run_b200(a):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
         "config": {"workload": workload_name(a, h, w), "global_batch": world * B, "parallelism": f"dp{world}",
-                   "backward": backward,
-                   "l2": f"inputs rotate over {nset} distinct sets ({nset * set_bytes / 2**20:.0f} MiB) > 126 MiB L2; no flush",
-                   "launch": "CUDA graph replay (one graph per input set)"
-                             if graphs is not None else "eager launches", "graph_error": graph_err},
+                   "backward": backward},
+        "timing": {"l2": f"inputs rotate over {nset} distinct sets ({nset * set_bytes / 2**20:.0f} MiB) > 126 MiB L2; no flush",
+                   "launch": ("CUDA graph replay (one graph per input set" +
+                              ("; three kernel-only graphs per step, the two ncclAllReduce launches eager in between)"
+                               if world > 1 else ")")) if graphs is not None else "eager launches",
+                   "graph_error": graph_err},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
         "cpu_baseline": cpu_baseline, "section_us": section_us, "host_enqueue_ms_per_step": host_enqueue_ms,
         "check": {"loss": loss_val, "mIoU": miou, "n_valid": n_valid_val, "confmat_total": cm_sum,

@@ -5,5 +5,5 @@ echo "rc=$?"
 python -c "
 import json,sys
 d=[json.loads(l) for l in open('gpurun_out/dp_$tag.json') if l.startswith('{')][0]
-print('$tag', round(d['value']), round(d['ms_per_step'],4), round(d['roofline']['kernel_us'],1), round(d['host_enqueue_ms_per_step'],3), d['config']['launch'], d['config']['graph_error'], (d['dp_check'] or {}).get('ok'))
+print('$tag', round(d['value']), round(d['ms_per_step'],4), round(d['roofline']['kernel_us'],1), round(d['host_enqueue_ms_per_step'],3), d['timing']['launch'], d['timing']['graph_error'], (d['dp_check'] or {}).get('ok'))
 "
