@@ -25,7 +25,10 @@ Pinning status
   ``confmat = bincount(target*C + pred, minlength=C*C).reshape(C, C)`` (rows=target),
   ``confmat[ignore_index] = 0``, ``iou = diag / (rowsum + colsum - diag)``,
   absent classes (union == 0) score 0.0, the ignore class is dropped, macro mean.
-  The reference holds no golden vector for this boundary.
+  The reference holds no golden vector for this boundary.  The restated definitions are cross-checked against an
+  independent implementation that is installed (scikit-learn ``confusion_matrix`` / ``jaccard_score``:
+  ``tests/test_oracle_golden.py::test_iou_formulas_against_scikit_learn``) - not the same as pinning against torchmetrics.
+* ``upsample_tokens_bicubic4`` (model/model.py:42-44): the reference lines themselves (einops rearranges as permutes).
 """
 from __future__ import annotations
 

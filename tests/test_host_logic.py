@@ -234,3 +234,18 @@ def test_ftn_decoder_mirrors_run_and_keep_the_reference_parameter_names():
         assert n in names, n
     blk = FTNBlock(SRTransformerDecoder(d_model=64, nhead=8, sr_ratio=2, dropout=0.0, batch_first=True)).eval()
     assert blk(tgt=torch.randn(1, 16, 64), memory=torch.randn(1, 3, 64)).shape == (1, 64, 64)
+
+
+def test_ragged_descriptor_table():
+    """The descriptor table of lc2is_argmax_confmat_ragged (host logic): element offsets are the running sum of H*W, first
+    tiles the running sum of lc2is_ragged_tiles (64 x 32 pixel tiles), images without pixels own no tile."""
+    from lc2is_b200 import ops
+    from lc2is_b200._lib import lib
+    sizes = [(64, 64), (1, 1), (33, 65), (0, 5), (100, 7)]
+    desc, n_tiles, n_elem = ops.ragged_descriptors(sizes)
+    assert desc.shape == (5, 4) and desc.dtype == torch.int64
+    tiles = [2 * 1, 1, 2 * 2, 0, 4 * 1]
+    assert [int(lib.lc2is_ragged_tiles(h, w)) for h, w in sizes] == tiles
+    assert desc[:, 0].tolist() == [0, 4096, 4097, 4097 + 33 * 65, 4097 + 33 * 65]
+    assert desc[:, 3].tolist() == [0, 2, 3, 7, 7] and n_tiles == 11 and n_elem == 4097 + 33 * 65 + 700
+    assert desc[:, 1:3].tolist() == [list(s) for s in sizes]
