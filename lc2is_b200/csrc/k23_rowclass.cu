@@ -416,7 +416,7 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
                 unsigned long long* pimg = P.per_image ? P.per_image + (size_t)n * 3 * C : nullptr;
                 constexpr float WSC = 1.f / (float)(4 * S * S);
                 float tsub = 0.f;
-#pragma unroll 4
+#pragma unroll 2
                 for (int j = 0; j < S; ++j) {
                     const unsigned r = rec[j * 32];
                     const unsigned lab = r & 0xffffu;
