@@ -222,7 +222,7 @@ k2_fast_kernel(const K2Params P) {
         float2 S01[4], S23[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) { S01[j] = make_float2(0.f, 0.f); S23[j] = make_float2(0.f, 0.f); }
-#pragma unroll 2
+#pragma unroll 4
         for (int c = 0; c < C; ++c) {
             float a, b, cc, d;
             taps(c, a, b, cc, d);
@@ -331,7 +331,7 @@ k2_fast_kernel(const K2Params P) {
                 K1v[i] = make_float2(U[i * 4 + 1], U[i * 4 + 1]);
                 K0[i] = make_float2(U[i * 4 + 0], 0.f);
             }
-#pragma unroll 2
+#pragma unroll 4
             for (int c = 0; c < C; ++c) {
                 float a, b, cc, d;
                 taps(c, a, b, cc, d);
