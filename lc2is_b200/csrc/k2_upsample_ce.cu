@@ -127,14 +127,20 @@ k2_fast_kernel(const K2Params P) {
             else st[c * cs + r] = 0.f;
         }
     } else {
-        for (int idx = threadIdx.x; idx < C * cs; idx += nthr) {
-            const int c = idx / cs, r = idx - c * cs;
+        // (a thread owns tile cells r, r + nthr, ... and walks the classes: no integer division per copied element - the
+        // staging loop was a third of this kernel's instructions)
+        const size_t plane = (size_t)P.h * P.w;
+        for (int r = threadIdx.x; r < cs; r += nthr) {
             const int i = r / ncx, j = r - i * ncx;
             const int gy = cy0 + i, gx = cx0 + j;
-            if (gy >= 0 && gy < P.h && gx >= 0 && gx < P.w)
-                cp_async4(st + idx, lowb + ((size_t)c * P.h + gy) * P.w + gx);
-            else
-                st[idx] = 0.f;
+            float* dst = st + r;
+            if (gy >= 0 && gy < P.h && gx >= 0 && gx < P.w) {
+                const float* src = lowb + (size_t)gy * P.w + gx;
+#pragma unroll 4
+                for (int c = 0; c < C; ++c) cp_async4(dst + (size_t)c * cs, src + (size_t)c * plane);
+            } else {
+                for (int c = 0; c < C; ++c) dst[(size_t)c * cs] = 0.f;
+            }
         }
     }
     cp_async_wait_all();
