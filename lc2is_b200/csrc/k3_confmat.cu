@@ -274,8 +274,10 @@ k3_low_fast_kernel(const K3LowParams P) {
     const float tx0 = ((float)x0 + 0.5f) * rs - 0.5f - (float)kx;
 
     // ---- non-finite taps?  (lanes of the group split the classes) -----------------------------------
+    // (bicubic only: the bilinear loop below detects them on the fly - a separate sweep over the taps was 11 % of the x4
+    // kernel's instructions)
     bool exotic = false;
-    if (group_in) {
+    if (MODE != 0 && group_in) {
         for (int c = u; c < C; c += LPG) {
             const float* p = st + (size_t)c * cs + o00;
 #pragma unroll
@@ -291,6 +293,7 @@ k3_low_fast_kernel(const K3LowParams P) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) { best[i] = -INFINITY; bidx[i] = 0; }
 
+    float poison = 0.f;                                     // becomes NaN when a tap of the group is not finite
     if (group_in && !exotic) {
         if constexpr (MODE == 0) {
             // bilinear; at the clamped borders both taps are the same cell, so any lambda is exact
@@ -299,6 +302,7 @@ k3_low_fast_kernel(const K3LowParams P) {
                 const float* p = st + (size_t)c * cs + o00;
                 const float a = p[0], b = p[1], cc = p[ncx], d = p[ncx + 1];
                 const float da = cc - a, db = d - b, dd = db - da;
+                poison = fmaf(0.f, dd, poison);                  // dd involves all four taps: inf / NaN -> NaN
                 const float L0 = fmaf(ty0, da, a), R0 = fmaf(ty0, db, b);
                 const float rl = R0 - L0;
                 const float l00 = fmaf(tx0, rl, L0);
@@ -361,8 +365,10 @@ k3_low_fast_kernel(const K3LowParams P) {
                     }
             }
         }
-    } else if (group_in) {
-        // exact per-pixel path with the NaN / +inf rule (rare)
+    }
+    if (MODE == 0) exotic = __any_sync(0xffffffffu, poison != poison);
+    if (group_in && exotic) {
+        // exact per-pixel path with the NaN / +inf rule (rare; for the bilinear kernel it replaces the results above)
         ArgmaxState stt[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) am_init(stt[i]);

@@ -398,3 +398,24 @@ def test_ragged_entry_rejects_bad_arguments():
         ops.argmax_confmat_ragged(low, [(8, 8), (4, 4)], None, want_pred=True)          # one size per image
     with pytest.raises(Exception):
         ops.argmax_confmat_ragged(low, [(8, 8)], torch.zeros(3, dtype=torch.int64, device=DEV))   # label count
+
+
+@pytest.mark.parametrize("mode", ["bilinear", "bicubic"])
+def test_x4_block_kernel_non_finite_taps(mode):
+    """k3_low_fast_kernel (x4): +-inf / NaN taps poison exactly the pixels they poison in argmax(softmax(interpolate(x)))
+    (class 0) - the bilinear kernel detects them inside its class loop and re-evaluates the warp exactly."""
+    g = torch.Generator().manual_seed(14)
+    N, C, h = 2, 13, 12
+    low = torch.randn(N, C, h, h, generator=g)
+    low[0, 3, 4, 5] = float("inf")
+    low[0, 7, 9, 2] = float("-inf")
+    low[1, 0, 6, 6] = float("nan")
+    low[1, 12, 11, 11] = float("inf")                       # corner cell (clamped taps)
+    labels = torch.randint(0, C, (N, 4 * h, 4 * h), generator=g)
+    up = F.interpolate(low, mode=mode, scale_factor=4)
+    ref = O.argmax_reference(up)
+    cm, _, pred = ops.argmax_confmat(low.to(DEV), labels.to(DEV), want_pred=True, size=(4 * h, 4 * h), mode=mode)
+    finite = torch.isfinite(up).all(1)
+    safe = _safe_mask(torch.nan_to_num(up, nan=0.0, posinf=0.0, neginf=0.0), 1e-4) | ~finite
+    assert torch.equal(pred.cpu()[safe], ref[safe])
+    assert (~finite).sum() > 0 and int(cm.sum()) == labels.numel()
