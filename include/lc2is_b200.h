@@ -180,6 +180,9 @@ int lc2is_mean_scale(const int64_t* d_n_valid, float mult, float* d_scale, lc2is
 /* *d_loss = *d_loss_sum / *d_n_valid  (NaN when nothing is valid, like torch). */
 int lc2is_finalize_loss(const double* d_loss_sum, const int64_t* d_n_valid, float* d_loss,
                         lc2is_stream_t stream);
+/* Both of the above in one launch (for steps in which the loss sum is complete before the gradient scale is needed). */
+int lc2is_mean_scale_finalize(const int64_t* d_n_valid, float mult, float* d_scale, const double* d_loss_sum,
+                              float* d_loss, lc2is_stream_t stream);
 int lc2is_upsample_ce_fwd_bwd(const float* d_low, const int64_t* d_labels,
                               int B, int C, int h, int w, int H, int W,
                               int64_t ignore_index, const float* d_grad_scale,

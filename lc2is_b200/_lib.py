@@ -57,6 +57,7 @@ SIGNATURES = {
     "lc2is_count_valid": (c_int, [_p, c_int64, c_int, c_int64, _p, _p]),
     "lc2is_mean_scale": (c_int, [_p, c_float, _p, _p]),
     "lc2is_finalize_loss": (c_int, [_p, _p, _p, _p]),
+    "lc2is_mean_scale_finalize": (c_int, [_p, c_float, _p, _p, _p, _p]),
     "lc2is_upsample_ce_fwd_bwd": (c_int, [_p, _p, c_int, c_int, c_int, c_int, c_int, c_int, c_int64, _p, _p,
                                           _p, _p, _p]),
     "lc2is_ce_split_supported": (c_int, [c_int, c_int, c_int, c_int]),

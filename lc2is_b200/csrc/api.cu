@@ -51,6 +51,14 @@ __global__ void finalize_loss_kernel(const double* loss_sum, const long long* n_
     *out = (float)(*loss_sum / (double)(*n_valid));
 }
 
+// both scalars of a 'mean' step in one launch (the loss sum is complete once K2 has run, the gradient scale is needed by K1b)
+__global__ void mean_scale_finalize_kernel(const long long* n_valid, float mult, float* scale, const double* loss_sum,
+                                           float* loss) {
+    const long long n = *n_valid;
+    *scale = n > 0 ? mult / (float)n : 0.f;
+    *loss = (float)(*loss_sum / (double)n);
+}
+
 }  // namespace lc2is
 
 using namespace lc2is;
@@ -64,6 +72,16 @@ extern "C" int lc2is_mean_scale(const int64_t* d_n_valid, float mult, float* d_s
     if (!d_n_valid || !d_scale) return fail(LC2IS_ERR_ARG, "null pointer%s");
     mean_scale_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const long long*)d_n_valid, mult, d_scale);
     LC2IS_CHECK_LAUNCH("mean_scale_kernel");
+    return 0;
+}
+
+extern "C" int lc2is_mean_scale_finalize(const int64_t* d_n_valid, float mult, float* d_scale, const double* d_loss_sum,
+                                         float* d_loss, lc2is_stream_t stream) {
+    if (int e = ensure_device()) return e;
+    if (!d_n_valid || !d_scale || !d_loss_sum || !d_loss) return fail(LC2IS_ERR_ARG, "null pointer%s");
+    mean_scale_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((const long long*)d_n_valid, mult, d_scale, d_loss_sum,
+                                                                   d_loss);
+    LC2IS_CHECK_LAUNCH("mean_scale_finalize_kernel");
     return 0;
 }
 

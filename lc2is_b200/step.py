@@ -336,7 +336,12 @@ class HeadStep:
         B, hw, D, C, h, w, H, W = self.B, self.hw, self.D, self.C, self.h, self.w, self.H, self.W
         blk = self._blocks[k]
         fuse = self._fuse(v)
-        check(lib.lc2is_mean_scale(ptr(blk.n_valid), 1.0, ptr(blk.gscale), st), "mean_scale")
+        if self.distributed:
+            check(lib.lc2is_mean_scale(ptr(blk.n_valid), 1.0, ptr(blk.gscale), st), "mean_scale")
+        else:
+            # single GPU: the loss sum is complete (K2 has run), so the loss leaves with the gradient scale in one launch
+            check(lib.lc2is_mean_scale_finalize(ptr(blk.n_valid), 1.0, ptr(blk.gscale), ptr(blk.loss_sum), ptr(blk.loss), st),
+                  "mean_scale_finalize")
         if self.backward:
             check(lib.lc2is_cosine_logits_bwd_ex(ptr(blk.grad_low), F32, ptr(self.logits),
                                                  ptr(v) if fuse else ptr(self.v_hat),
@@ -357,8 +362,6 @@ class HeadStep:
         self._mark("finalize")
         if self.distributed:
             blk.bucket.views[1].copy_(blk.loss_sum)              # fp32 copy of the loss sum rides in the bucket
-        else:
-            check(lib.lc2is_finalize_loss(ptr(blk.loss_sum), ptr(blk.n_valid), ptr(blk.loss), st), "finalize_loss")
 
 
 class HostStep:

@@ -2,13 +2,13 @@
 usage: make_profiles.py TAG launches.csv step.ncu-rep"""
 import csv, json, re, subprocess, sys
 tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
-# ---- 1. launch list of one bench step (between two finalize_loss launches)
+# ---- 1. launch list of one bench step (from one zero-fill of the accumulator block to the next)
 rows = list(csv.reader(open(launches)))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 H = rows[hdr]; ki = H.index('Kernel Name'); vi = H.index('Metric Value')
 L = [(r[ki], float(r[vi]) / 1e3) for r in rows[hdr + 1:] if len(r) > vi]
-fin = [i for i, (k, v) in enumerate(L) if 'finalize_loss' in k]
-a, b = fin[-2] + 1, fin[-1] + 1
+fin = [i for i, (k, v) in enumerate(L) if 'FillFunctor<float>' in k]
+a, b = fin[-2], fin[-1]
 tot = sum(v for k, v in L[a:b])
 open(f'profiles/{tag}_launch_list.csv', 'w').write("us,kernel\n" + "\n".join(f"{v:.1f},\"{k}\"" for k, v in L[a:b]) + "\n")
 md = [f"# {tag}: every launch of ONE bench step (cfg2 G-A, B=16, C=150), `ncu --metrics gpu__time_duration.sum --clock-control none`", "",
