@@ -275,10 +275,11 @@ int lc2is_argmax_confmat_ragged(const float* d_low, int N, int C, int h, int w, 
                                 int64_t* d_confmat, int64_t* d_per_image, int64_t* d_pred,
                                 lc2is_stream_t stream);
 
-/* K2 (split form) and K3 in ONE warp-specialised kernel for the x16 geometry (what the whole-step entries run when
- * lc2is_ce_argmax_fused_supported): the taps are staged once per 16 groups, four warps of a CTA run the
- * cross-entropy strips (FP32-pipe bound), four the argmax rows (ALU / issue bound).  Same results as
- * lc2is_upsample_ce_packed followed by lc2is_argmax_confmat_lowres_packed (bilinear). */
+/* K2 (split form) and K3 in ONE persistent kernel of independent warps for the x16 geometry (k23_rc_kernel; what the
+ * whole-step entries run when lc2is_ce_argmax_fused_supported): per job of two groups one TMA box stages the taps, a row
+ * phase (lane = pixel row) does pass A of the cross-entropy and the running argmax in one sweep over the classes, a class
+ * phase (lane = class) the tap gradients by Horner sweeps.  Same results as lc2is_upsample_ce_packed followed by
+ * lc2is_argmax_confmat_lowres_packed (bilinear).  LC2IS_FUSED_V1=1 selects round 1's warp-specialised kernel. */
 int lc2is_ce_argmax_fused_supported(int C, int h, int w, int H, int W);
 int lc2is_ce_argmax_fused_packed(const float* d_low, const uint16_t* d_labels_packed,
                                  int B, int C, int h, int w, int H, int W,
