@@ -297,7 +297,7 @@ k3_low_fast_kernel(const K3LowParams P) {
     if (group_in && !exotic) {
         if constexpr (MODE == 0) {
             // bilinear; at the clamped borders both taps are the same cell, so any lambda is exact
-#pragma unroll 2
+#pragma unroll 8
             for (int c = 0; c < C; ++c) {
                 const float* p = st + (size_t)c * cs + o00;
                 const float a = p[0], b = p[1], cc = p[ncx], d = p[ncx + 1];
