@@ -273,20 +273,10 @@ k3_low_fast_kernel(const K3LowParams P) {
     const float ty0 = ((float)y0 + 0.5f) * rs - 0.5f - (float)ky;     // fractional source position of row 0
     const float tx0 = ((float)x0 + 0.5f) * rs - 0.5f - (float)kx;
 
-    // ---- non-finite taps?  (lanes of the group split the classes) -----------------------------------
-    // (bicubic only: the bilinear loop below detects them on the fly - a separate sweep over the taps was 11 % of the x4
-    // kernel's instructions)
+    // ---- non-finite taps are detected inside the class loops (a value that involves all taps of the group is folded into
+    // `poison`: 0 * inf = NaN); a separate sweep over the taps was 11 % of the x4 kernel's instructions.  A warp that saw
+    // one re-evaluates its groups with the exact per-pixel path below.
     bool exotic = false;
-    if (MODE != 0 && group_in) {
-        for (int c = u; c < C; c += LPG) {
-            const float* p = st + (size_t)c * cs + o00;
-#pragma unroll
-            for (int a = 0; a < NT; ++a)
-#pragma unroll
-                for (int b = 0; b < NT; ++b) exotic |= !(fabsf(p[a * ncx + b]) < INFINITY);
-        }
-    }
-    exotic = __any_sync(0xffffffffu, exotic);
 
     float best[16];
     int bidx[16];
@@ -337,7 +327,7 @@ k3_low_fast_kernel(const K3LowParams P) {
                     wxp[1][b] = make_float2(wx[2][b], wx[3][b]);
                 }
             }
-#pragma unroll 1
+#pragma unroll 2
             for (int c = 0; c < C; ++c) {
                 const float* p = st + (size_t)c * cs + o00;
                 float2 hr[4][2];                                 // horizontal result of tap row a, column pairs
@@ -352,6 +342,8 @@ k3_low_fast_kernel(const K3LowParams P) {
                         hr[a][jp] = ffma2(make_float2(t3, t3), wxp[jp][3], acc);
                     }
                 }
+                // (the cubic weights are never 0 at half-pixel offsets: every tap of the group reaches this sum)
+                poison = fmaf(0.f, (hr[0][0].x + hr[1][0].x) + (hr[2][0].x + hr[3][0].x), poison);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -366,9 +358,9 @@ k3_low_fast_kernel(const K3LowParams P) {
             }
         }
     }
-    if (MODE == 0) exotic = __any_sync(0xffffffffu, poison != poison);
+    exotic = __any_sync(0xffffffffu, poison != poison);
     if (group_in && exotic) {
-        // exact per-pixel path with the NaN / +inf rule (rare; for the bilinear kernel it replaces the results above)
+        // exact per-pixel path with the NaN / +inf rule (rare; it replaces the results above)
         ArgmaxState stt[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) am_init(stt[i]);
