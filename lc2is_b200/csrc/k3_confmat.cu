@@ -327,7 +327,7 @@ k3_low_fast_kernel(const K3LowParams P) {
                     wxp[1][b] = make_float2(wx[2][b], wx[3][b]);
                 }
             }
-#pragma unroll 2
+#pragma unroll 4
             for (int c = 0; c < C; ++c) {
                 const float* p = st + (size_t)c * cs + o00;
                 float2 hr[4][2];                                 // horizontal result of tap row a, column pairs
