@@ -252,7 +252,7 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int mt = tile / P.n_ntiles;
                 const int b = mt / P.tiles_per_img, ti = mt - b * P.tiles_per_img;
                 tc::mbar_wait(tempty + buf, bphase ^ 1);       // the epilogue of tile it-2 has read inv_s[buf]
-                float ss = 0.f;
+                float ss = 0.f, ss1 = 0.f;                     // two chains: the 64 dependent fma per k-block were the norm warps' pace
                 for (int kb = 0; kb < P.num_kb; ++kb) {
                     tc::mbar_wait(full + stage, phase);
                     const uint8_t* ar = smem + (size_t)stage * stage_bytes + row * 128;
@@ -265,14 +265,14 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const float lo = __uint_as_float(w[k] << 16), hi = __uint_as_float(w[k] & 0xffff0000u);
-                            ss = fmaf(lo, lo, ss); ss = fmaf(hi, hi, ss);
+                            ss = fmaf(lo, lo, ss); ss1 = fmaf(hi, hi, ss1);
                         }
                     }
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(empty + stage);
                     if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
-                const float inv = __frcp_rn(fmaxf(sqrtf(ss), 1e-12f));
+                const float inv = __frcp_rn(fmaxf(sqrtf(ss + ss1), 1e-12f));
                 inv_s[buf * 128 + row] = inv;
                 const int p = ti * K1_BM + row;
                 if (p < P.hw && P.inv_v) P.inv_v[(size_t)b * P.hw + p] = inv;
@@ -348,16 +348,43 @@ k1_logits_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     tc::mbar_wait(nfull + buf, bphase);
                     sc *= inv_s[buf * 128 + q * 32 + lane];
                 }
-                for (int col = 0; col < P.NB; col += 16) {
-                    if (n0 + col >= P.C) break;                 // warp-uniform
+                // A thread owns a pixel ROW in TMEM and the class planes are hw floats apart: a warp store writes 128
+                // contiguous bytes of one class plane.  Per class: one FMUL, one IMAD.WIDE (plane offset = constant x hw)
+                // and the store - the first version (class index, bound check and a 64-bit address product per store,
+                // one tcgen05.wait per 16 columns) spent 20 instructions per class and made this epilogue, not HBM, the
+                // bound of the kernel at 128 x 128 patches (profiles/r02_gb_k1_ncu.md).
+                const int ncols = P.C - n0 < P.NB ? P.C - n0 : P.NB;       // classes of this N tile (warp-uniform)
+                const unsigned hwu = (unsigned)P.hw;
+                float* pc = orow + (size_t)n0 * P.hw;
+                int col = 0;
+                for (; col + 32 <= ncols; col += 32) {
+                    uint32_t r[32];
+                    tc::tmem_ld32(taddr + col, r);
+                    tc::tmem_ld_wait();
+                    if (rvalid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            __stcs(pc + (unsigned long long)hwu * (unsigned)j, __uint_as_float(r[j]) * sc);
+                    }
+                    pc += 32ull * hwu;
+                }
+                for (; col < ncols; col += 16) {
                     uint32_t r[16];
                     tc::tmem_ld16(taddr + col, r);
                     tc::tmem_ld_wait();
+                    const int nv = ncols - col;                             // 1..16 or more (warp-uniform)
+                    if (rvalid) {
+                        if (nv >= 16) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int c = n0 + col + j;
-                        if (rvalid && c < P.C) __stcs(orow + (size_t)c * P.hw, __uint_as_float(r[j]) * sc);
+                            for (int j = 0; j < 16; ++j)
+                                __stcs(pc + (unsigned long long)hwu * (unsigned)j, __uint_as_float(r[j]) * sc);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (j < nv) __stcs(pc + (unsigned long long)hwu * (unsigned)j, __uint_as_float(r[j]) * sc);
+                        }
                     }
+                    pc += 16ull * hwu;
                 }
             } else {
                 // row-major (C % 16 == 0 for this epilogue): this warp's 32 rows, staged for coalesced stores
