@@ -64,6 +64,8 @@ struct RCParams {
     unsigned* ctr;                   // {next job of the dynamic rounds, finished warps}: zero at launch, reset by the last warp
     unsigned cells_bytes;            // shared memory per warp: TMA landing zone (later the U tile), multiple of 128
     unsigned quads_bytes;            // shared memory per warp: quads + mbarrier
+    unsigned stagger_ns;             // start delay unit: warp w of a CTA starts ((w >> stagger_shift) & 3) units late (0 = off)
+    unsigned stagger_shift;          // 0: the four schedulers of the SM against each other; 2: the four warps of a scheduler
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int x, int y, int z,
@@ -74,6 +76,10 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+#ifdef RC_STAMPS
+__device__ unsigned long long rc_stamps[148 * 16 * 16];
+__device__ __forceinline__ unsigned long long rc_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 struct RCJob {
     int n, ky, kx0;                  // image, group row (-1..h-1), first group column (2*jx - 1)
 };
@@ -163,6 +169,15 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
         rc_stage(P, &tm, cells, bar, J0, lane);
     }
 
+#ifdef RC_STAMPS
+    unsigned long long* stp = rc_stamps + (size_t)(blockIdx.x * 16 + warp) * 16;
+    int sti = 1;
+    if (lane == 0) stp[0] = rc_now();
+#endif
+    // De-phasing: all warps start in step and stay nearly in step (equal jobs), so the SM's 16 warps are in the FMA-bound row
+    // phase together and in the LDS-bound class phase together - the first job takes 73 us against 56 us once the warps have
+    // drifted apart (tools/k23_timeline.py).  A staggered start trades a few us of idle warps for mixed phases from the start.
+    if (P.stagger_ns) __nanosleep((unsigned)((warp >> P.stagger_shift) & 3) * P.stagger_ns);
     // row-phase lane mapping
     const int gi = lane >> 4, i = lane & 15;
     const float ly = ((float)i + 0.5f) * RS;
@@ -577,6 +592,9 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
         }
         __syncwarp();                                       // U tile complete
 
+#ifdef RC_STAMPS
+        if (lane == 0 && sti < 15) stp[sti++] = rc_now();
+#endif
         // ================= class phase (lane = class): tap gradients by Horner sweeps ==============================
         if (!slow && P.grad != nullptr && (any0 || any1)) {
             float* gimg = P.grad + (size_t)n * C * plane;
@@ -692,12 +710,18 @@ k23_rc_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ RC
             if (kb < C) sweep(std::integral_constant<int, 1>{}, kb);
         }
         __syncwarp();                                       // quads / U free for the next job
+#ifdef RC_STAMPS
+        if (lane == 0 && sti < 15) stp[sti++] = rc_now();
+#endif
         // ---- the box of the warp's next job (its latency is covered by the SM's other warps) -----------------------
         if (next_job < njobs) {
             const RCJob Jn = rc_decode(P, next_job);
             rc_stage(P, &tm, cells, bar, Jn, lane);
         }
     }
+#ifdef RC_STAMPS
+    if (lane == 0) stp[15] = (unsigned long long)sti;
+#endif
     retire();
 }
 
@@ -769,6 +793,12 @@ int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, in
     if (P.njobs > 0x3fffffffLL) return fail(LC2IS_ERR_SHAPE, "too many groups for one launch%s");
     P.cells_bytes = (unsigned)rc_cells_bytes(C);
     P.quads_bytes = (unsigned)rc_quads_bytes(C);
+    // staggered start (see the kernel): on when a warp gets three jobs or more - with fewer the idle time is not won back;
+    // LC2IS_RC_STAGGER=<ns per step> / LC2IS_RC_STAGGER_SHIFT override (0 ns = off)
+    static const int stagger_env = getenv("LC2IS_RC_STAGGER") ? atoi(getenv("LC2IS_RC_STAGGER")) : -1;
+    static const int stagger_shift_env = getenv("LC2IS_RC_STAGGER_SHIFT") ? atoi(getenv("LC2IS_RC_STAGGER_SHIFT")) : 2;
+    P.stagger_ns = stagger_env >= 0 ? (unsigned)stagger_env : (P.njobs >= 3LL * sm_count() * nw ? 8000u : 0u);
+    P.stagger_shift = (unsigned)stagger_shift_env;
     P.use_tma = (C <= 256 && w % 4 == 0 && ((uintptr_t)d_low % 16) == 0 && !getenv("LC2IS_RC_NO_TMA")) ? 1 : 0;
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
@@ -798,4 +828,9 @@ int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, in
     return 0;
 }
 
+#ifdef RC_STAMPS
+extern "C" int lc2is_debug_stamps(unsigned long long* h_out) {
+    return (int)cudaMemcpyFromSymbol(h_out, rc_stamps, sizeof(unsigned long long) * 148 * 16 * 16);
+}
+#endif
 }  // namespace lc2is
