@@ -798,7 +798,7 @@ int launch_k23_rc(const float* d_low, const uint16_t* d_labels_packed, int B, in
     static const int stagger_env = getenv("LC2IS_RC_STAGGER") ? atoi(getenv("LC2IS_RC_STAGGER")) : -1;
     static const int stagger_shift_env = getenv("LC2IS_RC_STAGGER_SHIFT") ? atoi(getenv("LC2IS_RC_STAGGER_SHIFT")) : 2;
     P.stagger_ns = stagger_env >= 0 ? (unsigned)stagger_env : (P.njobs >= 3LL * sm_count() * nw ? 8000u : 0u);
-    P.stagger_shift = (unsigned)stagger_shift_env;
+    P.stagger_shift = stagger_shift_env == 0 ? 0u : 2u;
     P.use_tma = (C <= 256 && w % 4 == 0 && ((uintptr_t)d_low % 16) == 0 && !getenv("LC2IS_RC_NO_TMA")) ? 1 : 0;
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
